@@ -1,0 +1,157 @@
+/* medfusion_b200 — C ABI of the B200-native Medfusion sampling hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every
+ * pointer argument named `d_*` is a DEVICE pointer owned by the caller (PyTorch's caching allocator
+ * in the shipped Python host layer); the library borrows it for the duration of the stream-ordered
+ * call.  Weights are copied / re-laid-out once into library-owned device memory by *_set_param.
+ * All functions return 0 on success; on failure a thread-local message is available from
+ * mf_last_error().  Nothing in the forward/decode/step calls allocates or synchronises, so they
+ * can be captured into a CUDA graph after one warm-up call for the same (B, H, W, workspace).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   mf_unet_forward   <- medical_diffusion/models/estimators/unet2.py:222-269        UNet.forward
+ *   mf_vae_decode     <- medical_diffusion/models/embedders/latent_embedders.py:764-769  VAE.decode
+ *   mf_sched_step     <- medical_diffusion/models/noise_schedulers/gaussian_scheduler.py:80-124
+ *                        (estimate_x_t_prior_from_x_T / _x_0, estimate_x_0, estimate_mean_t,
+ *                        estimate_variance_t) + diffusion_pipeline.py:240-244 (CFG combine)
+ *                        + diffusion_pipeline.py:297-304 (DDIM-form re-noise)
+ *   mf_op_*           <- the individual torch ops those functions are made of (test surface)
+ */
+#ifndef MEDFUSION_B200_H_
+#define MEDFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mf_stream_t; /* cudaStream_t */
+
+#define MF_MAX_LEVELS 8
+
+/* -------------------------------------------------------------------------------------------------
+ * Errors / build info
+ * ---------------------------------------------------------------------------------------------- */
+const char* mf_last_error(void);
+int mf_abi_version(void);
+
+/* -------------------------------------------------------------------------------------------------
+ * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block
+ * configuration the hot path uses)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int in_ch;                       /* unet2.py:18  in_ch (x2 if self-conditioning; not supported) */
+  int out_ch;                      /* unet2.py:19  out_ch */
+  int depth;                       /* len(hid_chs) */
+  int hid_chs[MF_MAX_LEVELS];      /* unet2.py:21 */
+  int kernel_sizes[MF_MAX_LEVELS]; /* unet2.py:22 */
+  int strides[MF_MAX_LEVELS];      /* unet2.py:23 (last stride ignored, like the reference) */
+  int num_res_blocks;              /* unet2.py:37 */
+  int emb_dim;                     /* TimeEmbbeding emb_dim (time_embedder.py:54); 0 = no time embedder */
+  int pos_emb_dim;                 /* sinusoidal width (emb_dim // 4 by default, time_embedder.py:62) */
+  int num_classes;                 /* LabelEmbedder num_classes (cond_embedders.py:6); 0 = none */
+  int norm_groups;                 /* GroupNorm groups (32) */
+  int attention[MF_MAX_LEVELS];    /* 0 = 'none' (only value supported in this round) */
+} mf_unet_config;
+
+typedef struct mf_unet mf_unet;
+
+int mf_unet_create(const mf_unet_config* cfg, mf_unet** out);
+void mf_unet_destroy(mf_unet* h);
+/* Enumerate the state_dict entries the engine expects (same names/shapes as the reference module). */
+int mf_unet_param_count(const mf_unet* h);
+const char* mf_unet_param_name(const mf_unet* h, int i);
+int mf_unet_param_shape(const mf_unet* h, int i, int64_t shape[4], int* ndim);
+/* Copy one fp32 parameter from a device buffer (contiguous, reference layout: conv OIHW, linear [out,in]). */
+int mf_unet_set_param(mf_unet* h, const char* name, const float* d_data, const int64_t* shape, int ndim,
+                      mf_stream_t stream);
+/* Sinusoidal frequency table exp(-ln(max_period) * k / (half - shift)), k < pos_emb_dim/2, computed by
+ * the host exactly like time_embedder.py:17-18 so sin/cos arguments match the reference bit for bit. */
+int mf_unet_set_time_freqs(mf_unet* h, const float* d_freqs, int n, mf_stream_t stream);
+size_t mf_unet_workspace_bytes(mf_unet* h, int B, int H, int W);
+/* y[B,out_ch,H,W] = UNet(x_t[B,in_ch,H,W], t[B] (int64), cond[B] (int64) or NULL).  NCHW fp32. */
+int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
+                    int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream);
+/* Path census of the last prepared plan: number of convs on the tcgen05 path / on the SIMT path. */
+int mf_unet_plan_info(const mf_unet* h, int* n_tc_convs, int* n_simt_convs, int* n_launches);
+
+/* -------------------------------------------------------------------------------------------------
+ * VAE decoder (latent_embedders.py:718-743 ctor, :764-769 decode)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int emb_channels;              /* latent channels (8) */
+  int out_channels;              /* image channels (3) */
+  int depth;                     /* len(hid_chs) */
+  int hid_chs[MF_MAX_LEVELS];    /* [64,128,256,512] */
+  int strides[MF_MAX_LEVELS];    /* [1,2,2,2]; levels 1.. must be 2 (nearest x2 + conv3x3) */
+  int norm_groups;               /* 8 */
+} mf_vae_config;
+
+typedef struct mf_vae mf_vae;
+
+int mf_vae_create(const mf_vae_config* cfg, mf_vae** out);
+void mf_vae_destroy(mf_vae* h);
+int mf_vae_param_count(const mf_vae* h);
+const char* mf_vae_param_name(const mf_vae* h, int i);
+int mf_vae_param_shape(const mf_vae* h, int i, int64_t shape[4], int* ndim);
+int mf_vae_set_param(mf_vae* h, const char* name, const float* d_data, const int64_t* shape, int ndim,
+                     mf_stream_t stream);
+size_t mf_vae_workspace_bytes(mf_vae* h, int B, int H, int W);
+/* x[B,out_channels,H*2^(depth-1),W*2^(depth-1)] = decode(z[B,emb_channels,H,W]) */
+int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
+                  size_t workspace_bytes, mf_stream_t stream);
+int mf_vae_plan_info(const mf_vae* h, int* n_tc_convs, int* n_simt_convs, int* n_launches);
+
+/* -------------------------------------------------------------------------------------------------
+ * Scheduler step (all tensors [B, chw] fp32 contiguous; tables fp32[T] as registered by
+ * gaussian_scheduler.py:44-58; t int64[B]; t_next int64 scalar or NULL)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_variance;
+  const float* betas;
+  const float* alphas_cumprod;
+} mf_sched_tables;
+
+int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred,
+                  const float* d_pred_uncond /* NULL: no guidance */, float guidance_scale, const int64_t* d_t,
+                  const float* d_noise /* scheduler draw, NULL = 0 */, const int64_t* d_t_next /* NULL: no DDIM */,
+                  const float* d_noise_ddim, int objective_is_x0, int clip_x0, float* d_x_prior, float* d_x_0,
+                  float* d_x_T, float* d_x_next, int B, int chw, mf_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------
+ * Kernel-level ops (test / profiling surface; layouts: 0 = NCHW fp32, 1 = NHWC fp32, 2 = NHWC TF32 hi/lo planes)
+ * ---------------------------------------------------------------------------------------------- */
+int mf_op_pack_split(const float* d_x_nchw, float* d_out, int64_t plane, int N, int C, int H, int W, mf_stream_t s);
+int mf_op_unpack_nchw(const float* d_in, int64_t plane, int layout, float* d_out_nchw, int N, int C, int H, int W,
+                      mf_stream_t s);
+int mf_op_prep_weight_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
+int mf_op_prep_weight_simt(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
+int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
+/* stride-1 'same' conv on the tcgen05 path; src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL */
+int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
+                  int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
+                  int64_t out_plane, int out_layout, float* d_stats, mf_stream_t s);
+int mf_op_conv_tc_stats_chunks(int H, int W);
+int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
+                    const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,
+                    int64_t out_plane, int out_layout, mf_stream_t s);
+int mf_op_gn_partial(const float* d_raw, float* d_partial, int N, int HW, int C, mf_stream_t s);
+int mf_op_gn_finalize(const float* d_partial, float* d_mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
+                      mf_stream_t s);
+int mf_op_gn_apply(const float* d_raw, const float* d_mean_rstd, const float* d_gamma, const float* d_beta,
+                   const float* d_res, int64_t res_plane, int res_kind /* 0 none, 1 split, 2 raw */,
+                   const float* d_emb, int emb_stride, float* d_out, int64_t out_plane, int N, int HW, int C, int G,
+                   mf_stream_t s);
+int mf_op_upsample2x(const float* d_in, int64_t in_plane, float* d_out, int64_t out_plane, int N, int H, int W, int C,
+                     mf_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDFUSION_B200_H_ */

@@ -1,0 +1,116 @@
+"""ctypes binding of the C-ABI shared library (include/medfusion_b200.h).
+
+The library is the product: if it is missing or fails to load, importing any compute path raises —
+there is deliberately no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmedfusion_b200.so")
+MF_MAX_LEVELS = 8
+
+
+class MedfusionLibError(RuntimeError):
+    pass
+
+
+class UNetConfig(ctypes.Structure):
+    _fields_ = [
+        ("in_ch", c_int), ("out_ch", c_int), ("depth", c_int),
+        ("hid_chs", c_int * MF_MAX_LEVELS), ("kernel_sizes", c_int * MF_MAX_LEVELS),
+        ("strides", c_int * MF_MAX_LEVELS), ("num_res_blocks", c_int), ("emb_dim", c_int),
+        ("pos_emb_dim", c_int), ("num_classes", c_int), ("norm_groups", c_int),
+        ("attention", c_int * MF_MAX_LEVELS),
+    ]
+
+
+class VAEConfig(ctypes.Structure):
+    _fields_ = [
+        ("emb_channels", c_int), ("out_channels", c_int), ("depth", c_int),
+        ("hid_chs", c_int * MF_MAX_LEVELS), ("strides", c_int * MF_MAX_LEVELS), ("norm_groups", c_int),
+    ]
+
+
+class SchedTables(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+        "posterior_mean_coef2", "posterior_variance", "betas", "alphas_cumprod")]
+
+
+# name -> (restype, argtypes); every symbol declared in include/medfusion_b200.h
+_P = c_void_p
+SIGNATURES = {
+    "mf_last_error": (c_char_p, []),
+    "mf_abi_version": (c_int, []),
+    "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
+    "mf_unet_destroy": (None, [_P]),
+    "mf_unet_param_count": (c_int, [_P]),
+    "mf_unet_param_name": (c_char_p, [_P, c_int]),
+    "mf_unet_param_shape": (c_int, [_P, c_int, POINTER(c_int64), POINTER(c_int)]),
+    "mf_unet_set_param": (c_int, [_P, c_char_p, _P, POINTER(c_int64), c_int, _P]),
+    "mf_unet_set_time_freqs": (c_int, [_P, _P, c_int, _P]),
+    "mf_unet_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
+    "mf_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_unet_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mf_vae_create": (c_int, [POINTER(VAEConfig), POINTER(_P)]),
+    "mf_vae_destroy": (None, [_P]),
+    "mf_vae_param_count": (c_int, [_P]),
+    "mf_vae_param_name": (c_char_p, [_P, c_int]),
+    "mf_vae_param_shape": (c_int, [_P, c_int, POINTER(c_int64), POINTER(c_int)]),
+    "mf_vae_set_param": (c_int, [_P, c_char_p, _P, POINTER(c_int64), c_int, _P]),
+    "mf_vae_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
+    "mf_vae_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_vae_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mf_sched_step": (c_int, [POINTER(SchedTables), _P, _P, _P, c_float, _P, _P, _P, _P, c_int, c_int,
+                              _P, _P, _P, _P, c_int, c_int, _P]),
+    "mf_op_pack_split": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_unpack_nchw": (c_int, [_P, c_int64, c_int, _P, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_prep_weight_tc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_prep_weight_simt": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_conv_tc_supported": (c_int, [c_int] * 8),
+    "mf_op_conv_tc_stats_chunks": (c_int, [c_int, c_int]),
+    "mf_op_conv_tc": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P,
+                              _P, c_int64, c_int, _P, _P]),
+    "mf_op_conv_simt": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P,
+                                c_int64, c_int, _P]),
+    "mf_op_gn_partial": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "mf_op_gn_finalize": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
+    "mf_op_gn_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, c_int, _P, c_int64, c_int, c_int, c_int,
+                               c_int, _P]),
+    "mf_op_upsample2x": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libmedfusion_b200.so (built by `__graft_entry__.build()` / csrc/Makefile). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MedfusionLibError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no fallback path.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise MedfusionLibError(f"failed to load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().mf_last_error()
+        msg = msg.decode() if msg else "unknown error"
+        exc = ValueError if rc == 2 else RuntimeError
+        raise exc(f"medfusion_b200 {what} failed (status {rc}): {msg}")

@@ -1,0 +1,590 @@
+// C ABI (include/medfusion_b200.h): UNet / VAE-decoder engines built on EngineBase, scheduler step,
+// and the kernel-level test surface.
+#include "../../include/medfusion_b200.h"
+
+#include <algorithm>
+
+#include "mf_engine.cuh"
+
+using namespace mf;
+
+// =================================================================================================
+// UNet  (reference: medical_diffusion/models/estimators/unet2.py)
+// =================================================================================================
+struct mf_unet : public EngineBase {
+  mf_unet_config cfg{};
+  // layers in reference module order
+  ConvLayer in_conv;
+  struct EncEntry { bool is_down = false; ResBlockLayer rb; ConvLayer down; };
+  std::vector<std::unique_ptr<EncEntry>> enc;          // in_blocks
+  ResBlockLayer mid0, mid2;                            // middle_block.{0,2}
+  struct DecEntry { ResBlockLayer rb; bool has_up = false; ConvLayer up; int up_factor = 1; };
+  std::vector<std::unique_ptr<DecEntry>> dec;          // out_blocks (module index order)
+  ConvLayer outc;
+  Param *t_w1 = nullptr, *t_b1 = nullptr, *t_w2 = nullptr, *t_b2 = nullptr, *cond_table = nullptr;
+  DevBuf freqs;
+  bool freqs_set = false;
+  // fused local-embedder matrix [emb_total][emb_dim] + bias [emb_total]
+  int emb_total = 0;
+  DevBuf loc_w, loc_b;
+  int loc_version = -1;
+  std::vector<ResBlockLayer*> all_rb;
+  // per-call IO (read by the launch closures)
+  const float* io_x = nullptr;
+  const long long* io_t = nullptr;
+  const long long* io_cond = nullptr;
+  float* io_y = nullptr;
+  int n_launches = 0;
+
+  int init(const mf_unet_config& c);
+  int build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s);
+  int ensure_local_embedder(cudaStream_t s);
+};
+
+int mf_unet::init(const mf_unet_config& c) {
+  cfg = c;
+  MF_REQUIRE(c.depth >= 2 && c.depth <= MF_MAX_LEVELS, "depth must be in [2, 8]");
+  MF_REQUIRE(c.num_res_blocks >= 1, "num_res_blocks >= 1");
+  for (int i = 0; i < c.depth; ++i) MF_REQUIRE(c.attention[i] == 0, "attention != 'none' is not built in this round");
+  const int E = c.emb_dim;
+  if (E > 0) {
+    MF_REQUIRE(c.pos_emb_dim > 0 && c.pos_emb_dim % 64 == 0, "pos_emb_dim must be a multiple of 64");
+    t_w1 = add_param("time_embedder.time_emb.1.weight", {E, c.pos_emb_dim});
+    t_b1 = add_param("time_embedder.time_emb.1.bias", {E});
+    t_w2 = add_param("time_embedder.time_emb.3.weight", {E, E});
+    t_b2 = add_param("time_embedder.time_emb.3.bias", {E});
+    if (c.num_classes > 0) cond_table = add_param("cond_embedder.embedding.weight", {c.num_classes, E});
+  }
+  const int* hid = c.hid_chs;
+  init_conv(*this, in_conv, "in_conv.conv", hid[0], c.in_ch, c.kernel_sizes[0], c.strides[0]);
+  // encoder (unet2.py:70-114)
+  for (int i = 1; i < c.depth; ++i) {
+    for (int k = 0; k < c.num_res_blocks; ++k) {
+      enc.emplace_back(new EncEntry());
+      const std::string pre = "in_blocks." + std::to_string(enc.size() - 1) + ".0";
+      init_resblock(*this, enc.back()->rb, pre, hid[k == 0 ? i - 1 : i], hid[i], c.kernel_sizes[i], E);
+      all_rb.push_back(&enc.back()->rb);
+    }
+    if (i < c.depth - 1) {
+      enc.emplace_back(new EncEntry());
+      enc.back()->is_down = true;
+      init_conv(*this, enc.back()->down, "in_blocks." + std::to_string(enc.size() - 1) + ".down_op", hid[i], hid[i],
+                c.kernel_sizes[i], c.strides[i]);
+    }
+  }
+  // middle (unet2.py:117-153)
+  init_resblock(*this, mid0, "middle_block.0", hid[c.depth - 1], hid[c.depth - 1], c.kernel_sizes[c.depth - 1], E);
+  init_resblock(*this, mid2, "middle_block.2", hid[c.depth - 1], hid[c.depth - 1], c.kernel_sizes[c.depth - 1], E);
+  all_rb.push_back(&mid0);
+  all_rb.push_back(&mid2);
+  // decoder (unet2.py:158-206)
+  for (int i = 1; i < c.depth; ++i) {
+    for (int k = 0; k <= c.num_res_blocks; ++k) {
+      dec.emplace_back(new DecEntry());
+      DecEntry& d = *dec.back();
+      const int oc = hid[k == 0 ? i - 1 : i];
+      const std::string pre = "out_blocks." + std::to_string(dec.size() - 1);
+      init_resblock(*this, d.rb, pre + ".0", hid[i] + oc, oc, c.kernel_sizes[i], E);
+      all_rb.push_back(&d.rb);
+      if (i > 1 && k == 0) {
+        d.has_up = true;
+        d.up_factor = c.strides[i];
+        MF_REQUIRE(d.up_factor == 1 || d.up_factor == 2, "BasicUp supports stride 1 or 2");
+        init_conv(*this, d.up, pre + ".2.up_op", oc, oc, 3, 1);
+      }
+    }
+  }
+  init_conv(*this, outc, "outc.conv.conv", c.out_ch, hid[0], 1, 1);
+  // embedding offsets
+  emb_total = 0;
+  if (E > 0)
+    for (ResBlockLayer* rb : all_rb) {
+      rb->emb_offset = emb_total;
+      emb_total += rb->Cout;
+    }
+  return 0;
+}
+
+int mf_unet::ensure_local_embedder(cudaStream_t s) {
+  if (cfg.emb_dim <= 0 || loc_version == version) return 0;
+  const int E = cfg.emb_dim;
+  if (loc_w.alloc(static_cast<size_t>(emb_total) * E) || loc_b.alloc(emb_total)) return 1;
+  for (ResBlockLayer* rb : all_rb) {
+    MF_CUDA_OK(cudaMemcpyAsync(loc_w.p + static_cast<size_t>(rb->emb_offset) * E, rb->emb_w->data.p,
+                               static_cast<size_t>(rb->Cout) * E * 4, cudaMemcpyDeviceToDevice, s));
+    MF_CUDA_OK(cudaMemcpyAsync(loc_b.p + rb->emb_offset, rb->emb_b->data.p, static_cast<size_t>(rb->Cout) * 4,
+                               cudaMemcpyDeviceToDevice, s));
+  }
+  loc_version = version;
+  return 0;
+}
+
+// Build the launch plan for UNet.forward (unet2.py:222-269) at a fixed (B, H, W, workspace).
+int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
+  dry = dry_run;
+  base = ws;
+  prep_stream = s;
+  arena = Arena();
+  ops.clear();
+  tc_plans.clear();
+  n_tc = n_simt = 0;
+  const int E = cfg.emb_dim, G = cfg.norm_groups;
+  int rc = 0;
+  if (!dry) {
+    rc = check_all_set();
+    if (rc) return rc;
+    MF_REQUIRE(E <= 0 || freqs_set, "time frequency table not set (mf_unet_set_time_freqs)");
+    rc = ensure_local_embedder(s);
+    if (rc) return rc;
+  }
+
+  // ---- embeddings (time_embedder.py:67-75, cond_embedders.py:18-23, conv_blocks.py:16-18, :350)
+  Tens embT;
+  const Tens* embTp = nullptr;
+  if (E > 0) {
+    Tens h1 = new_floats(static_cast<size_t>(B) * E);
+    Tens emb = new_floats(static_cast<size_t>(B) * E);
+    Tens semb = new_floats(static_cast<size_t>(B) * E);
+    embT = new_floats(static_cast<size_t>(B) * emb_total);
+    embTp = &embT;
+    if (!dry) {
+      LinearDesc l1{};
+      l1.in_mode = 1; l1.freqs = freqs.p; l1.W = t_w1->data.p; l1.bias = t_b1->data.p;
+      l1.out = h1.ptr; l1.post = 1; l1.B = B; l1.J = E; l1.K = cfg.pos_emb_dim;
+      ops.push_back([this, l1](cudaStream_t st) {
+        LinearDesc d = l1;
+        d.t = io_t;
+        return linear_small(d, st);
+      });
+      LinearDesc l2{};
+      l2.in_mode = 0; l2.in = h1.ptr; l2.W = t_w2->data.p; l2.bias = t_b2->data.p;
+      l2.out = emb.ptr; l2.out2 = semb.ptr; l2.post = 0; l2.B = B; l2.J = E; l2.K = E;
+      const float* table = cond_table ? cond_table->data.p : nullptr;
+      ops.push_back([this, l2, table](cudaStream_t st) {
+        LinearDesc d = l2;
+        if (io_cond != nullptr && table != nullptr) {
+          d.add_table = table;
+          d.add_idx = io_cond;
+        }
+        return linear_small(d, st);
+      });
+      LinearDesc l3{};
+      l3.in_mode = 0; l3.in = semb.ptr; l3.W = loc_w.p; l3.bias = loc_b.p;
+      l3.out = embT.ptr; l3.post = 0; l3.B = B; l3.J = emb_total; l3.K = E;
+      ops.push_back([l3](cudaStream_t st) { return linear_small(l3, st); });
+    }
+    free_tensor(h1);
+    free_tensor(emb);
+    free_tensor(semb);
+  }
+
+  // ---- encoder
+  const int pad0 = cfg.kernel_sizes[0] / 2;
+  int h = (H + 2 * pad0 - cfg.kernel_sizes[0]) / cfg.strides[0] + 1;
+  int w = (W + 2 * pad0 - cfg.kernel_sizes[0]) / cfg.strides[0] + 1;
+  std::vector<Tens> skips;
+  Tens x0 = new_tensor(B, h, w, cfg.hid_chs[0], kNHWCSplit);
+  rc = add_conv_nchw_in(in_conv, &io_x, B, cfg.in_ch, H, W, x0, nullptr, nullptr);
+  if (rc) return rc;
+  skips.push_back(x0);
+  for (auto& e : enc) {
+    const Tens& cur = skips.back();
+    Tens nxt;
+    if (e->is_down) {
+      const int k = e->down.k, st = e->down.stride, pd = k / 2;
+      nxt = new_tensor(B, (cur.H + 2 * pd - k) / st + 1, (cur.W + 2 * pd - k) / st + 1, e->down.Cout, kNHWCSplit);
+      rc = add_conv(e->down, cur, nullptr, nxt, nullptr, nullptr);
+    } else {
+      rc = add_resblock(e->rb, G, cur, nullptr, embTp, emb_total, &nxt);
+    }
+    if (rc) return rc;
+    skips.push_back(nxt);
+  }
+  // ---- middle
+  Tens hcur, tmp;
+  rc = add_resblock(mid0, G, skips.back(), nullptr, embTp, emb_total, &tmp);
+  if (rc) return rc;
+  rc = add_resblock(mid2, G, tmp, nullptr, embTp, emb_total, &hcur);
+  if (rc) return rc;
+  free_tensor(tmp);
+  // ---- decoder: h = cat([h, skip]) -> out_blocks[i-1]  (unet2.py:258-264)
+  for (int i = static_cast<int>(dec.size()); i >= 1; --i) {
+    DecEntry& d = *dec[i - 1];
+    Tens skip = skips.back();
+    skips.pop_back();
+    Tens o;
+    rc = add_resblock(d.rb, G, hcur, &skip, embTp, emb_total, &o);
+    if (rc) return rc;
+    free_tensor(hcur);
+    free_tensor(skip);
+    if (d.has_up) {
+      // BasicUp: nearest x2 then conv3x3 (conv_blocks.py:121-131)
+      Tens src = o;
+      if (d.up_factor == 2) {
+        Tens up = new_tensor(B, o.H * 2, o.W * 2, o.C, kNHWCSplit);
+        if (!dry) {
+          const float* ip = o.ptr; float* op = up.ptr;
+          const long long ipl = o.plane, opl = up.plane;
+          const int oh = o.H, ow = o.W, oc = o.C;
+          ops.push_back([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
+            return upsample2x_split(ip, ipl, op, opl, B, oh, ow, oc, st);
+          });
+        }
+        free_tensor(o);
+        src = up;
+      }
+      Tens u = new_tensor(B, src.H, src.W, d.up.Cout, kNHWCSplit);
+      rc = add_conv(d.up, src, nullptr, u, nullptr, nullptr);
+      if (rc) return rc;
+      free_tensor(src);
+      o = u;
+    }
+    hcur = o;
+  }
+  // ---- head (unet2.py:267)
+  rc = add_conv_nchw_out(outc, hcur, &io_y);
+  if (rc) return rc;
+  free_tensor(hcur);
+  if (E > 0) free_tensor(embT);
+  n_launches = static_cast<int>(ops.size());
+  return 0;
+}
+
+// =================================================================================================
+// VAE decoder (reference: latent_embedders.py:718-743, :764-769; conv_blocks.py:444-528 UpBlock)
+// =================================================================================================
+struct mf_vae : public EngineBase {
+  mf_vae_config cfg{};
+  ResBlockLayer inc_dec;
+  struct Up { ConvLayer up; ResBlockLayer rb; int factor = 2; };
+  std::vector<std::unique_ptr<Up>> decoders;  // index i == decoders.{i}
+  ConvLayer outc;
+  const float* io_z = nullptr;
+  float* io_x = nullptr;
+  int n_launches = 0;
+
+  int init(const mf_vae_config& c);
+  int build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s);
+};
+
+int mf_vae::init(const mf_vae_config& c) {
+  cfg = c;
+  MF_REQUIRE(c.depth >= 1 && c.depth <= MF_MAX_LEVELS, "depth must be in [1, 8]");
+  init_resblock(*this, inc_dec, "inc_dec", c.emb_channels, c.hid_chs[c.depth - 1], 3, 0);
+  for (int i = 0; i < c.depth - 1; ++i) {
+    decoders.emplace_back(new Up());
+    Up& u = *decoders.back();
+    u.factor = c.strides[i + 1];
+    MF_REQUIRE(u.factor == 2, "VAE decoder levels must upsample by 2");
+    const std::string pre = "decoders." + std::to_string(i);
+    init_conv(*this, u.up, pre + ".up_op.up_op", c.hid_chs[i], c.hid_chs[i + 1], 3, 1);
+    init_resblock(*this, u.rb, pre + ".conv_block", c.hid_chs[i], c.hid_chs[i], 3, 0);
+  }
+  init_conv(*this, outc, "outc.conv", c.out_channels, c.hid_chs[0], 1, 1);
+  return 0;
+}
+
+int mf_vae::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
+  dry = dry_run;
+  base = ws;
+  prep_stream = s;
+  arena = Arena();
+  ops.clear();
+  tc_plans.clear();
+  n_tc = n_simt = 0;
+  int rc = 0;
+  if (!dry) {
+    rc = check_all_set();
+    if (rc) return rc;
+  }
+  const int G = cfg.norm_groups;
+  const int Ctop = cfg.hid_chs[cfg.depth - 1];
+  // ---- inc_dec: UnetResBlock(emb_channels -> Ctop), stem convs read the NCHW latent directly
+  Tens raw = new_tensor(B, H, W, Ctop, kNHWCRaw);
+  Tens part = new_floats(static_cast<size_t>(B) * std::max(1, conv_tc_stats_chunks(H, W)) * (Ctop / 8) * 2);
+  int chunks = 1;
+  rc = add_conv_nchw_in(inc_dec.conv1, &io_z, B, cfg.emb_channels, H, W, raw, &part, &chunks);
+  if (rc) return rc;
+  Tens res_raw;
+  const Tens* res = nullptr;
+  MF_REQUIRE(inc_dec.has_res_conv, "inc_dec with emb_channels == hid_chs[-1] is not supported");
+  res_raw = new_tensor(B, H, W, Ctop, kNHWCRaw);
+  rc = add_conv_nchw_in(inc_dec.conv_res, &io_z, B, cfg.emb_channels, H, W, res_raw, nullptr, nullptr);
+  if (rc) return rc;
+  res = &res_raw;
+  Tens x1 = new_tensor(B, H, W, Ctop, kNHWCSplit);
+  rc = add_gn_apply(inc_dec.norm1, G, raw, part, chunks, res, nullptr, 0, x1);
+  if (rc) return rc;
+  free_tensor(res_raw);
+  rc = add_conv(inc_dec.conv2, x1, nullptr, raw, &part, &chunks);
+  if (rc) return rc;
+  Tens hcur = new_tensor(B, H, W, Ctop, kNHWCSplit);
+  rc = add_gn_apply(inc_dec.norm2, G, raw, part, chunks, &x1, nullptr, 0, hcur);
+  if (rc) return rc;
+  free_tensor(raw);
+  free_tensor(part);
+  free_tensor(x1);
+  // ---- decoders[depth-2 .. 0]: nearest x2 + conv3x3, then UnetResBlock
+  for (int i = cfg.depth - 2; i >= 0; --i) {
+    Up& u = *decoders[i];
+    Tens up = new_tensor(B, hcur.H * 2, hcur.W * 2, hcur.C, kNHWCSplit);
+    if (!dry) {
+      const float* ip = hcur.ptr; float* op = up.ptr;
+      const long long ipl = hcur.plane, opl = up.plane;
+      const int oh = hcur.H, ow = hcur.W, oc = hcur.C;
+      ops.push_back([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
+        return upsample2x_split(ip, ipl, op, opl, B, oh, ow, oc, st);
+      });
+    }
+    free_tensor(hcur);
+    Tens uo = new_tensor(B, up.H, up.W, u.up.Cout, kNHWCSplit);
+    rc = add_conv(u.up, up, nullptr, uo, nullptr, nullptr);
+    if (rc) return rc;
+    free_tensor(up);
+    Tens o;
+    rc = add_resblock(u.rb, G, uo, nullptr, nullptr, 0, &o);
+    if (rc) return rc;
+    free_tensor(uo);
+    hcur = o;
+  }
+  rc = add_conv_nchw_out(outc, hcur, &io_x);
+  if (rc) return rc;
+  free_tensor(hcur);
+  n_launches = static_cast<int>(ops.size());
+  return 0;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+template <class E>
+static int prepare_plan(E* h, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (h->key.B == B && h->key.H == H && h->key.W == W && h->key.base == ws && h->key.version == h->version) return 0;
+  // dry run for the size check
+  int rc = h->build(B, H, W, nullptr, true, s);
+  if (rc) return rc;
+  const size_t need = h->arena.peak;
+  if (ws_bytes < need) {
+    set_error("workspace too small: need " + std::to_string(need) + " bytes, got " + std::to_string(ws_bytes));
+    return 2;
+  }
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) {
+    set_error("workspace must be 1024-byte aligned");
+    return 2;
+  }
+  rc = h->build(B, H, W, static_cast<char*>(ws), false, s);
+  if (rc) {
+    h->key = typename E::PlanKey();
+    return rc;
+  }
+  h->key.B = B; h->key.H = H; h->key.W = W; h->key.base = ws; h->key.version = h->version;
+  return 0;
+}
+
+extern "C" {
+
+const char* mf_last_error(void) { return mf::get_error(); }
+int mf_abi_version(void) { return 1; }
+
+// ---- UNet ---------------------------------------------------------------------------------------
+int mf_unet_create(const mf_unet_config* cfg, mf_unet** out) {
+  if (!cfg || !out) { set_error("null argument"); return 2; }
+  std::unique_ptr<mf_unet> h(new mf_unet());
+  int rc = h->init(*cfg);
+  if (rc) return rc;
+  *out = h.release();
+  return 0;
+}
+void mf_unet_destroy(mf_unet* h) { delete h; }
+int mf_unet_param_count(const mf_unet* h) { return static_cast<int>(h->params.size()); }
+const char* mf_unet_param_name(const mf_unet* h, int i) {
+  return (i >= 0 && i < static_cast<int>(h->params.size())) ? h->params[i]->name.c_str() : nullptr;
+}
+int mf_unet_param_shape(const mf_unet* h, int i, int64_t shape[4], int* ndim) {
+  if (i < 0 || i >= static_cast<int>(h->params.size())) { set_error("param index out of range"); return 2; }
+  const auto& s = h->params[i]->shape;
+  *ndim = static_cast<int>(s.size());
+  for (size_t k = 0; k < s.size(); ++k) shape[k] = s[k];
+  return 0;
+}
+int mf_unet_set_param(mf_unet* h, const char* name, const float* d_data, const int64_t* shape, int ndim,
+                      mf_stream_t stream) {
+  return h->set_param(name, d_data, shape, ndim, static_cast<cudaStream_t>(stream));
+}
+int mf_unet_set_time_freqs(mf_unet* h, const float* d_freqs, int n, mf_stream_t stream) {
+  MF_REQUIRE(h->cfg.emb_dim > 0 && n == h->cfg.pos_emb_dim / 2, "frequency table must have pos_emb_dim/2 entries");
+  if (h->freqs.alloc(n)) return 1;
+  MF_CUDA_OK(cudaMemcpyAsync(h->freqs.p, d_freqs, n * sizeof(float), cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+  h->freqs_set = true;
+  ++h->version;
+  return 0;
+}
+size_t mf_unet_workspace_bytes(mf_unet* h, int B, int H, int W) {
+  const auto saved = h->key;
+  if (h->build(B, H, W, nullptr, true, nullptr)) return 0;
+  const size_t need = h->arena.peak;
+  h->key = typename mf_unet::PlanKey();  // the dry build clobbered the op list
+  (void)saved;
+  return need;
+}
+int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
+                    int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MF_REQUIRE(d_x_t && d_y && B > 0 && H > 0 && W > 0, "bad arguments");
+  MF_REQUIRE(h->cfg.emb_dim <= 0 || d_t != nullptr, "t is required when the UNet has a time embedder");
+  int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_x = d_x_t;
+  h->io_t = reinterpret_cast<const long long*>(d_t);
+  h->io_cond = reinterpret_cast<const long long*>(d_cond);
+  h->io_y = d_y;
+  return h->run(s);
+}
+int mf_unet_plan_info(const mf_unet* h, int* n_tc_convs, int* n_simt_convs, int* n_launches) {
+  if (n_tc_convs) *n_tc_convs = h->n_tc;
+  if (n_simt_convs) *n_simt_convs = h->n_simt;
+  if (n_launches) *n_launches = h->n_launches;
+  return 0;
+}
+
+// ---- VAE ----------------------------------------------------------------------------------------
+int mf_vae_create(const mf_vae_config* cfg, mf_vae** out) {
+  if (!cfg || !out) { set_error("null argument"); return 2; }
+  std::unique_ptr<mf_vae> h(new mf_vae());
+  int rc = h->init(*cfg);
+  if (rc) return rc;
+  *out = h.release();
+  return 0;
+}
+void mf_vae_destroy(mf_vae* h) { delete h; }
+int mf_vae_param_count(const mf_vae* h) { return static_cast<int>(h->params.size()); }
+const char* mf_vae_param_name(const mf_vae* h, int i) {
+  return (i >= 0 && i < static_cast<int>(h->params.size())) ? h->params[i]->name.c_str() : nullptr;
+}
+int mf_vae_param_shape(const mf_vae* h, int i, int64_t shape[4], int* ndim) {
+  if (i < 0 || i >= static_cast<int>(h->params.size())) { set_error("param index out of range"); return 2; }
+  const auto& s = h->params[i]->shape;
+  *ndim = static_cast<int>(s.size());
+  for (size_t k = 0; k < s.size(); ++k) shape[k] = s[k];
+  return 0;
+}
+int mf_vae_set_param(mf_vae* h, const char* name, const float* d_data, const int64_t* shape, int ndim,
+                     mf_stream_t stream) {
+  return h->set_param(name, d_data, shape, ndim, static_cast<cudaStream_t>(stream));
+}
+size_t mf_vae_workspace_bytes(mf_vae* h, int B, int H, int W) {
+  if (h->build(B, H, W, nullptr, true, nullptr)) return 0;
+  const size_t need = h->arena.peak;
+  h->key = typename mf_vae::PlanKey();
+  return need;
+}
+int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
+                  size_t workspace_bytes, mf_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MF_REQUIRE(d_z && d_x && B > 0 && H > 0 && W > 0, "bad arguments");
+  int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_z = d_z;
+  h->io_x = d_x;
+  return h->run(s);
+}
+int mf_vae_plan_info(const mf_vae* h, int* n_tc_convs, int* n_simt_convs, int* n_launches) {
+  if (n_tc_convs) *n_tc_convs = h->n_tc;
+  if (n_simt_convs) *n_simt_convs = h->n_simt;
+  if (n_launches) *n_launches = h->n_launches;
+  return 0;
+}
+
+// ---- scheduler ----------------------------------------------------------------------------------
+int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred, const float* d_pred_uncond,
+                  float guidance_scale, const int64_t* d_t, const float* d_noise, const int64_t* d_t_next,
+                  const float* d_noise_ddim, int objective_is_x0, int clip_x0, float* d_x_prior, float* d_x_0,
+                  float* d_x_T, float* d_x_next, int B, int chw, mf_stream_t stream) {
+  MF_REQUIRE(tables && d_x_t && d_pred && d_t, "bad arguments");
+  SchedStepDesc d{};
+  d.x_t = d_x_t; d.pred = d_pred; d.pred_uncond = d_pred_uncond; d.guidance = guidance_scale;
+  d.t = reinterpret_cast<const long long*>(d_t);
+  d.noise = d_noise;
+  d.t_next = reinterpret_cast<const long long*>(d_t_next);
+  d.noise2 = d_noise_ddim;
+  d.objective_x0 = objective_is_x0; d.clip_x0 = clip_x0;
+  d.x_prior = d_x_prior; d.x_0 = d_x_0; d.x_T = d_x_T; d.x_next = d_x_next;
+  d.B = B; d.CHW = chw;
+  d.tab.sqrt_recip_ac = tables->sqrt_recip_alphas_cumprod;
+  d.tab.sqrt_recipm1_ac = tables->sqrt_recipm1_alphas_cumprod;
+  d.tab.coef1 = tables->posterior_mean_coef1;
+  d.tab.coef2 = tables->posterior_mean_coef2;
+  d.tab.post_var = tables->posterior_variance;
+  d.tab.betas = tables->betas;
+  d.tab.alphas_cumprod = tables->alphas_cumprod;
+  return sched_step(d, static_cast<cudaStream_t>(stream));
+}
+
+// ---- kernel-level ops ---------------------------------------------------------------------------
+int mf_op_pack_split(const float* d_x_nchw, float* d_out, int64_t plane, int N, int C, int H, int W, mf_stream_t s) {
+  return pack_nchw_to_split(d_x_nchw, d_out, plane, N, C, H, W, static_cast<cudaStream_t>(s));
+}
+int mf_op_unpack_nchw(const float* d_in, int64_t plane, int layout, float* d_out_nchw, int N, int C, int H, int W,
+                      mf_stream_t s) {
+  return unpack_to_nchw(d_in, plane, layout, d_out_nchw, N, C, H, W, static_cast<cudaStream_t>(s));
+}
+int mf_op_prep_weight_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s) {
+  return prep_weight_tc(d_w_oihw, d_out, Cout, Cin, kh, kw, static_cast<cudaStream_t>(s));
+}
+int mf_op_prep_weight_simt(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s) {
+  return prep_weight_simt(d_w_oihw, d_out, Cout, Cin, kh, kw, static_cast<cudaStream_t>(s));
+}
+int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride) {
+  return conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride);
+}
+int mf_op_conv_tc_stats_chunks(int H, int W) { return conv_tc_stats_chunks(H, W); }
+int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
+                  int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
+                  int64_t out_plane, int out_layout, float* d_stats, mf_stream_t s) {
+  MF_REQUIRE(out_layout == kNHWCRaw || out_layout == kNHWCSplit, "conv_tc writes NHWC");
+  ConvTcDesc d{};
+  d.src0 = d_src0; d.src0_plane = src0_plane; d.C0 = C0;
+  d.src1 = d_src1; d.src1_plane = src1_plane; d.C1 = C1;
+  d.N = N; d.H = H; d.W = W;
+  d.w_planes = d_w_planes; d.Cout = Cout; d.ksize = ksize; d.bias = d_bias;
+  d.out = d_out; d.out_plane = out_plane; d.out_mode = out_layout == kNHWCSplit ? kOutSplit : kOutRaw;
+  d.stats = d_stats;
+  ConvTcPlan plan;
+  int rc = conv_tc_build(d, &plan);
+  if (rc) return rc;
+  return conv_tc_launch(plan, static_cast<cudaStream_t>(s));
+}
+int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
+                    const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,
+                    int64_t out_plane, int out_layout, mf_stream_t s) {
+  ConvSimtDesc d{};
+  d.in = d_in; d.in_plane = in_plane; d.in_layout = in_layout;
+  d.N = N; d.Cin = Cin; d.Hin = Hin; d.Win = Win;
+  d.w_kc = d_w_kc; d.bias = d_bias; d.Cout = Cout; d.ksize = ksize; d.stride = stride;
+  d.out = d_out; d.out_plane = out_plane; d.out_layout = out_layout;
+  return conv_simt(d, static_cast<cudaStream_t>(s));
+}
+int mf_op_gn_partial(const float* d_raw, float* d_partial, int N, int HW, int C, mf_stream_t s) {
+  return gn_partial_from_raw(d_raw, d_partial, N, HW, C, static_cast<cudaStream_t>(s));
+}
+int mf_op_gn_finalize(const float* d_partial, float* d_mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
+                      mf_stream_t s) {
+  return gn_finalize(d_partial, d_mean_rstd, N, chunks, C, G, HW, eps, static_cast<cudaStream_t>(s));
+}
+int mf_op_gn_apply(const float* d_raw, const float* d_mean_rstd, const float* d_gamma, const float* d_beta,
+                   const float* d_res, int64_t res_plane, int res_kind, const float* d_emb, int emb_stride,
+                   float* d_out, int64_t out_plane, int N, int HW, int C, int G, mf_stream_t s) {
+  GnApplyDesc d{};
+  d.raw = d_raw; d.mean_rstd = d_mean_rstd; d.gamma = d_gamma; d.beta = d_beta;
+  d.res = d_res; d.res_plane = res_plane; d.res_kind = res_kind;
+  d.emb = d_emb; d.emb_stride = emb_stride;
+  d.out = d_out; d.out_plane = out_plane; d.N = N; d.HW = HW; d.C = C; d.G = G;
+  return gn_apply(d, static_cast<cudaStream_t>(s));
+}
+int mf_op_upsample2x(const float* d_in, int64_t in_plane, float* d_out, int64_t out_plane, int N, int H, int W, int C,
+                     mf_stream_t s) {
+  return upsample2x_split(d_in, in_plane, d_out, out_plane, N, H, W, C, static_cast<cudaStream_t>(s));
+}
+
+}  // extern "C"

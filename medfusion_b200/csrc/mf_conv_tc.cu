@@ -1,0 +1,382 @@
+// See mf_conv_tc.cuh for the design.  sm_100a only: TMA + mbarrier pipeline + tcgen05.mma (TMEM accumulators).
+#include "mf_conv_tc.cuh"
+
+#include <mutex>
+
+namespace mf {
+
+// =================================================================================================
+// Device side
+// =================================================================================================
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int kABytes = kTcBlockM * 128;  // one 128-row x 128-byte plane tile
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int kAuxBytes = 2048;  // barriers, TMEM slot, stats scratch
+  static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // +1024: manual alignment slack
+  static_assert(4 * (BLOCK_N / 8) * 2 * 4 + 256 <= kAuxBytes, "aux region too small");
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* red = reinterpret_cast<float*>(aux + 256);  // [4 warps][BLOCK_N/8][2]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates -------------------------------------------------------------------------
+  const int mt = blockIdx.x;
+  const int nt = blockIdx.y;
+  const int tw = mt % p.tiles_w;
+  const int th = (mt / p.tiles_w) % p.tiles_h;
+  const int tn = mt / (p.tiles_w * p.tiles_h);
+  const int n0 = tn * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
+  const int cin = p.C0 + p.C1;
+  const int cblks = cin / kTcBlockK;
+  const int nkb = p.ntaps * cblks;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        const int tap = kb / cblks;
+        const int c = (kb - tap * cblks) * kTcBlockK;
+        const int x = w0 * p.in_stride + p.dx[tap];
+        const int y = h0 * p.in_stride + p.dy[tap];
+        if (c < p.C0) {
+          tma_load_5d(st, &map_a0, &full_bar[s], c, x, y, n0, 0);
+          tma_load_5d(st + Cfg::kABytes, &map_a0, &full_bar[s], c, x, y, n0, 1);
+        } else {
+          tma_load_5d(st, &map_a1, &full_bar[s], c - p.C0, x, y, n0, 0);
+          tma_load_5d(st + Cfg::kABytes, &map_a1, &full_bar[s], c - p.C0, x, y, n0, 1);
+        }
+        tma_load_3d(st + 2 * Cfg::kABytes, &map_w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 0);
+        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &map_w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM, BLOCK_N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint64_t a_hi = umma_smem_desc_sw128(st);
+        const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
+        const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
+        const uint64_t b_lo = umma_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < kTcBlockK / 8; ++k) {
+          // advance 8 tf32 = 32 bytes inside the 128-byte swizzled row: +2 in 16-byte units
+          const uint64_t koff = static_cast<uint64_t>(k * 2);
+          // small cross terms first, then the dominant hi*hi term
+          umma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+          umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 rows) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // accumulator row == pixel index inside the tile box
+    const int iw = row % p.bw;
+    const int ih = (row / p.bw) % p.bh;
+    const int in = row / (p.bw * p.bh);
+    const int n = n0 + in, h = h0 + ih, w = w0 + iw;
+    const bool valid = n < p.N;
+    const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+    float* orow = p.out + pix * p.Cout + nt * BLOCK_N;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+#pragma unroll 1
+    for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * 32, v);
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      }
+      if (p.stats != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = v[8 * g + j];
+            s += x;
+            ss = fmaf(x, x, ss);
+          }
+          if (!valid) { s = 0.f; ss = 0.f; }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            ss += __shfl_xor_sync(0xffffffffu, ss, off);
+          }
+          if (lane == 0) {
+            float* r = red + ((q * (BLOCK_N / 8)) + ch * 4 + g) * 2;
+            r[0] = s;
+            r[1] = ss;
+          }
+        }
+      }
+      if (valid) {
+        if (p.out_mode == kOutRaw) {
+          float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          float4* o4h = reinterpret_cast<float4*>(orow + ch * 32);
+          float4* o4l = reinterpret_cast<float4*>(orow + p.out_plane + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 hi, lo;
+            tf32_split(v[4 * j + 0], hi.x, lo.x);
+            tf32_split(v[4 * j + 1], hi.y, lo.y);
+            tf32_split(v[4 * j + 2], hi.z, lo.z);
+            tf32_split(v[4 * j + 3], hi.w, lo.w);
+            o4h[j] = hi;
+            o4l[j] = lo;
+          }
+        }
+      }
+    }
+
+    if (p.stats != nullptr) {
+      // combine the 4 epilogue warps (named barrier 1: only the 128 epilogue threads participate)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int te = threadIdx.x - 64;                 // 0..127
+      const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
+      const int wps = 4 / spt;                         // warps per sample
+      constexpr int G8 = BLOCK_N / 8;
+      if (te < G8 * spt) {
+        const int j = te / G8, i = te - j * G8;
+        // red[] is indexed by TMEM lane quarter q, i.e. by row/32
+        float s = 0.f, ss = 0.f;
+        for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
+          s += red[(wq * G8 + i) * 2 + 0];
+          ss += red[(wq * G8 + i) * 2 + 1];
+        }
+        const int ns = n0 + (spt > 1 ? j : 0);
+        const int chunk = (p.chunks_per_sample > 1) ? (th * p.tiles_w + tw) : 0;
+        if (ns < p.N) {
+          float* dst = p.stats + ((static_cast<long long>(ns) * p.chunks_per_sample + chunk) * (p.Cout / 8) +
+                                  nt * G8 + i) * 2;
+          dst[0] = s;
+          dst[1] = ss;
+        }
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, const cuuint32_t* estr) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return 3;
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 3;
+  }
+  return 0;
+}
+
+static bool pick_box(int H, int W, int* bw, int* bh, int* bn) {
+  if (W >= kTcBlockM) {
+    if (W % kTcBlockM) return false;
+    *bw = kTcBlockM; *bh = 1; *bn = 1;
+    return true;
+  }
+  if (W <= 0 || kTcBlockM % W) return false;
+  const int rows = kTcBlockM / W;
+  *bw = W;
+  if (H >= rows) {
+    if (H % rows) return false;
+    *bh = rows; *bn = 1;
+  } else {
+    if (rows % H) return false;
+    *bh = H; *bn = rows / H;
+  }
+  return true;
+}
+
+int conv_tc_stats_chunks(int H, int W) {
+  const int hw = H * W;
+  return hw >= kTcBlockM ? hw / kTcBlockM : 1;
+}
+
+int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride) {
+  int bw, bh, bn;
+  if (stride != 1) return 0;
+  if (ksize != 1 && ksize != 3) return 0;
+  if (C0 <= 0 || C0 % kTcBlockK || C1 % kTcBlockK || Cout % 64) return 0;
+  if (!pick_box(H, W, &bw, &bh, &bn)) return 0;
+  const int hw = H * W;
+  if (hw < 32 || (hw < kTcBlockM && kTcBlockM % hw) || (hw >= kTcBlockM && hw % kTcBlockM)) return 0;
+  (void)N;
+  return 1;
+}
+
+static int encode_act_map(CUtensorMap* m, const float* base, long long plane, int N, int H, int W, int C, int bw,
+                          int bh, int bn) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4,
+                           (cuuint64_t)plane * 4};
+  cuuint32_t box[5] = {(cuuint32_t)kTcBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return encode_map(m, base, 5, dims, strides, box, estr);
+}
+
+int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
+  MF_REQUIRE(conv_tc_supported(d.N, d.H, d.W, d.C0, d.C1, d.Cout, d.ksize, 1), "shape not supported by conv_tc");
+  MF_REQUIRE((reinterpret_cast<uintptr_t>(d.src0) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.w_planes) & 15) == 0,
+             "TMA sources must be 16-byte aligned");
+  ConvTcParams& p = plan->p;
+  p.N = d.N; p.H = d.H; p.W = d.W;
+  pick_box(d.H, d.W, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = d.W / p.bw;
+  p.tiles_h = d.H / p.bh;
+  p.tiles_n = (d.N + p.bn - 1) / p.bn;
+  p.C0 = d.C0; p.C1 = d.C1; p.Cout = d.Cout;
+  p.ntaps = d.ksize * d.ksize;
+  for (int t = 0; t < p.ntaps; ++t) {
+    p.dy[t] = t / d.ksize - d.ksize / 2;
+    p.dx[t] = t % d.ksize - d.ksize / 2;
+  }
+  p.in_stride = 1;
+  p.bias = d.bias;
+  p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
+  p.stats = d.stats;
+  p.chunks_per_sample = conv_tc_stats_chunks(d.H, d.W);
+  p.rows_per_sample = d.H * d.W >= kTcBlockM ? kTcBlockM : d.H * d.W;
+
+  plan->block_n = (d.Cout % 256 == 0) ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
+  plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.Cout / plan->block_n, 1);
+  plan->smem_bytes = plan->block_n == 256 ? TcCfg<256>::kSmemBytes
+                                          : (plan->block_n == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes);
+
+  int rc = encode_act_map(&plan->map_a0, d.src0, d.src0_plane, d.N, d.H, d.W, d.C0, p.bw, p.bh, p.bn);
+  if (rc) return rc;
+  if (d.C1 > 0) {
+    MF_REQUIRE((reinterpret_cast<uintptr_t>(d.src1) & 15) == 0, "TMA sources must be 16-byte aligned");
+    rc = encode_act_map(&plan->map_a1, d.src1, d.src1_plane, d.N, d.H, d.W, d.C1, p.bw, p.bh, p.bn);
+    if (rc) return rc;
+  } else {
+    plan->map_a1 = plan->map_a0;
+  }
+  const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
+  cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
+  cuuint64_t ws[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * d.Cout * 4};
+  cuuint32_t wb[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)plan->block_n, 1};
+  cuuint32_t we[3] = {1, 1, 1};
+  return encode_map(&plan->map_w, d.w_planes, 3, wd, ws, wb, we);
+}
+
+template <int BLOCK_N>
+static int launch_t(const ConvTcPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    TcCfg<BLOCK_N>::kSmemBytes));
+    attr_set = true;
+  }
+  conv_tc_kernel<BLOCK_N><<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.map_a0, plan.map_a1, plan.map_w,
+                                                                              plan.p);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
+  switch (plan.block_n) {
+    case 256: return launch_t<256>(plan, stream);
+    case 128: return launch_t<128>(plan, stream);
+    case 64: return launch_t<64>(plan, stream);
+  }
+  set_error("conv_tc_launch: bad block_n");
+  return 2;
+}
+
+}  // namespace mf

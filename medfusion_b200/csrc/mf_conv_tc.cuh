@@ -1,0 +1,76 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), error-compensated 3xTF32.
+//
+// Replaces the reference's nn.Conv2d call sites on the hot path
+//   /root/reference/medical_diffusion/models/utils/conv_blocks.py:185   (BasicBlock.conv, 3x3 s1 p1)
+//   /root/reference/medical_diffusion/models/utils/conv_blocks.py:224   (BasicResBlock.conv_res, 1x1)
+//   /root/reference/medical_diffusion/models/utils/conv_blocks.py:104   (BasicUp.up_op, 3x3 after nearest x2)
+// and the torch.cat of unet2.py:259 (two-source K loop instead of a materialised concat).
+//
+// GEMM view:  D[M = N*H*W output pixels][Cout] = sum_{tap, c} A[pixel shifted by tap][c] * Wt[Cout][tap*Cin + c]
+// Activations live in HBM as NHWC fp32 in two planes (TF32 hi, fp32 residual lo); weights as
+// [plane][Cout][K] with K = tap-major, channel-minor.  One CTA computes a 128-pixel x BLOCK_N tile:
+//   warp 0      : TMA producer  (5-D activation boxes with zero-filled halo, 3-D weight boxes)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per K-step: hi*hi, hi*lo, lo*hi)
+//   warps 2..5  : epilogue (tcgen05.ld -> +bias -> GroupNorm partial sums -> global store)
+#pragma once
+
+#include "mf_common.cuh"
+
+namespace mf {
+
+constexpr int kTcBlockM = 128;  // output pixels per tile (UMMA M)
+constexpr int kTcBlockK = 32;   // fp32 elements per K block = 128 B = one swizzle row
+constexpr int kTcThreads = 192;
+constexpr int kTcMaxTaps = 9;
+
+enum ConvOutMode : int {
+  kOutRaw = 0,    // single fp32 plane (input of GroupNorm)
+  kOutSplit = 1,  // TF32 hi/lo planes (direct input of the next conv)
+};
+
+struct ConvTcParams {
+  int N, H, W;                   // output geometry (== input geometry, stride 1)
+  int bw, bh, bn;                // pixel box of one tile, bw*bh*bn == 128
+  int tiles_w, tiles_h, tiles_n;
+  int C0, C1;                    // channels of source 0 / 1 (C1 == 0: single source)
+  int Cout;
+  int ntaps;
+  int dy[kTcMaxTaps], dx[kTcMaxTaps];
+  int in_stride;                 // spatial stride of the conv (1; 2 uses strided tensor maps)
+  const float* bias;             // [Cout] or nullptr
+  float* out;                    // NHWC [N,H,W,Cout]; split mode: hi plane
+  long long out_plane;           // elements between hi and lo plane (split mode)
+  int out_mode;
+  float* stats;                  // [N][chunks][Cout/8][2] partial (sum, sumsq) or nullptr
+  int chunks_per_sample;         // tiles per sample (1 if a tile spans >= 1 whole samples)
+  int rows_per_sample;           // min(128, H*W)
+};
+
+struct ConvTcPlan {
+  CUtensorMap map_a0, map_a1, map_w;
+  ConvTcParams p;
+  int block_n;
+  dim3 grid;
+  size_t smem_bytes;
+};
+
+// Host API -------------------------------------------------------------------------------------
+struct ConvTcDesc {
+  // sources: NHWC split tensors (hi plane pointer, lo = hi + plane elements)
+  const float* src0; long long src0_plane; int C0;
+  const float* src1; long long src1_plane; int C1;  // C1 == 0 -> none
+  int N, H, W;              // input == output spatial size
+  const float* w_planes;    // [2][Cout][K] prepared by prep_weight_tc
+  int Cout, ksize;          // ksize 1 or 3 (pad = ksize/2, stride 1)
+  const float* bias;
+  float* out; long long out_plane; int out_mode;
+  float* stats;             // optional
+};
+
+int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
+int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+// number of chunks (tiles per sample) the stats buffer must provide for this geometry
+int conv_tc_stats_chunks(int H, int W);
+
+}  // namespace mf

@@ -1,0 +1,143 @@
+// Host-side execution engine shared by the UNet and VAE-decoder C-ABI objects: parameter registry
+// (reference state_dict names), workspace arena, and a static launch plan per (B, H, W, workspace).
+#pragma once
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "mf_conv_tc.cuh"
+#include "mf_kernels.cuh"
+
+namespace mf {
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t elems) {
+    if (elems == n && p) return 0;
+    release();
+    if (cudaMalloc(&p, elems * sizeof(float)) != cudaSuccess) {
+      set_error("cudaMalloc failed for " + std::to_string(elems * sizeof(float)) + " bytes");
+      return 1;
+    }
+    n = elems;
+    return 0;
+  }
+};
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  DevBuf data;  // reference layout (conv OIHW, linear [out,in], vectors)
+  bool is_set = false;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto d : shape) n *= static_cast<size_t>(d);
+    return n;
+  }
+};
+
+struct ConvLayer {
+  Param* w = nullptr;
+  Param* b = nullptr;
+  int Cout = 0, Cin = 0, k = 1, stride = 1;
+  DevBuf w_tc, w_simt;  // derived layouts, built lazily by the plan builder
+  int tc_version = -1, simt_version = -1;
+};
+struct NormLayer {
+  Param* g = nullptr;
+  Param* b = nullptr;
+  int C = 0;
+};
+struct ResBlockLayer {
+  ConvLayer conv1, conv2, conv_res;
+  NormLayer norm1, norm2;
+  bool has_res_conv = false;
+  int emb_offset = -1;  // row offset in the fused local-embedder matrix, -1: no embedding
+  Param* emb_w = nullptr;
+  Param* emb_b = nullptr;
+  int Cin = 0, Cout = 0;
+};
+
+// ---- workspace arena (static planning; single-stream ordering makes reuse safe) ------------------
+struct Arena {
+  struct Block { size_t off, size; };
+  std::vector<Block> free_list;
+  size_t top = 0, peak = 0;
+  size_t alloc(size_t bytes);
+  void release(size_t off, size_t bytes);
+};
+
+struct Tens {
+  size_t off = 0, bytes = 0;
+  int N = 0, H = 0, W = 0, C = 0;
+  int layout = kNHWCSplit;
+  long long plane = 0;  // elements between hi and lo plane
+  float* ptr = nullptr;
+  long long elems() const { return static_cast<long long>(N) * H * W * C; }
+};
+
+using Launch = std::function<int(cudaStream_t)>;
+
+class EngineBase {
+ public:
+  virtual ~EngineBase() = default;
+  std::vector<std::unique_ptr<Param>> params;
+  std::map<std::string, Param*> by_name;
+  int version = 0;  // bumped by set_param; invalidates derived weight layouts and plans
+
+  Param* add_param(const std::string& name, std::vector<int64_t> shape);
+  int set_param(const char* name, const float* d_data, const int64_t* shape, int ndim, cudaStream_t s);
+  int check_all_set() const;
+
+  // ---- plan state
+  struct PlanKey { int B = -1, H = -1, W = -1; void* base = nullptr; int version = -1; } key;
+  std::vector<Launch> ops;
+  std::vector<std::unique_ptr<ConvTcPlan>> tc_plans;
+  int n_tc = 0, n_simt = 0;
+
+  // ---- builder state (valid during build())
+  bool dry = false;
+  char* base = nullptr;
+  Arena arena;
+  cudaStream_t prep_stream = nullptr;
+
+  Tens new_tensor(int N, int H, int W, int C, int layout);
+  Tens new_floats(size_t n);
+  void free_tensor(const Tens& t);
+
+  // conv: in0 (+ optional in1 channel-concatenated) -> out.  If stats != nullptr the (sum, sumsq)
+  // partials of the output are produced too and *chunks receives their chunk count.
+  int add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const Tens& out, const Tens* stats, int* chunks);
+  // conv reading an external NCHW fp32 pointer that is only known at call time
+  int add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, int Cin, int H, int W, const Tens& out,
+                       const Tens* stats, int* chunks);
+  // conv writing an external NCHW fp32 pointer only known at call time
+  int add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst);
+  int add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks, const Tens* res,
+                   const float* emb, int emb_stride, const Tens& out);
+  // full res block: in0 (+in1 concat) -> returns output tensor (split)
+  int add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, const Tens* in1, const Tens* embT, int emb_stride,
+                   Tens* out);
+  int ensure_w_tc(ConvLayer& L);
+  int ensure_w_simt(ConvLayer& L);
+  int run(cudaStream_t s);
+};
+
+void init_conv(EngineBase& e, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int k, int stride);
+void init_norm(EngineBase& e, NormLayer& L, const std::string& prefix, int C);
+void init_resblock(EngineBase& e, ResBlockLayer& rb, const std::string& prefix, int Cin, int Cout, int k, int emb_dim);
+
+}  // namespace mf

@@ -1,0 +1,537 @@
+#include "mf_kernels.cuh"
+
+namespace mf {
+
+static inline int ceil_div_ll(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+__device__ __forceinline__ float swish(float x) { return x / (1.0f + expf(-x)); }
+
+// =================================================================================================
+// Layout packing
+// =================================================================================================
+__global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, float* __restrict__ out, long long plane, int N,
+                                          int C, int H, int W) {
+  const long long total = static_cast<long long>(N) * H * W * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    const float v = x[((static_cast<long long>(n) * C + c) * H + h) * W + w];
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    out[i] = hi;
+    out[plane + i] = lo;
+  }
+}
+
+int pack_nchw_to_split(const float* x, float* out, long long plane, int N, int C, int H, int W, cudaStream_t s) {
+  const long long total = static_cast<long long>(N) * H * W * C;
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void unpack_to_nchw_kernel(const float* __restrict__ in, long long plane, int layout, float* __restrict__ out,
+                                      int N, int C, int H, int W) {
+  const long long total = static_cast<long long>(N) * H * W * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float v = in[i];
+    if (layout == kNHWCSplit) v += in[plane + i];
+    out[((static_cast<long long>(n) * C + c) * H + h) * W + w] = v;
+  }
+}
+
+int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
+                   cudaStream_t s) {
+  MF_REQUIRE(in_layout == kNHWCRaw || in_layout == kNHWCSplit, "unpack_to_nchw expects an NHWC source");
+  const long long total = static_cast<long long>(N) * H * W * C;
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  unpack_to_nchw_kernel<<<blocks, 256, 0, s>>>(in, plane, in_layout, out, N, C, H, W);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// Weight re-layout (once, at load time)
+// =================================================================================================
+__global__ void prep_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
+                                      int kw) {
+  const long long K = static_cast<long long>(kh) * kw * Cin;
+  const long long total = K * Cout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long k = i % K;
+    const int o = static_cast<int>(i / K);
+    const int c = static_cast<int>(k % Cin);
+    const int tap = static_cast<int>(k / Cin);
+    const float v = w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap];
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    out[i] = hi;
+    out[total + i] = lo;
+  }
+}
+
+int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout) * Cin * kh * kw;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  prep_weight_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, Cout, Cin, kh, kw);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void prep_weight_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
+                                        int kw) {
+  const long long K = static_cast<long long>(kh) * kw * Cin;
+  const long long total = K * Cout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i % Cout);
+    const long long k = i / Cout;
+    const int c = static_cast<int>(k % Cin);
+    const int tap = static_cast<int>(k / Cin);
+    out[i] = w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap];
+  }
+}
+
+int prep_weight_simt(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout) * Cin * kh * kw;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  prep_weight_simt_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, Cout, Cin, kh, kw);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// Exact fp32 convolution on CUDA cores (implicit GEMM, smem tiled, 4x4 register micro-tile)
+//   reference call sites: unet2.py:67 (in_conv, Cin=8), conv_blocks.py:43-52 (BasicDown, stride 2),
+//   unet2.py:213 (UnetOutBlock 1x1 -> 8), latent_embedders.py:719 (inc_dec stem, Cin=8), :743 (outc 64->3)
+// =================================================================================================
+constexpr int kSimtBK = 16;
+
+template <int TM, int TN>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const ConvSimtDesc d, int Hout, int Wout) {
+  static_assert(TM * TN == 4096, "256 threads x 16 outputs");
+  __shared__ float As[kSimtBK][TM + 4];
+  __shared__ float Bs[kSimtBK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % (TN / 4);
+  const int ty = tid / (TN / 4);
+  const long long M = static_cast<long long>(d.N) * Hout * Wout;
+  const long long m0 = static_cast<long long>(blockIdx.x) * TM;
+  const int n0 = blockIdx.y * TN;
+  const int K = d.ksize * d.ksize * d.Cin;
+  const int pad = d.ksize / 2;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += kSimtBK) {
+    // ---- A tile: TM pixels x BK (tap, channel) entries, gathered with zero padding
+    for (int e = tid; e < TM * kSimtBK; e += 256) {
+      int kk, mm;
+      if (d.in_layout == kNCHW) { mm = e % TM; kk = e / TM; } else { kk = e % kSimtBK; mm = e / kSimtBK; }
+      const int k = k0 + kk;
+      const long long m = m0 + mm;
+      float v = 0.f;
+      if (k < K && m < M) {
+        const int c = k % d.Cin;
+        const int tap = k / d.Cin;
+        const int r = tap / d.ksize, sx = tap % d.ksize;
+        const int wo = static_cast<int>(m % Wout);
+        const int ho = static_cast<int>((m / Wout) % Hout);
+        const int n = static_cast<int>(m / (static_cast<long long>(Wout) * Hout));
+        const int hi = ho * d.stride + r - pad;
+        const int wi = wo * d.stride + sx - pad;
+        if (hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win) {
+          if (d.in_layout == kNCHW) {
+            v = d.in[((static_cast<long long>(n) * d.Cin + c) * d.Hin + hi) * d.Win + wi];
+          } else {
+            const long long off = ((static_cast<long long>(n) * d.Hin + hi) * d.Win + wi) * d.Cin + c;
+            v = d.in[off];
+            if (d.in_layout == kNHWCSplit) v += d.in[d.in_plane + off];
+          }
+        }
+      }
+      As[kk][mm] = v;
+    }
+    // ---- B tile: BK x TN weights ([K][Cout], Cout contiguous)
+    for (int e = tid; e < TN * kSimtBK; e += 256) {
+      const int nn = e % TN, kk = e / TN;
+      const int k = k0 + kk, o = n0 + nn;
+      Bs[kk][nn] = (k < K && o < d.Cout) ? d.w_kc[static_cast<long long>(k) * d.Cout + o] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSimtBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int wo = static_cast<int>(m % Wout);
+    const int ho = static_cast<int>((m / Wout) % Hout);
+    const int n = static_cast<int>(m / (static_cast<long long>(Wout) * Hout));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = n0 + tx * 4 + j;
+      if (o >= d.Cout) continue;
+      float v = acc[i][j] + (d.bias ? d.bias[o] : 0.f);
+      if (d.out_layout == kNCHW) {
+        d.out[((static_cast<long long>(n) * d.Cout + o) * Hout + ho) * Wout + wo] = v;
+      } else {
+        const long long off = m * d.Cout + o;
+        if (d.out_layout == kNHWCSplit) {
+          float hi, lo;
+          tf32_split(v, hi, lo);
+          d.out[off] = hi;
+          d.out[d.out_plane + off] = lo;
+        } else {
+          d.out[off] = v;
+        }
+      }
+    }
+  }
+}
+
+int conv_simt(const ConvSimtDesc& d, cudaStream_t s) {
+  MF_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv_simt supports 1x1 and 3x3");
+  MF_REQUIRE(d.stride == 1 || d.stride == 2, "conv_simt supports stride 1 and 2");
+  const int pad = d.ksize / 2;
+  const int Hout = (d.Hin + 2 * pad - d.ksize) / d.stride + 1;
+  const int Wout = (d.Win + 2 * pad - d.ksize) / d.stride + 1;
+  const long long M = static_cast<long long>(d.N) * Hout * Wout;
+  if (M == 0) return 0;
+  if (d.Cout <= 8) {
+    dim3 grid(ceil_div_ll(M, 512), ceil_div_ll(d.Cout, 8));
+    conv_simt_kernel<512, 8><<<grid, 256, 0, s>>>(d, Hout, Wout);
+  } else if (d.Cout <= 16) {
+    dim3 grid(ceil_div_ll(M, 256), ceil_div_ll(d.Cout, 16));
+    conv_simt_kernel<256, 16><<<grid, 256, 0, s>>>(d, Hout, Wout);
+  } else {
+    dim3 grid(ceil_div_ll(M, 64), ceil_div_ll(d.Cout, 64));
+    conv_simt_kernel<64, 64><<<grid, 256, 0, s>>>(d, Hout, Wout);
+  }
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// GroupNorm (reference: conv_blocks.py:177,187 -> nn.GroupNorm(eps=1e-5, affine), biased variance)
+// =================================================================================================
+// One block per (n, 8-channel slab): sum / sumsq over all pixels.  Only used after SIMT convs.
+__global__ void gn_partial_from_raw_kernel(const float* __restrict__ raw, float* __restrict__ partial, int HW, int C) {
+  const int n = blockIdx.y, g8 = blockIdx.x;
+  const float* base = raw + static_cast<long long>(n) * HW * C + g8 * 8;
+  float s = 0.f, ss = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C);
+    const float4 b = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C + 4);
+    s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+  }
+  __shared__ float sh[2][32];
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = ss; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? sh[0][lane] : 0.f;
+    ss = lane < nw ? sh[1][lane] : 0.f;
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (lane == 0) {
+      float* dst = partial + (static_cast<long long>(n) * (C / 8) + g8) * 2;
+      dst[0] = s;
+      dst[1] = ss;
+    }
+  }
+}
+
+int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s) {
+  MF_REQUIRE(C % 8 == 0, "GroupNorm partial sums need C % 8 == 0");
+  dim3 grid(C / 8, N);
+  gn_partial_from_raw_kernel<<<grid, 256, 0, s>>>(raw, partial, HW, C);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// One warp per (n, group): reduce chunks x (cpg/8) partial pairs in double for a stable variance.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean_rstd, int N, int chunks,
+                                   int C, int G, int HW, float eps) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= N * G) return;
+  const int n = gw / G, g = gw % G;
+  const int cpg = C / G, sub = cpg / 8, c8 = C / 8;
+  double s = 0.0, ss = 0.0;
+  const int items = chunks * sub;
+  for (int it = lane; it < items; it += 32) {
+    const int ch = it / sub, j = it % sub;
+    const float* src = partial + ((static_cast<long long>(n) * chunks + ch) * c8 + g * sub + j) * 2;
+    s += static_cast<double>(src[0]);
+    ss += static_cast<double>(src[1]);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  }
+  if (lane == 0) {
+    const double cnt = static_cast<double>(cpg) * HW;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[(static_cast<long long>(n) * G + g) * 2 + 0] = static_cast<float>(mean);
+    mean_rstd[(static_cast<long long>(n) * G + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+int gn_finalize(const float* partial, float* mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
+                cudaStream_t s) {
+  MF_REQUIRE(C % G == 0 && (C / G) % 8 == 0, "GroupNorm groups must span a multiple of 8 channels");
+  const int warps = N * G;
+  gn_finalize_kernel<<<ceil_div_ll(warps, 8), 256, 0, s>>>(partial, mean_rstd, N, chunks, C, G, HW, eps);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// y = swish(gn(raw)) + residual (+ emb)   -> split planes
+//   reference: conv_blocks.py:184-192 (conv -> norm -> drop(p=0) -> act), :236-240 (+ residual), :362-363 (+= emb)
+__global__ void gn_apply_kernel(const GnApplyDesc d) {
+  const int c4n = d.C / 4;
+  const long long total = static_cast<long long>(d.N) * d.HW * c4n;
+  const int cpg = d.C / d.G;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int n = static_cast<int>(pix / d.HW);
+    const long long off = pix * d.C + c;
+    const float4 x = *reinterpret_cast<const float4*>(d.raw + off);
+    const float2 mr = *reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + c / cpg) * 2);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + c));
+    float y[4] = {(x.x - mr.x) * mr.y * ga.x + be.x, (x.y - mr.x) * mr.y * ga.y + be.y,
+                  (x.z - mr.x) * mr.y * ga.z + be.z, (x.w - mr.x) * mr.y * ga.w + be.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
+    if (d.res_kind == kResSplit) {
+      const float4 rh = *reinterpret_cast<const float4*>(d.res + off);
+      const float4 rl = *reinterpret_cast<const float4*>(d.res + d.res_plane + off);
+      y[0] += rh.x + rl.x; y[1] += rh.y + rl.y; y[2] += rh.z + rl.z; y[3] += rh.w + rl.w;
+    } else if (d.res_kind == kResRaw) {
+      const float4 r = *reinterpret_cast<const float4*>(d.res + off);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+    }
+    if (d.emb != nullptr) {
+      const float4 e = *reinterpret_cast<const float4*>(d.emb + static_cast<long long>(n) * d.emb_stride + c);
+      y[0] += e.x; y[1] += e.y; y[2] += e.z; y[3] += e.w;
+    }
+    float4 hi, lo;
+    tf32_split(y[0], hi.x, lo.x);
+    tf32_split(y[1], hi.y, lo.y);
+    tf32_split(y[2], hi.z, lo.z);
+    tf32_split(y[3], hi.w, lo.w);
+    *reinterpret_cast<float4*>(d.out + off) = hi;
+    *reinterpret_cast<float4*>(d.out + d.out_plane + off) = lo;
+  }
+}
+
+int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
+  MF_REQUIRE(d.C % 4 == 0 && d.C % d.G == 0 && (d.C / d.G) % 4 == 0, "gn_apply channel constraints");
+  MF_REQUIRE(d.emb == nullptr || d.emb_stride % 4 == 0, "emb rows must be float4 aligned");
+  const long long total = static_cast<long long>(d.N) * d.HW * (d.C / 4);
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+  gn_apply_kernel<<<blocks, 256, 0, s>>>(d);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// nearest x2 upsample (split -> split)
+// =================================================================================================
+__global__ void upsample2x_split_kernel(const float* __restrict__ in, long long in_plane, float* __restrict__ out,
+                                        long long out_plane, int N, int H, int W, int C) {
+  const int c4n = C / 4;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = static_cast<long long>(N) * Ho * Wo * c4n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int wo = static_cast<int>(pix % Wo);
+    const int ho = static_cast<int>((pix / Wo) % Ho);
+    const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    const long long src = ((static_cast<long long>(n) * H + (ho >> 1)) * W + (wo >> 1)) * C + c;
+    const long long dst = pix * C + c;
+    *reinterpret_cast<float4*>(out + dst) = *reinterpret_cast<const float4*>(in + src);
+    *reinterpret_cast<float4*>(out + out_plane + dst) = *reinterpret_cast<const float4*>(in + in_plane + src);
+  }
+}
+
+int upsample2x_split(const float* in, long long in_plane, float* out, long long out_plane, int N, int H, int W, int C,
+                     cudaStream_t s) {
+  MF_REQUIRE(C % 4 == 0, "upsample2x_split needs C % 4 == 0");
+  const long long total = static_cast<long long>(N) * 4 * H * W * (C / 4);
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+  upsample2x_split_kernel<<<blocks, 256, 0, s>>>(in, in_plane, out, out_plane, N, H, W, C);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// Embedding MLP (reference: time_embedder.py:15-28,67-75; cond_embedders.py:18-23; conv_blocks.py:340-350)
+//   One warp per output feature j; the weight row stays in registers while the warp walks the batch.
+// =================================================================================================
+template <int KPL>  // K per lane (K = 32*KPL)
+__global__ void linear_small_kernel(const LinearDesc d) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= d.J) return;
+  float w[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) w[i] = d.W[static_cast<long long>(j) * d.K + i * 32 + lane];
+  const float bj = d.bias ? d.bias[j] : 0.f;
+  for (int b = 0; b < d.B; ++b) {
+    float acc = 0.f;
+    if (d.in_mode == 0) {
+      const float* x = d.in + static_cast<long long>(b) * d.K;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) acc = fmaf(w[i], x[i * 32 + lane], acc);
+    } else {
+      // sinusoidal position embedding: cat(sin(t*f), cos(t*f)), f given by the host table
+      const float tf = static_cast<float>(d.t[b]);
+      const int half = d.K / 2;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const int k = i * 32 + lane;
+        const float a = tf * d.freqs[k < half ? k : k - half];
+        acc = fmaf(w[i], k < half ? sinf(a) : cosf(a), acc);
+      }
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      float v = acc + bj;
+      if (d.add_table != nullptr) v += d.add_table[d.add_idx[b] * d.J + j];
+      if (d.post == 1) v = swish(v);
+      d.out[static_cast<long long>(b) * d.J + j] = v;
+      if (d.out2 != nullptr) d.out2[static_cast<long long>(b) * d.J + j] = swish(v);
+    }
+  }
+}
+
+int linear_small(const LinearDesc& d, cudaStream_t s) {
+  MF_REQUIRE(d.K % 32 == 0 && d.K <= 2048, "linear_small: K must be a multiple of 32, <= 2048");
+  if (d.B == 0 || d.J == 0) return 0;
+  const int blocks = ceil_div_ll(static_cast<long long>(d.J) * 32, 256);
+  switch (d.K / 32) {
+#define MF_LIN_CASE(n) case n: linear_small_kernel<n><<<blocks, 256, 0, s>>>(d); break;
+    MF_LIN_CASE(1) MF_LIN_CASE(2) MF_LIN_CASE(4) MF_LIN_CASE(8) MF_LIN_CASE(16) MF_LIN_CASE(32) MF_LIN_CASE(64)
+#undef MF_LIN_CASE
+    default:
+      set_error("linear_small: unsupported K (need K/32 in {1,2,4,8,16,32,64})");
+      return 2;
+  }
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// Scheduler step (reference: gaussian_scheduler.py:80-124, diffusion_pipeline.py:240-244, :297-304)
+// =================================================================================================
+__global__ void sched_step_kernel(const SchedStepDesc d) {
+  const long long total = static_cast<long long>(d.B) * d.CHW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / d.CHW);
+    const long long t = d.t[b];
+    float pred = d.pred[i];
+    if (d.pred_uncond != nullptr) {
+      const float pu = d.pred_uncond[i];
+      pred = pu + d.guidance * (pred - pu);  // classifier-free guidance combine
+    }
+    const float xt = d.x_t[i];
+    const float A = d.tab.sqrt_recip_ac[t], Bm = d.tab.sqrt_recipm1_ac[t];
+    float x0, xT;
+    if (d.objective_x0) {
+      x0 = pred;
+      if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+      xT = __fdiv_rn(__fsub_rn(__fmul_rn(A, xt), x0), Bm);
+    } else {
+      xT = pred;
+      x0 = __fsub_rn(__fmul_rn(A, xt), __fmul_rn(Bm, pred));
+      if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    }
+    const float mean = __fadd_rn(__fmul_rn(d.tab.coef1[t], x0), __fmul_rn(d.tab.coef2[t], xt));
+    float stdv = 0.f;
+    if (t != 0) stdv = expf(0.5f * logf(fmaxf(d.tab.post_var[t], 1e-20f)));
+    const float nz = d.noise ? d.noise[i] : 0.f;
+    const float prior = __fadd_rn(mean, __fmul_rn(stdv, nz));
+    if (d.x_prior) d.x_prior[i] = prior;
+    if (d.x_0) d.x_0[i] = x0;
+    if (d.x_T) d.x_T[i] = xT;
+    if (d.x_next) {
+      float xn = prior;
+      if (d.t_next != nullptr) {
+        // DDIM-form re-noise with eta == 1 (diffusion_pipeline.py:297-304)
+        const float a = d.tab.alphas_cumprod[t];
+        const float an = d.tab.alphas_cumprod[*d.t_next];
+        const float sig2arg =
+            __fdiv_rn(__fmul_rn(__fsub_rn(1.f, __fdiv_rn(a, an)), __fsub_rn(1.f, an)), __fsub_rn(1.f, a));
+        const float sigma = __fsqrt_rn(sig2arg);
+        const float cc = __fsqrt_rn(__fsub_rn(__fsub_rn(1.f, an), __fmul_rn(sigma, sigma)));
+        const float n2 = d.noise2 ? d.noise2[i] : 0.f;
+        xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, __fsqrt_rn(an)), __fmul_rn(cc, xT)), __fmul_rn(sigma, n2));
+      }
+      d.x_next[i] = xn;
+    }
+  }
+}
+
+int sched_step(const SchedStepDesc& d, cudaStream_t s) {
+  const long long total = static_cast<long long>(d.B) * d.CHW;
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  sched_step_kernel<<<blocks, 256, 0, s>>>(d);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mf

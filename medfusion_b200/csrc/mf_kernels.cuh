@@ -1,0 +1,91 @@
+// Non-tensor-core kernels of the hot path: layout packing, exact-fp32 SIMT convolution for the
+// narrow layers (Cin = 8 stems, Cout = 3/8 heads, stride-2 downsamplers), GroupNorm finalize/apply
+// with fused Swish + residual + embedding add, nearest x2 upsample, timestep/label embedding MLP,
+// and the scheduler update.  Reference call sites are cited at each launcher in mf_kernels.cu.
+#pragma once
+
+#include "mf_common.cuh"
+
+namespace mf {
+
+enum ActLayout : int {
+  kNCHW = 0,       // contiguous fp32 [N,C,H,W]        (reference tensor layout at the API boundary)
+  kNHWCRaw = 1,    // fp32 [N,H,W,C], one plane
+  kNHWCSplit = 2,  // fp32 [2][N,H,W,C], TF32-hi plane + residual-lo plane
+};
+
+// ---- layout / weight preparation -----------------------------------------------------------------
+int pack_nchw_to_split(const float* x, float* out, long long plane, int N, int C, int H, int W, cudaStream_t s);
+int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
+                   cudaStream_t s);
+// OIHW -> [2][Cout][K], K = (r*kw+s)*Cin + c  (tensor-core path)
+int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+// OIHW -> [K][Cout] fp32 (SIMT path)
+int prep_weight_simt(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+
+// ---- exact fp32 convolution on CUDA cores ---------------------------------------------------------
+struct ConvSimtDesc {
+  const float* in; long long in_plane; int in_layout;
+  int N, Cin, Hin, Win;
+  const float* w_kc;      // [K][Cout]
+  const float* bias;      // [Cout] or nullptr
+  int Cout, ksize, stride;  // pad = ksize/2
+  float* out; long long out_plane; int out_layout;
+};
+int conv_simt(const ConvSimtDesc& d, cudaStream_t s);
+
+// ---- GroupNorm ------------------------------------------------------------------------------------
+// partial stats layout (shared with conv_tc epilogue): [N][chunks][C/8][2] = (sum, sumsq) over 8 channels
+int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s);
+// partial -> (mean, rstd) per (n, group): out [N][G][2]
+int gn_finalize(const float* partial, float* mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
+                cudaStream_t s);
+enum ResKind : int { kResNone = 0, kResSplit = 1, kResRaw = 2 };
+struct GnApplyDesc {
+  const float* raw;         // [N,HW,C] conv output (+bias)
+  const float* mean_rstd;   // [N][G][2]
+  const float* gamma; const float* beta;  // [C]
+  const float* res; long long res_plane; int res_kind;
+  const float* emb; int emb_stride;       // emb[n*emb_stride + c] or nullptr
+  float* out; long long out_plane;        // split planes
+  int N, HW, C, G;
+};
+int gn_apply(const GnApplyDesc& d, cudaStream_t s);
+
+// nearest x2 upsample of a split tensor (reference: conv_blocks.py:123-125, F.interpolate nearest-exact)
+int upsample2x_split(const float* in, long long in_plane, float* out, long long out_plane, int N, int H, int W, int C,
+                     cudaStream_t s);
+
+// ---- embedding MLP --------------------------------------------------------------------------------
+// out[b][j] = post( sum_k W[j][k] * in[b][k] + bias[j] + add[b][j] );  W row-major [J][K]
+//   in_mode 0: in is a float [B][K] matrix;  in_mode 1: in is built on the fly as sinusoidal(t[b]) with freqs[K/2]
+//   post 0: identity, 1: swish;  out2 (optional) receives swish(out)
+struct LinearDesc {
+  const float* in; const long long* t; const float* freqs; int in_mode;
+  const float* W; const float* bias;
+  const float* add_table; const long long* add_idx;  // optional embedding-table add: add_table[add_idx[b]][j]
+  float* out; float* out2; int post;
+  int B, J, K;
+};
+int linear_small(const LinearDesc& d, cudaStream_t s);
+
+// ---- scheduler step -------------------------------------------------------------------------------
+struct SchedTables {  // device pointers, length T each (fp32), computed in fp64 on the host like the reference
+  const float* sqrt_recip_ac; const float* sqrt_recipm1_ac; const float* coef1; const float* coef2;
+  const float* post_var; const float* betas; const float* alphas_cumprod;
+};
+struct SchedStepDesc {
+  const float* x_t; const float* pred; const float* pred_uncond; float guidance;  // pred_uncond nullable
+  const long long* t;        // [B]
+  const float* noise;        // randn_like(x_t) (scheduler draw); nullable -> treated as 0
+  const long long* t_next;   // scalar device int64 (DDIM re-noise) or nullptr
+  const float* noise2;       // DDIM draw
+  int objective_x0;          // 0: estimator predicts x_T (noise), 1: predicts x_0
+  int clip_x0;
+  float* x_prior; float* x_0; float* x_T; float* x_next;  // outputs (x_next only with t_next)
+  int B, CHW;
+  SchedTables tab;
+};
+int sched_step(const SchedStepDesc& d, cudaStream_t s);
+
+}  // namespace mf

@@ -1,0 +1,9 @@
+import torch.nn as nn
+
+
+class LPIPS(nn.Module):
+    def __init__(self, *a, **k):
+        super().__init__()
+
+    def forward(self, *a, **k):
+        raise NotImplementedError
