@@ -36,6 +36,8 @@ typedef void* mf_stream_t; /* cudaStream_t */
  * ---------------------------------------------------------------------------------------------- */
 const char* mf_last_error(void);
 int mf_abi_version(void);
+/* Default TMEM drain interval used by the engines' tensor-core convolutions (see mf_op_conv_tc). */
+int mf_set_drain_interval(int k_blocks);
 
 /* -------------------------------------------------------------------------------------------------
  * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block
@@ -133,10 +135,12 @@ int mf_op_unpack_nchw(const float* d_in, int64_t plane, int layout, float* d_out
 int mf_op_prep_weight_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
 int mf_op_prep_weight_simt(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
 int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
-/* stride-1 'same' conv on the tcgen05 path; src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL */
+/* stride-1 'same' conv on the tcgen05 path; src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL.
+ * drain_interval: K blocks (of 32 channels) summed inside TMEM before the round-to-nearest fp32 register
+ * accumulation; 0 = library default (1, the most exact). */
 int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
                   int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
-                  int64_t out_plane, int out_layout, float* d_stats, mf_stream_t s);
+                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, mf_stream_t s);
 int mf_op_conv_tc_stats_chunks(int H, int W);
 int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
                     const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,

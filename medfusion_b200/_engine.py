@@ -1,0 +1,95 @@
+"""Shared host-side plumbing between the torch-facing modules and the C-ABI engines."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._params import build_param_tree, param_signature
+
+
+def cuda_stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: medfusion_b200 runs on CUDA (sm_100a) only — got a {t.device} tensor. "
+            "There is no CPU fallback; move the module and its inputs to a B200.")
+
+
+class EngineModule(nn.Module):
+    """nn.Module whose parameters mirror a C engine's registry and whose compute is the engine's."""
+
+    _prefix = ""  # "mf_unet" / "mf_vae"
+
+    def _engine_init(self, handle, zero_init=()):
+        lib = _lib.load()
+        self._h = handle
+        self._ws = {}          # (B,H,W) -> uint8 workspace tensor
+        self._synced_sig = None
+        n = getattr(lib, f"{self._prefix}_param_count")(handle)
+        entries = []
+        shape = (ctypes.c_int64 * 4)()
+        ndim = ctypes.c_int()
+        for i in range(n):
+            name = getattr(lib, f"{self._prefix}_param_name")(handle, i).decode()
+            _lib.check(getattr(lib, f"{self._prefix}_param_shape")(handle, i, shape, ctypes.byref(ndim)), "param_shape")
+            entries.append((name, tuple(int(shape[k]) for k in range(ndim.value))))
+        self._entries = entries
+        build_param_tree(self, entries, zero_init=zero_init)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                getattr(_lib.load(), f"{self._prefix}_destroy")(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def sync_params(self, force=False):
+        """Push parameters whose storage/version changed since the last push into the engine."""
+        sig = param_signature(self)
+        if not force and sig == self._synced_sig:
+            return
+        lib = _lib.load()
+        sd = dict(self.named_parameters())
+        stream = cuda_stream_ptr()
+        setter = getattr(lib, f"{self._prefix}_set_param")
+        for name, shape in self._entries:
+            p = sd[name]
+            require_cuda(p, f"parameter {name}")
+            data = p.detach().contiguous()
+            arr = (ctypes.c_int64 * len(shape))(*shape)
+            _lib.check(setter(self._h, name.encode(), data.data_ptr(), arr, len(shape), stream), f"set_param({name})")
+        self._after_param_sync(stream)
+        self._synced_sig = sig
+
+    def _after_param_sync(self, stream):
+        pass
+
+    def _workspace(self, B, H, W):
+        key = (B, H, W, torch.cuda.current_device())
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = getattr(_lib.load(), f"{self._prefix}_workspace_bytes")(self._h, B, H, W)
+            if nbytes == 0:
+                _lib.check(2, "workspace_bytes")
+            self._ws.clear()  # one live plan per module: the engine caches a single (B,H,W,workspace) plan
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        off = (-ws.data_ptr()) % 1024
+        return ws.data_ptr() + off, ws.numel() - off
+
+    def plan_info(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        getattr(_lib.load(), f"{self._prefix}_plan_info")(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return dict(tc_convs=a.value, simt_convs=b.value, launches=c.value)

@@ -46,6 +46,7 @@ _P = c_void_p
 SIGNATURES = {
     "mf_last_error": (c_char_p, []),
     "mf_abi_version": (c_int, []),
+    "mf_set_drain_interval": (c_int, [c_int]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),
     "mf_unet_param_count": (c_int, [_P]),
@@ -74,7 +75,7 @@ SIGNATURES = {
     "mf_op_conv_tc_supported": (c_int, [c_int] * 8),
     "mf_op_conv_tc_stats_chunks": (c_int, [c_int, c_int]),
     "mf_op_conv_tc": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P,
-                              _P, c_int64, c_int, _P, _P]),
+                              _P, c_int64, c_int, _P, c_int, _P]),
     "mf_op_conv_simt": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P,
                                 c_int64, c_int, _P]),
     "mf_op_gn_partial": (c_int, [_P, _P, c_int, c_int, c_int, _P]),

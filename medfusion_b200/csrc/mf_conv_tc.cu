@@ -5,6 +5,8 @@
 
 namespace mf {
 
+int g_default_drain_interval = 1;
+
 // =================================================================================================
 // Device side
 // =================================================================================================
@@ -14,24 +16,34 @@ struct TcCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
-  static constexpr int kAuxBytes = 2048;  // barriers, TMEM slot, stats scratch
+  static constexpr int kAuxBytes = 2560;  // barriers, TMEM slot, stats scratch
   static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // +1024: manual alignment slack
-  static_assert(4 * (BLOCK_N / 8) * 2 * 4 + 256 <= kAuxBytes, "aux region too small");
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two chunk accumulators (ping-pong)
+  static constexpr int kColsPerWarp = BLOCK_N / 2;  // 8 drain warps: 4 lane quarters x 2 column halves
+  static_assert(4 * (BLOCK_N / 8) * 2 * 4 + 512 <= kAuxBytes, "aux region too small");
 };
 
+// Why the accumulation leaves the tensor core: tcgen05.mma adds into its fp32 TMEM accumulator with
+// truncation (round-toward-zero), so a long chain of MMAs drifts by ~0.5 ulp(|acc|) per instruction
+// (measured: 2e-4 abs at K=2304, i.e. far outside the 1e-5 parity budget).  We therefore let the
+// tensor core produce SHORT partial sums (one 32-channel K block: 8 tiny cross-term MMAs first, then the
+// 4 hi*hi MMAs) into one of two TMEM buffers, and the drain warps add each finished partial into
+// round-to-nearest fp32 running sums held in registers while the next K block is being multiplied.
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
+  constexpr int CPW = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* red = reinterpret_cast<float*>(aux + 256);  // [4 warps][BLOCK_N/8][2]
+  uint64_t* acc_full_bar = empty_bar + Cfg::kStages;   // [2] MMA -> drain
+  uint64_t* acc_empty_bar = acc_full_bar + 2;          // [2] drain -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+  float* red = reinterpret_cast<float*>(aux + 512);  // [4 quarters][BLOCK_N/8][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -46,6 +58,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int cin = p.C0 + p.C1;
   const int cblks = cin / kTcBlockK;
   const int nkb = p.ntaps * cblks;
+  const int drain = p.drain_interval < 1 ? 1 : p.drain_interval;  // K blocks per TMEM partial sum
+  const int nchunks = (nkb + drain - 1) / drain;
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -56,11 +70,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full_bar[b], 1);
+      mbar_init(&acc_empty_bar[b], kTcDrainWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BLOCK_N);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -96,54 +113,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM, BLOCK_N);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int kb = 0;
+      for (int j = 0; j < nchunks; ++j) {
+        const int buf = j & 1;
+        mbar_wait(&acc_empty_bar[buf], ((j >> 1) & 1) ^ 1);  // drained two chunks ago (first use: free)
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t a_hi = umma_smem_desc_sw128(st);
-        const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
-        const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
-        const uint64_t b_lo = umma_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        const int kb_end = min(nkb, kb + drain);
+        bool first = true;
+        for (; kb < kb_end; ++kb) {
+          const int s = kb % Cfg::kStages;
+          const uint32_t ph = (kb / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t a_hi = umma_smem_desc_sw128(st);
+          const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
+          const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
+          const uint64_t b_lo = umma_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+          // K advance inside the 128-byte swizzled row: 8 tf32 = 32 bytes = +2 in 16-byte units.
+          // Cross terms first (tiny magnitudes, truncation negligible), dominant hi*hi products last.
 #pragma unroll
-        for (int k = 0; k < kTcBlockK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes inside the 128-byte swizzled row: +2 in 16-byte units
-          const uint64_t koff = static_cast<uint64_t>(k * 2);
-          // small cross terms first, then the dominant hi*hi term
-          umma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
-          umma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
-          umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1);
+          for (int k = 0; k < kTcBlockK / 8; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(k * 2);
+            umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+            first = false;
+            umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+          }
+#pragma unroll
+          for (int k = 0; k < kTcBlockK / 8; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(k * 2);
+            umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+        umma_commit(&acc_full_bar[buf]);  // partial sum complete -> drain warps
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue (4 warps, 128 rows) =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;     // accumulator row == pixel index inside the tile box
+    // ===================== drain + epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) =========
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which BLOCK_N/2 column range
+    const int col0 = half * CPW;
+    const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile box
+    float acc[CPW];
+#pragma unroll
+    for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
+
+    for (int j = 0; j < nchunks; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&acc_full_bar[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + col0;
+#pragma unroll
+      for (int ch = 0; ch < CPW / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32(taddr + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] += v[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+    }
+
+    // ---- epilogue from registers
     const int iw = row % p.bw;
     const int ih = (row / p.bw) % p.bh;
     const int in = row / (p.bw * p.bh);
     const int n = n0 + in, h = h0 + ih, w = w0 + iw;
     const bool valid = n < p.N;
     const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
-    float* orow = p.out + pix * p.Cout + nt * BLOCK_N;
+    float* orow = p.out + pix * p.Cout + nt * BLOCK_N + col0;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
-#pragma unroll 1
-    for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * 32, v);
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + ch * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    for (int ch = 0; ch < CPW / 32; ++ch) {
+      float* v = &acc[ch * 32];
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + col0 + ch * 32);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 b = __ldg(b4 + jj);
+          v[4 * jj + 0] += b.x; v[4 * jj + 1] += b.y; v[4 * jj + 2] += b.z; v[4 * jj + 3] += b.w;
         }
       }
       if (p.stats != nullptr) {
@@ -151,8 +202,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int g = 0; g < 4; ++g) {
           float s = 0.f, ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float x = v[8 * g + j];
+          for (int jj = 0; jj < 8; ++jj) {
+            const float x = v[8 * g + jj];
             s += x;
             ss = fmaf(x, x, ss);
           }
@@ -163,7 +214,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             ss += __shfl_xor_sync(0xffffffffu, ss, off);
           }
           if (lane == 0) {
-            float* r = red + ((q * (BLOCK_N / 8)) + ch * 4 + g) * 2;
+            float* r = red + ((q * (BLOCK_N / 8)) + (col0 + ch * 32) / 8 + g) * 2;
             r[0] = s;
             r[1] = ss;
           }
@@ -173,34 +224,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (p.out_mode == kOutRaw) {
           float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int jj = 0; jj < 8; ++jj)
+            o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
         } else {
           float4* o4h = reinterpret_cast<float4*>(orow + ch * 32);
           float4* o4l = reinterpret_cast<float4*>(orow + p.out_plane + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int jj = 0; jj < 8; ++jj) {
             float4 hi, lo;
-            tf32_split(v[4 * j + 0], hi.x, lo.x);
-            tf32_split(v[4 * j + 1], hi.y, lo.y);
-            tf32_split(v[4 * j + 2], hi.z, lo.z);
-            tf32_split(v[4 * j + 3], hi.w, lo.w);
-            o4h[j] = hi;
-            o4l[j] = lo;
+            tf32_split(v[4 * jj + 0], hi.x, lo.x);
+            tf32_split(v[4 * jj + 1], hi.y, lo.y);
+            tf32_split(v[4 * jj + 2], hi.z, lo.z);
+            tf32_split(v[4 * jj + 3], hi.w, lo.w);
+            o4h[jj] = hi;
+            o4l[jj] = lo;
           }
         }
       }
     }
 
     if (p.stats != nullptr) {
-      // combine the 4 epilogue warps (named barrier 1: only the 128 epilogue threads participate)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int te = threadIdx.x - 64;                 // 0..127
+      // combine the lane quarters (named barrier 1: only the 256 drain/epilogue threads participate)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int te = threadIdx.x - 64;                 // 0..255
       const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
-      const int wps = 4 / spt;                         // warps per sample
+      const int wps = 4 / spt;                         // lane quarters per sample
       constexpr int G8 = BLOCK_N / 8;
       if (te < G8 * spt) {
         const int j = te / G8, i = te - j * G8;
-        // red[] is indexed by TMEM lane quarter q, i.e. by row/32
         float s = 0.f, ss = 0.f;
         for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
           s += red[(wq * G8 + i) * 2 + 0];
@@ -223,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, BLOCK_N);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -327,6 +378,7 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
     p.dx[t] = t % d.ksize - d.ksize / 2;
   }
   p.in_stride = 1;
+  p.drain_interval = d.drain_interval > 0 ? d.drain_interval : g_default_drain_interval;
   p.bias = d.bias;
   p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
   p.stats = d.stats;

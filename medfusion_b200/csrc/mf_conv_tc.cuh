@@ -11,7 +11,8 @@
 // [plane][Cout][K] with K = tap-major, channel-minor.  One CTA computes a 128-pixel x BLOCK_N tile:
 //   warp 0      : TMA producer  (5-D activation boxes with zero-filled halo, 3-D weight boxes)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per K-step: hi*hi, hi*lo, lo*hi)
-//   warps 2..5  : epilogue (tcgen05.ld -> +bias -> GroupNorm partial sums -> global store)
+//   warps 2..9  : drain (tcgen05.ld of each finished TMEM partial sum -> round-to-nearest fp32 register
+//                 accumulation) and epilogue (+bias -> GroupNorm partial sums -> global store)
 #pragma once
 
 #include "mf_common.cuh"
@@ -20,7 +21,8 @@ namespace mf {
 
 constexpr int kTcBlockM = 128;  // output pixels per tile (UMMA M)
 constexpr int kTcBlockK = 32;   // fp32 elements per K block = 128 B = one swizzle row
-constexpr int kTcThreads = 192;
+constexpr int kTcDrainWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kTcDrainWarps;  // TMA warp + MMA warp + drain/epilogue warps
 constexpr int kTcMaxTaps = 9;
 
 enum ConvOutMode : int {
@@ -37,6 +39,7 @@ struct ConvTcParams {
   int ntaps;
   int dy[kTcMaxTaps], dx[kTcMaxTaps];
   int in_stride;                 // spatial stride of the conv (1; 2 uses strided tensor maps)
+  int drain_interval;            // K blocks accumulated inside TMEM before the fp32 register add (1 = most exact)
   const float* bias;             // [Cout] or nullptr
   float* out;                    // NHWC [N,H,W,Cout]; split mode: hi plane
   long long out_plane;           // elements between hi and lo plane (split mode)
@@ -65,8 +68,10 @@ struct ConvTcDesc {
   const float* bias;
   float* out; long long out_plane; int out_mode;
   float* stats;             // optional
+  int drain_interval;       // 0 -> default (1)
 };
 
+extern int g_default_drain_interval;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);

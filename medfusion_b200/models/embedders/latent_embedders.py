@@ -1,0 +1,113 @@
+"""VAE latent embedder — decoder half only (reference: medical_diffusion/models/embedders/latent_embedders.py:620-855).
+
+`VAE.decode` (:764-769) is on the sampling hot path and runs as an sm_100a launch plan (mf_vae_decode).
+The encoder / losses / GAN variants are training-side and outside this package's scope;
+`load_state_dict` accepts a full reference VAE state_dict and ignores the encoder-side keys.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ... import _lib
+from ..._engine import EngineModule, cuda_stream_ptr, require_cuda
+
+_ENCODER_SIDE_PREFIXES = ("inc.", "encoders.", "out_enc.", "outc_ver.", "perceiver.", "loss_fct.", "quantizer.")
+
+
+class VAE(EngineModule):
+    _prefix = "mf_vae"
+
+    def __init__(
+        self,
+        in_channels=3,
+        out_channels=3,
+        spatial_dims=2,
+        emb_channels=4,
+        hid_chs=(64, 128, 256, 512),
+        kernel_sizes=(3, 3, 3, 3),
+        strides=(1, 2, 2, 2),
+        norm_name=("GROUP", {"num_groups": 8, "affine": True}),
+        act_name=("Swish", {}),
+        dropout=None,
+        use_res_block=True,
+        deep_supervision=False,
+        learnable_interpolation=True,
+        use_attention="none",
+        embedding_loss_weight=1e-6,
+        perceiver=None,
+        perceiver_kwargs=None,
+        perceptual_loss_weight=1.0,
+        optimizer=None,
+        optimizer_kwargs=None,
+        lr_scheduler=None,
+        lr_scheduler_kwargs=None,
+        loss=None,
+        loss_kwargs=None,
+        sample_every_n_steps=1000,
+    ):
+        super().__init__()
+        if spatial_dims != 2:
+            raise NotImplementedError("medfusion_b200.VAE implements the 2-D decoder (spatial_dims=2)")
+        if not use_res_block or not learnable_interpolation:
+            raise NotImplementedError("only use_res_block=True, learnable_interpolation=True is implemented")
+        attn = list(use_attention) if isinstance(use_attention, (list, tuple)) else [use_attention] * len(strides)
+        if any(a != "none" for a in attn):
+            raise NotImplementedError("VAE attention is not implemented")
+        if any(k != 3 for k in kernel_sizes[1:]):
+            raise NotImplementedError("decoder res-blocks use 3x3 convolutions")
+        depth = len(strides)
+        self.depth = depth
+        self.emb_channels, self.out_channels = emb_channels, out_channels
+        self.in_channels = in_channels
+        self.up_factor = 1
+        for s in strides[1:]:
+            self.up_factor *= s
+        cfg = _lib.VAEConfig()
+        cfg.emb_channels, cfg.out_channels, cfg.depth = emb_channels, out_channels, depth
+        for i in range(depth):
+            cfg.hid_chs[i], cfg.strides[i] = hid_chs[i], strides[i]
+        cfg.norm_groups = dict(norm_name[1]).get("num_groups", 8) if isinstance(norm_name, (tuple, list)) else 8
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().mf_vae_create(ctypes.byref(cfg), ctypes.byref(handle)), "mf_vae_create")
+        # zero-init: 2nd conv of each res block (conv_blocks.py:336) and the image head (latent_embedders.py:743)
+        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc."))
+
+    # --- checkpoint compatibility -------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        own = {k: v for k, v in state_dict.items() if not k.startswith(_ENCODER_SIDE_PREFIXES)}
+        return super().load_state_dict(own, strict=strict, **kw)
+
+    @classmethod
+    def load_from_checkpoint(cls, path, map_location=None, **overrides):
+        """Lightning-style checkpoint: {'state_dict': ..., 'hyper_parameters': {...}} (model_base.py:68-85)."""
+        ckpt = torch.load(path, map_location=map_location or "cpu", weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        accepted = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
+        model = cls(**{k: v for k, v in hp.items() if k in accepted})
+        model.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
+        return model
+
+    # --- hot path -------------------------------------------------------------------------------
+    def decode(self, z):
+        """z [B,emb_channels,h,w] -> x [B,out_channels,h*f,w*f]  (latent_embedders.py:764-769)"""
+        require_cuda(z, "VAE.decode(z)")
+        if z.dim() != 4 or z.shape[1] != self.emb_channels:
+            raise ValueError(f"z must be [B,{self.emb_channels},h,w], got {tuple(z.shape)}")
+        self.sync_params()
+        B, _, H, W = z.shape
+        zc = z.contiguous().float()
+        x = torch.empty((B, self.out_channels, H * self.up_factor, W * self.up_factor), device=z.device,
+                        dtype=torch.float32)
+        ws, ws_bytes = self._workspace(B, H, W)
+        _lib.check(_lib.load().mf_vae_decode(self._h, zc.data_ptr(), x.data_ptr(), B, H, W, ws, ws_bytes,
+                                             cuda_stream_ptr()), "mf_vae_decode")
+        return x
+
+    def encode(self, x):
+        raise NotImplementedError("VAE.encode is training-side and out of scope of the sampling hot path")
+
+    def forward(self, x_in):
+        raise NotImplementedError("VAE.forward (encode+decode with losses) is training-side; use decode(z)")

@@ -1,0 +1,135 @@
+"""UNet noise estimator — drop-in for the reference's live `unet2.UNet`
+(/root/reference/medical_diffusion/models/estimators/unet2.py:15-269; exported by estimators/__init__.py:1).
+
+Same constructor keywords, same state_dict keys, same `forward(x_t, t, condition, self_cond) -> (y, y_ver)`
+contract; the arithmetic is a launch plan of sm_100a kernels inside libmedfusion_b200.so
+(mf_unet_forward).  Options of the reference that are outside the sampling hot path of the
+canonical model raise NotImplementedError instead of silently diverging.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ... import _lib
+from ..._engine import EngineModule, cuda_stream_ptr, require_cuda
+from ..embedders import TimeEmbbeding
+
+
+def _name_of(spec):
+    return str(spec[0] if isinstance(spec, (tuple, list)) else spec).lower()
+
+
+class UNet(EngineModule):
+    _prefix = "mf_unet"
+
+    def __init__(
+        self,
+        in_ch=1,
+        out_ch=1,
+        spatial_dims=3,
+        hid_chs=(256, 256, 512, 1024),
+        kernel_sizes=(3, 3, 3, 3),
+        strides=(1, 2, 2, 2),
+        act_name=("SWISH", {}),
+        norm_name=("GROUP", {"num_groups": 32, "affine": True}),
+        time_embedder=TimeEmbbeding,
+        time_embedder_kwargs=None,
+        cond_embedder=None,
+        cond_embedder_kwargs=None,
+        deep_supervision=True,
+        use_res_block=True,
+        estimate_variance=False,
+        use_self_conditioning=False,
+        dropout=0.0,
+        learnable_interpolation=True,
+        use_attention="none",
+        num_res_blocks=2,
+    ):
+        super().__init__()
+        if spatial_dims != 2:
+            raise NotImplementedError("medfusion_b200.UNet implements the 2-D model (spatial_dims=2)")
+        if not use_res_block:
+            raise NotImplementedError("use_res_block=False (UnetBasicBlock) is not on the accelerated hot path")
+        if deep_supervision not in (False, 0):
+            raise NotImplementedError("deep_supervision heads are training-only; construct with deep_supervision=False")
+        if use_self_conditioning:
+            raise NotImplementedError("use_self_conditioning=True is not implemented yet")
+        if not learnable_interpolation:
+            raise NotImplementedError("learnable_interpolation=False (pooling) is not implemented")
+        if dropout not in (0, 0.0, None):
+            raise NotImplementedError("dropout is identity at inference; construct with dropout=0.0")
+        if _name_of(act_name) != "swish" or _name_of(norm_name) != "group":
+            raise NotImplementedError("only Swish + GroupNorm are implemented")
+        attn = list(use_attention) if isinstance(use_attention, (list, tuple)) else [use_attention] * len(strides)
+        if any(a != "none" for a in attn):
+            raise NotImplementedError("attention ('linear'/'spatial') is not implemented yet; use 'none'")
+        depth = len(strides)
+        if not (len(hid_chs) == len(kernel_sizes) == depth) or depth > _lib.MF_MAX_LEVELS:
+            raise ValueError("hid_chs, kernel_sizes and strides must have equal length <= 8")
+
+        self.use_self_conditioning = use_self_conditioning
+        self.use_res_block = use_res_block
+        self.depth = depth
+        self.num_res_blocks = num_res_blocks
+        self.in_ch, self.out_ch = in_ch, out_ch
+        self.estimate_variance = estimate_variance
+
+        self.time_spec = time_embedder(**dict(time_embedder_kwargs or {})) if time_embedder is not None else None
+        self.cond_spec = cond_embedder(**dict(cond_embedder_kwargs or {})) if cond_embedder is not None else None
+        if self.cond_spec is not None and self.time_spec is None:
+            raise NotImplementedError("a condition embedder without a time embedder is not supported")
+        if self.cond_spec is not None and self.cond_spec.emb_dim != self.time_spec.emb_dim:
+            raise ValueError("cond_embedder emb_dim must equal the time embedding dim")
+
+        cfg = _lib.UNetConfig()
+        cfg.in_ch, cfg.out_ch, cfg.depth = in_ch, (out_ch * 2 if estimate_variance else out_ch), depth
+        for i in range(depth):
+            cfg.hid_chs[i], cfg.kernel_sizes[i], cfg.strides[i] = hid_chs[i], kernel_sizes[i], strides[i]
+            cfg.attention[i] = 0
+        cfg.num_res_blocks = num_res_blocks
+        cfg.emb_dim = self.time_spec.emb_dim if self.time_spec is not None else 0
+        cfg.pos_emb_dim = self.time_spec.pos_emb_dim if self.time_spec is not None else 0
+        cfg.num_classes = self.cond_spec.num_classes if self.cond_spec is not None else 0
+        cfg.norm_groups = dict(norm_name[1]).get("num_groups", 32) if isinstance(norm_name, (tuple, list)) else 32
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().mf_unet_create(ctypes.byref(cfg), ctypes.byref(handle)), "mf_unet_create")
+        # zero-initialised modules of the reference: 2nd conv of every res block (conv_blocks.py:336 -> :174)
+        # and the output head (unet2.py:213)
+        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc."))
+
+    # ------------------------------------------------------------------------------------------
+    def _after_param_sync(self, stream):
+        if self.time_spec is not None:
+            freqs = self.time_spec.pos_embedder.frequencies().to(self.device, torch.float32).contiguous()
+            self._freqs = freqs  # keep alive until the async copy has been enqueued/ordered
+            _lib.check(_lib.load().mf_unet_set_time_freqs(self._h, freqs.data_ptr(), freqs.numel(), stream),
+                       "set_time_freqs")
+
+    def forward(self, x_t, t=None, condition=None, self_cond=None):
+        """x_t [B,C,H,W] fp32, t [B] int64, condition [B] int64 | None  ->  (y [B,out,H,W], [])  (unet2.py:222-269)"""
+        require_cuda(x_t, "UNet.forward(x_t)")
+        if x_t.dim() != 4 or x_t.shape[1] != self.in_ch:
+            raise ValueError(f"x_t must be [B,{self.in_ch},H,W], got {tuple(x_t.shape)}")
+        if self.time_spec is not None and t is None:
+            raise NotImplementedError("t=None with a time embedder is not supported")
+        self.sync_params()
+        B, _, H, W = x_t.shape
+        x = x_t.contiguous().float()
+        tt = None if t is None else t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
+        cc = None
+        if condition is not None and self.cond_spec is not None:
+            cc = condition.to(device=x.device, dtype=torch.int64).contiguous()
+        y = torch.empty((B, self.out_ch * (2 if self.estimate_variance else 1), H, W), device=x.device,
+                        dtype=torch.float32)
+        self._forward_into(x, tt, cc, y)
+        return y, []
+
+    def _forward_into(self, x, t, cond, y):
+        """Hot-loop entry: contiguous CUDA tensors of the right dtype, no checks, no parameter sync."""
+        B, _, H, W = x.shape
+        ws, ws_bytes = self._workspace(B, H, W)
+        _lib.check(_lib.load().mf_unet_forward(self._h, x.data_ptr(), None if t is None else t.data_ptr(),
+                                               None if cond is None else cond.data_ptr(), y.data_ptr(), B, H, W, ws,
+                                               ws_bytes, cuda_stream_ptr()), "mf_unet_forward")

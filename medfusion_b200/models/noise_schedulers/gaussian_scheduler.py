@@ -1,0 +1,148 @@
+"""Gaussian (DDPM) noise scheduler — reverse-process half
+(reference: medical_diffusion/models/noise_schedulers/gaussian_scheduler.py:7-151, scheduler_base.py:5-46).
+
+Buffers are the reference's (same names, fp64 -> fp32), so state_dicts interchange.  The per-step
+arithmetic (x_0 estimate, posterior mean/std, + noise, CFG combine, DDIM-form re-noise) is one fused
+elementwise kernel, `mf_sched_step`; the methods below are thin views of it.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ..._engine import cuda_stream_ptr, require_cuda
+
+_TABLES = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+           "posterior_mean_coef2", "posterior_variance", "betas", "alphas_cumprod")
+
+
+def make_betas(schedule_strategy, timesteps, beta_start, beta_end):
+    """Closed-form beta schedules in fp64 (gaussian_scheduler.py:22-36)."""
+    f64 = torch.float64
+    if schedule_strategy == "linear":
+        return torch.linspace(beta_start, beta_end, timesteps, dtype=f64)
+    if schedule_strategy == "scaled_linear":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, timesteps, dtype=f64) ** 2
+    if schedule_strategy == "cosine":
+        s = 0.008
+        x = torch.linspace(0, timesteps, timesteps + 1, dtype=f64)
+        ac = torch.cos(((x / timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        return torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    raise NotImplementedError(f"{schedule_strategy} does is not implemented for GaussianNoiseScheduler")
+
+
+class BasicNoiseScheduler(nn.Module):
+    def __init__(self, timesteps=1000, T=None):
+        super().__init__()
+        self.timesteps = timesteps
+        self.T = timesteps if T is None else T
+        self.register_buffer("timesteps_array", torch.linspace(0, self.T - 1, self.timesteps, dtype=torch.long))
+
+    @staticmethod
+    def extract(x, t, ndim):
+        return x.gather(0, t).reshape(-1, *((1,) * (ndim - 1)))
+
+
+class GaussianNoiseScheduler(BasicNoiseScheduler):
+    def __init__(self, timesteps=1000, T=None, schedule_strategy="cosine", beta_start=0.0001, beta_end=0.02,
+                 betas=None):
+        super().__init__(timesteps, T)
+        self.schedule_strategy = schedule_strategy
+        b = torch.as_tensor(betas, dtype=torch.float64) if betas is not None else make_betas(
+            schedule_strategy, timesteps, beta_start, beta_end)
+        a = 1 - b
+        ac = torch.cumprod(a, dim=0)
+        ac_prev = torch.cat([torch.ones(1, dtype=torch.float64), ac[:-1]])
+        tables = {
+            "betas": b, "alphas": a, "alphas_cumprod": ac, "alphas_cumprod_prev": ac_prev,
+            "sqrt_alphas_cumprod": ac.sqrt(), "sqrt_one_minus_alphas_cumprod": (1. - ac).sqrt(),
+            "sqrt_recip_alphas_cumprod": (1. / ac).sqrt(), "sqrt_recipm1_alphas_cumprod": (1. / ac - 1).sqrt(),
+            "posterior_mean_coef1": b * ac_prev.sqrt() / (1. - ac),
+            "posterior_mean_coef2": (1. - ac_prev) * a.sqrt() / (1. - ac),
+            "posterior_variance": b * (1. - ac_prev) / (1. - ac),
+        }
+        for name, val in tables.items():  # registration order == gaussian_scheduler.py:46-58
+            self.register_buffer(name, val.to(torch.float32))
+
+    # ------------------------------------------------------------------------------------------
+    def _tables(self):
+        tab = _lib.SchedTables()
+        for n in _TABLES:
+            buf = getattr(self, n)
+            require_cuda(buf, f"scheduler buffer {n}")
+            setattr(tab, n, buf.data_ptr())
+        return tab
+
+    def step(self, x_t, t, pred, *, pred_uncond=None, guidance_scale=1.0, noise=None, t_next=None, noise_ddim=None,
+             objective="x_T", clip_x0=True, want=("x_prior", "x_0", "x_T")):
+        """One fused reverse step. Returns dict with the requested tensors among x_prior, x_0, x_T, x_next."""
+        require_cuda(x_t, "scheduler step")
+        x_t = x_t.contiguous()
+        pred = pred.contiguous()
+        B = x_t.shape[0]
+        chw = x_t[0].numel()
+        t = t.to(device=x_t.device, dtype=torch.int64).expand(B).contiguous()
+        outs = {k: torch.empty_like(x_t) for k in want}
+        if t_next is not None:
+            t_next = t_next.to(device=x_t.device, dtype=torch.int64).reshape(1).contiguous()
+        tab = self._tables()
+
+        def ptr(v):
+            return None if v is None else v.contiguous().data_ptr()
+
+        _lib.check(_lib.load().mf_sched_step(
+            ctypes.byref(tab), x_t.data_ptr(), pred.data_ptr(), ptr(pred_uncond), float(guidance_scale), t.data_ptr(),
+            ptr(noise), ptr(t_next), ptr(noise_ddim), 1 if objective == "x_0" else 0, 1 if clip_x0 else 0,
+            ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")), B, chw,
+            cuda_stream_ptr()), "mf_sched_step")
+        return outs
+
+    # --- reference-named views (gaussian_scheduler.py:80-151) ---------------------------------
+    def estimate_x_t_prior_from_x_T(self, x_t, t, x_T, use_log=True, clip_x0=True, var_scale=0, cold_diffusion=False):
+        self._check_step_opts(use_log, var_scale, cold_diffusion)
+        o = self.step(x_t, t, x_T, noise=self.x_final(x_t), objective="x_T", clip_x0=clip_x0, want=("x_prior", "x_0"))
+        return o["x_prior"], o["x_0"]
+
+    def estimate_x_t_prior_from_x_0(self, x_t, t, x_0, use_log=True, clip_x0=True, var_scale=0, cold_diffusion=False):
+        self._check_step_opts(use_log, var_scale, cold_diffusion)
+        o = self.step(x_t, t, x_0, noise=self.x_final(x_t), objective="x_0", clip_x0=clip_x0, want=("x_prior", "x_0"))
+        return o["x_prior"], o["x_0"]
+
+    def estimate_x_0(self, x_t, x_T, t, clip_x0=True):
+        return self.step(x_t, t, x_T, objective="x_T", clip_x0=clip_x0, want=("x_0",))["x_0"]
+
+    def estimate_x_T(self, x_t, x_0, t, clip_x0=True):
+        return self.step(x_t, t, x_0, objective="x_0", clip_x0=clip_x0, want=("x_T",))["x_T"]
+
+    def estimate_mean_t(self, x_t, x_0, t):
+        # posterior mean == x_prior with zero noise and no clipping of the supplied x_0
+        return self.step(x_t, t, x_0, objective="x_0", clip_x0=False, want=("x_prior",))["x_prior"]
+
+    def estimate_variance_t(self, t, ndim, log=True, var_scale=0, eps=1e-20):
+        lo = self.extract(self.posterior_variance, t, ndim)
+        hi = self.extract(self.betas, t, ndim)
+        if log:
+            lo, hi = torch.log(lo.clamp(min=eps)), torch.log(hi.clamp(min=eps))
+        return var_scale * hi + (1 - var_scale) * lo
+
+    @staticmethod
+    def _check_step_opts(use_log, var_scale, cold_diffusion):
+        if cold_diffusion:
+            raise NotImplementedError("cold_diffusion sampling is not implemented")
+        if not use_log:
+            raise NotImplementedError("use_log=False is not implemented")
+        if not (isinstance(var_scale, (int, float)) and var_scale == 0):
+            raise NotImplementedError("learned variance (var_scale != 0) is not implemented")
+
+    @classmethod
+    def x_final(cls, x):
+        return torch.randn_like(x)
+
+    @classmethod
+    def _clip_x_0(cls, x_0):
+        return x_0.clamp(-1, 1)

@@ -1,0 +1,175 @@
+"""DiffusionPipeline — sampling half, drop-in for
+/root/reference/medical_diffusion/models/pipelines/diffusion_pipeline.py (forward :232-275, denoise :278-310,
+sample :312-317).
+
+Semantics kept exactly: `use_ddim=True` default with eta == 1 (two RNG draws per step, the
+scheduler draw being discarded except on the last step), partial DDPM schedule for `use_ddim=False, steps=k`,
+CFG with two estimator passes, noise drawn with `torch.randn_like` in the reference's order so that a given
+`torch.manual_seed` yields the reference's trajectory.  What changes is where the arithmetic runs: the UNet,
+the scheduler update and the VAE decoder are sm_100a launch plans behind the C ABI, and the loop issues no
+host synchronisation and no progress-bar calls.
+
+Multi-GPU (not in the reference): `sample(..., shard=True)` under torch.distributed partitions
+the batch across ranks with no per-step communication and all-gathers the decoded images once at the end.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..._engine import require_cuda
+
+
+class DiffusionPipeline(nn.Module):
+    def __init__(
+        self,
+        noise_scheduler,
+        noise_estimator,
+        latent_embedder=None,
+        noise_scheduler_kwargs=None,
+        noise_estimator_kwargs=None,
+        latent_embedder_checkpoint="",
+        estimator_objective="x_T",
+        estimate_variance=False,
+        use_self_conditioning=False,
+        classifier_free_guidance_dropout=0.5,
+        num_samples=4,
+        do_input_centering=True,
+        clip_x0=True,
+        use_ema=False,
+        ema_kwargs=None,
+        optimizer=None,
+        optimizer_kwargs=None,
+        lr_scheduler=None,
+        lr_scheduler_kwargs=None,
+        loss=None,
+        loss_kwargs=None,
+        sample_every_n_steps=1000,
+    ):
+        super().__init__()
+        if estimate_variance:
+            raise NotImplementedError("estimate_variance=True (learned variance) is not implemented")
+        if use_self_conditioning:
+            raise NotImplementedError("use_self_conditioning=True is not implemented")
+        if use_ema:
+            raise NotImplementedError("use_ema=True: load the EMA weights into noise_estimator instead")
+        if estimator_objective not in ("x_T", "x_0"):
+            raise ValueError("Unknown Objective")
+        est_kwargs = dict(noise_estimator_kwargs or {})
+        est_kwargs["estimate_variance"] = estimate_variance          # diffusion_pipeline.py:50-51
+        est_kwargs["use_self_conditioning"] = use_self_conditioning
+        self.noise_scheduler = noise_scheduler(**dict(noise_scheduler_kwargs or {}))
+        self.noise_estimator = noise_estimator(**est_kwargs)
+        if latent_embedder is not None:
+            self.latent_embedder = latent_embedder.load_from_checkpoint(latent_embedder_checkpoint)
+            for p in self.latent_embedder.parameters():
+                p.requires_grad = False
+        else:
+            self.latent_embedder = None
+        self.estimator_objective = estimator_objective
+        self.use_self_conditioning = use_self_conditioning
+        self.num_samples = num_samples
+        self.classifier_free_guidance_dropout = classifier_free_guidance_dropout
+        self.do_input_centering = do_input_centering
+        self.estimate_variance = estimate_variance
+        self.clip_x0 = clip_x0
+        self.use_ema = use_ema
+
+    @property
+    def device(self):
+        return self.noise_scheduler.betas.device
+
+    @classmethod
+    def load_from_checkpoint(cls, path, map_location=None, **overrides):
+        ckpt = torch.load(path, map_location=map_location or "cpu", weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        accepted = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
+        model = cls(**{k: v for k, v in hp.items() if k in accepted})
+        sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+        sd = {k: v for k, v in sd.items() if not k.startswith(("ema_model.", "loss_fct."))}
+        model.load_state_dict(sd)
+        return model
+
+    # ---------------------------------------------------------------------------------------------
+    def _predict(self, x_t, t, condition, guidance_scale, un_cond):
+        """Estimator pass(es); returns (pred, pred_uncond|None). CFG combine happens in the step kernel."""
+        est = self.noise_estimator
+        if (condition is not None) and (guidance_scale != 1.0):
+            pred_uncond, _ = est(x_t, t, condition=un_cond, self_cond=None)
+            pred_cond, _ = est(x_t, t, condition=condition, self_cond=None)
+            return pred_cond, pred_uncond
+        pred, _ = est(x_t, t, condition=condition, self_cond=None)
+        return pred, None
+
+    def forward(self, x_t, t, condition=None, self_cond=None, guidance_scale=1.0, cold_diffusion=False, un_cond=None):
+        """-> (x_t_prior, x_0, x_T, self_cond)   (diffusion_pipeline.py:232-275)"""
+        if cold_diffusion:
+            raise NotImplementedError("cold_diffusion sampling is not implemented")
+        require_cuda(x_t, "DiffusionPipeline.forward(x_t)")
+        pred, pred_u = self._predict(x_t, t, condition, guidance_scale, un_cond)
+        noise = self.noise_scheduler.x_final(x_t)
+        o = self.noise_scheduler.step(x_t, t, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
+                                      objective=self.estimator_objective, clip_x0=self.clip_x0,
+                                      want=("x_prior", "x_0", "x_T"))
+        self_cond_out = o["x_T"] if self.estimator_objective == "x_0" else o["x_0"]
+        return o["x_prior"], o["x_0"], o["x_T"], self_cond_out
+
+    @torch.no_grad()
+    def denoise(self, x_t, steps=None, condition=None, use_ddim=True, **kwargs):
+        """Reverse loop + latent decode (diffusion_pipeline.py:278-310)."""
+        noise_fn = kwargs.pop("_noise_fn", None) or self.noise_scheduler.x_final
+        unknown = set(kwargs) - {"guidance_scale", "un_cond", "cold_diffusion"}
+        if unknown:  # the reference forwards **kwargs to forward(), which raises TypeError on anything else
+            raise TypeError(f"forward() got an unexpected keyword argument '{sorted(unknown)[0]}'")
+        if kwargs.get("cold_diffusion", False):
+            raise NotImplementedError("cold_diffusion sampling is not implemented")
+        guidance_scale = kwargs.get("guidance_scale", 1.0)
+        un_cond = kwargs.get("un_cond", None)
+        require_cuda(x_t, "DiffusionPipeline.denoise(x_t)")
+        sched = self.noise_scheduler
+        if use_ddim:
+            steps = sched.timesteps if steps is None else steps
+            timesteps_array = torch.linspace(0, sched.T - 1, steps, dtype=torch.long, device=x_t.device)
+        else:
+            timesteps_array = sched.timesteps_array[slice(0, steps)]
+            steps = len(timesteps_array)
+        B = x_t.shape[0]
+        x_t = x_t.contiguous().float()
+        ts = timesteps_array.flip(0)
+        for i in range(steps):
+            t = ts[i]
+            tb = t.expand(B)
+            pred, pred_u = self._predict(x_t, tb, condition, guidance_scale, un_cond)
+            noise = noise_fn(x_t)                             # scheduler draw (gaussian_scheduler.py:99)
+            ddim = use_ddim and (steps - i - 1 > 0)
+            if ddim:
+                noise2 = noise_fn(x_t)                        # DDIM draw (diffusion_pipeline.py:303)
+                o = sched.step(x_t, tb, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
+                               t_next=timesteps_array[steps - i - 2], noise_ddim=noise2,
+                               objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",))
+            else:
+                o = sched.step(x_t, tb, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
+                               objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",))
+            x_t = o["x_next"]
+        if self.latent_embedder is not None:
+            x_t = self.latent_embedder.decode(x_t)
+        return x_t
+
+    @torch.no_grad()
+    def sample(self, num_samples, img_size, condition=None, shard=False, **kwargs):
+        """x_T ~ N(0, I) -> denoise -> images (diffusion_pipeline.py:312-317).
+
+        shard=True (torch.distributed initialised): every rank draws the FULL-batch noise stream (so seeds match
+        the single-GPU result), keeps its contiguous slice of the batch, and the decoded images are all-gathered
+        once at the end — no per-step collective.
+        """
+        template = torch.zeros((num_samples, *img_size), device=self.device)
+        if shard:
+            from ...parallel import sharded_sample
+            return sharded_sample(self, template, condition, **kwargs)
+        x_T = self.noise_scheduler.x_final(template)
+        return self.denoise(x_T, condition=condition, **kwargs)
+
+    def interpolate(self, *a, **k):
+        raise NotImplementedError("interpolate() needs the forward diffusion (training side); out of scope")

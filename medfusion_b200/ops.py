@@ -58,7 +58,7 @@ def conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride=1) -> bool:
     return bool(_lib.load().mf_op_conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride))
 
 
-def conv_tc(src0, w_planes, bias, ksize, src1=None, split_out=False, want_stats=False):
+def conv_tc(src0, w_planes, bias, ksize, src1=None, split_out=False, want_stats=False, drain_interval=0):
     """src*: split tensors [2,N,H,W,C]; returns (out, stats or None)."""
     _, N, H, W, C0 = src0.shape
     C1 = 0 if src1 is None else src1.shape[-1]
@@ -72,7 +72,7 @@ def conv_tc(src0, w_planes, bias, ksize, src1=None, split_out=False, want_stats=
     _lib.check(_lib.load().mf_op_conv_tc(
         _p(src0), src0[0].numel(), C0, _p(src1), 0 if src1 is None else src1[0].numel(), C1, N, H, W,
         _p(w_planes), Cout, ksize, _p(bias), _p(out), out[0].numel() if split_out else 0,
-        NHWC_SPLIT if split_out else NHWC_RAW, _p(stats), _stream()), "conv_tc")
+        NHWC_SPLIT if split_out else NHWC_RAW, _p(stats), drain_interval, _stream()), "conv_tc")
     return out, stats
 
 

@@ -28,6 +28,14 @@ CASES = {
     "tc_3x3_64": dict(kind="tc", N=1, H=64, W=64, C0=64, C1=0, Cout=128, k=3, stats=True, split=True),
     "tc_3x3_256w": dict(kind="tc", N=1, H=8, W=256, C0=32, C1=0, Cout=64, k=3, stats=True),
     "tc_1x1_cat_512": dict(kind="tc", N=2, H=16, W=16, C0=512, C1=512, Cout=512, k=1),
+    "tc_drain_sweep": dict(kind="tc_sweep", N=2, H=32, W=32, C0=256, C1=0, Cout=256, k=3),
+    "tc_drain_sweep_8": dict(kind="tc_sweep", N=4, H=8, W=8, C0=1024, C1=1024, Cout=1024, k=3),
+    "perf_32_256": dict(kind="perf", N=64, H=32, W=32, C0=256, C1=0, Cout=256, k=3),
+    "perf_16_512": dict(kind="perf", N=64, H=16, W=16, C0=512, C1=0, Cout=512, k=3),
+    "perf_8_1024": dict(kind="perf", N=64, H=8, W=8, C0=1024, C1=0, Cout=1024, k=3),
+    "perf_8_cat": dict(kind="perf", N=64, H=8, W=8, C0=1024, C1=1024, Cout=1024, k=3),
+    "perf_vae_128": dict(kind="perf", N=16, H=128, W=128, C0=128, C1=0, Cout=128, k=3),
+    "perf_vae_256": dict(kind="perf", N=8, H=256, W=256, C0=64, C1=0, Cout=64, k=3),
     "norm": dict(kind="norm"),
     "upsample": dict(kind="upsample"),
 }
@@ -88,6 +96,46 @@ def run_case(name):
             st = stats.sum(dim=1)
             res["stats_sum_err"] = float((st[..., 0] - s_ref).abs().max())
             res["stats_sumsq_relerr"] = float(((st[..., 1] - ss_ref).abs() / ss_ref.abs().clamp_min(1e-6)).max())
+    elif c["kind"] in ("tc_sweep", "perf"):
+        C = c["C0"] + c["C1"]
+        x = rnd(c["N"], C, c["H"], c["W"])
+        w = rnd(c["Cout"], C, c["k"], c["k"], scale=0.05)
+        b = rnd(c["Cout"])
+        s0 = ops.pack_split(x[:, :c["C0"]].contiguous())
+        s1 = ops.pack_split(x[:, c["C0"]:].contiguous()) if c["C1"] else None
+        wp = ops.prep_weight_tc(w)
+        flops = 2.0 * c["N"] * c["H"] * c["W"] * c["Cout"] * C * c["k"] ** 2
+        res["sweep"] = {}
+        ref = None
+        if c["kind"] == "tc_sweep":
+            ref = F.conv2d(x.double(), w.double(), b.double(), padding=c["k"] // 2)
+            r32 = F.conv2d(x, w, b, padding=c["k"] // 2)
+            res["torch_fp32_vs_fp64"] = float((r32.double() - ref).abs().max())
+        for di in ([1, 2, 4, 8, 1000] if c["kind"] == "tc_sweep" else [1, 4, 1000]):
+            out, _ = ops.conv_tc(s0, wp, b, c["k"], src1=s1, drain_interval=di)
+            torch.cuda.synchronize()
+            ent = {}
+            if ref is not None:
+                d = (ops.unpack_nchw(out).double() - ref).abs()
+                ent["max_abs"] = float(d.max())
+                ent["mean_abs"] = float(d.mean())
+                ent["viol"] = int((d > 1e-5 + 1e-3 * ref.abs()).sum())
+                ent["ref_rms"] = float(ref.pow(2).mean().sqrt())
+            else:
+                st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for _ in range(3):
+                    ops.conv_tc(s0, wp, b, c["k"], src1=s1, drain_interval=di)
+                st.record()
+                iters = 10
+                for _ in range(iters):
+                    ops.conv_tc(s0, wp, b, c["k"], src1=s1, drain_interval=di)
+                en.record()
+                torch.cuda.synchronize()
+                ms = st.elapsed_time(en) / iters
+                ent["ms"] = round(ms, 4)
+                ent["tflops_alg"] = round(flops / ms / 1e9, 1)
+            res["sweep"][str(di)] = ent
+        res["viol"] = 0
     elif c["kind"] == "norm":
         N, Cc, H, W, G = 2, 64, 16, 16, 8
         x = rnd(N, Cc, H, W) * 2 + 0.5
