@@ -21,6 +21,21 @@ def require_cuda(t: torch.Tensor, what: str):
             "There is no CPU fallback; move the module and its inputs to a B200.")
 
 
+class _Handle:
+    """Owns one C engine object; destroyed when the owning module is garbage collected."""
+
+    def __init__(self, ptr, destroy):
+        self.ptr, self._destroy = ptr, destroy
+
+    def __del__(self):
+        try:
+            if self.ptr and self._destroy is not None:
+                self._destroy(self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
+
+
 class EngineModule(nn.Module):
     """nn.Module whose parameters mirror a C engine's registry and whose compute is the engine's."""
 
@@ -28,6 +43,7 @@ class EngineModule(nn.Module):
 
     def _engine_init(self, handle, zero_init=()):
         lib = _lib.load()
+        self._handle = _Handle(handle, getattr(lib, f"{self._prefix}_destroy"))
         self._h = handle
         self._ws = {}          # (B,H,W) -> uint8 workspace tensor
         self._synced_sig = None
@@ -41,15 +57,6 @@ class EngineModule(nn.Module):
             entries.append((name, tuple(int(shape[k]) for k in range(ndim.value))))
         self._entries = entries
         build_param_tree(self, entries, zero_init=zero_init)
-
-    def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            try:
-                getattr(_lib.load(), f"{self._prefix}_destroy")(h)
-            except Exception:
-                pass
-            self._h = None
 
     @property
     def device(self):

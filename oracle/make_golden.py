@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on CPU fp32.
+
+Run in the build container only (the reference is not present on the GPU box):
+    python oracle/make_golden.py
+Third-party packages the reference imports but that are not installable offline (monai, pytorch_lightning,
+streamlit, lpips, pytorch_msssim) are provided by oracle/shims/ — minimal stand-ins for the symbols used.
+Weights are NOT stored: both sides regenerate them from medfusion_b200.synthetic (per-key seeded), which also
+overwrites the reference's zero-initialised tensors (SURVEY.md finding 4).  Noise is injected by replacing
+torch.randn_like with a recording seeded CPU generator, so trajectories are reproducible on any device.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), "/root/reference", ROOT]
+
+import torch  # noqa: E402
+
+from medfusion_b200.synthetic import fill_  # noqa: E402  (RNG recipe only, no compute)
+from medical_diffusion.models.estimators import UNet  # noqa: E402
+from medical_diffusion.models.embedders import TimeEmbbeding, LabelEmbedder  # noqa: E402
+from medical_diffusion.models.embedders.latent_embedders import VAE  # noqa: E402
+from medical_diffusion.models.noise_schedulers import GaussianNoiseScheduler  # noqa: E402
+from medical_diffusion.models.pipelines import DiffusionPipeline  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(8)
+
+UNET_SMALL = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[64, 64, 128, 256], kernel_sizes=[3, 3, 3, 3],
+                  strides=[1, 2, 2, 2], norm_name=("GROUP", {"num_groups": 8, "affine": True}),
+                  time_embedder_kwargs={"emb_dim": 256}, cond_embedder_kwargs={"emb_dim": 256, "num_classes": 2},
+                  deep_supervision=False, use_res_block=True, use_attention="none")
+UNET_CANON = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
+                  strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
+                  cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False,
+                  use_res_block=True, use_attention="none")
+VAE_CANON = dict(in_channels=3, out_channels=3, emb_channels=8, spatial_dims=2, hid_chs=[64, 128, 256, 512],
+                 kernel_sizes=[3, 3, 3, 3], strides=[1, 2, 2, 2], deep_supervision=1, use_attention="none")
+VAE_SMALL = dict(in_channels=3, out_channels=3, emb_channels=8, spatial_dims=2, hid_chs=[64, 128],
+                 kernel_sizes=[3, 3], strides=[1, 2], deep_supervision=False, use_attention="none")
+SCHED = dict(timesteps=1000, beta_start=0.002, beta_end=0.02, schedule_strategy="scaled_linear")
+
+
+def fresh(cfg):
+    """Deep-ish copy; also hands TimeEmbbeding a FRESH pos_embedder_kwargs dict: the reference mutates its
+    mutable default argument (time_embedder.py:57,63), which would leak the first model's sinusoidal width
+    into every later model built in the same process."""
+    kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}
+    kw["time_embedder_kwargs"] = dict(kw["time_embedder_kwargs"], pos_embedder_kwargs={})
+    return kw
+
+
+def make_unet(cfg):
+    kw = fresh(cfg)
+    m = UNet(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder, **kw).eval()
+    return fill_(m)
+
+
+def gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+@torch.no_grad()
+def unet_fixture(name, cfg, seed):
+    m = make_unet(cfg)
+    g = gen(seed)
+    x = torch.randn(2, 8, 32, 32, generator=g)
+    t = torch.tensor([999, 17])
+    c = torch.tensor([1, 0])
+    y_c, _ = m(x, t, c)
+    y_u, _ = m(x, t, None)
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    torch.save(dict(cfg=cfg, x=x, t=t, cond=c, y_cond=y_c, y_uncond=y_u, keys=keys), os.path.join(OUT, name))
+    print(name, float(y_c.abs().max()), float(y_u.abs().max()))
+
+
+@torch.no_grad()
+def vae_fixture():
+    m = fill_(VAE(loss=torch.nn.MSELoss, **VAE_CANON).eval())
+    z = torch.randn(1, 8, 32, 32, generator=gen(11))
+    x = m.decode(z)
+    z2 = torch.randn(3, 8, 8, 8, generator=gen(12))
+    x2 = m.decode(z2)
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    torch.save(dict(cfg=VAE_CANON, z=z, x=x, z2=z2, x2=x2, keys=keys), os.path.join(OUT, "vae_canonical.pt"))
+    print("vae", float(x.abs().max()), float(x2.abs().max()))
+
+
+@torch.no_grad()
+def sched_fixture():
+    s = GaussianNoiseScheduler(**SCHED)
+    g = gen(21)
+    x_t = torch.randn(5, 8, 16, 16, generator=g)
+    pred = torch.randn(5, 8, 16, 16, generator=g)
+    noise = torch.randn(5, 8, 16, 16, generator=g)
+    t = torch.tensor([999, 500, 37, 1, 0])
+    out = {}
+    orig = torch.randn_like
+    torch.randn_like = lambda x, **k: noise.clone()
+    try:
+        for clip in (False, True):
+            p, x0 = s.estimate_x_t_prior_from_x_T(x_t, t, pred, clip_x0=clip, var_scale=0)
+            out[f"xT_clip{int(clip)}"] = dict(prior=p, x_0=x0)
+            p, x0 = s.estimate_x_t_prior_from_x_0(x_t, t, pred, clip_x0=clip, var_scale=0)
+            xT = s.estimate_x_T(x_t, x_0=pred, t=t, clip_x0=clip)
+            out[f"x0_clip{int(clip)}"] = dict(prior=p, x_0=x0, x_T=xT)
+    finally:
+        torch.randn_like = orig
+    buffers = {k: v.clone() for k, v in s.state_dict().items()}
+    torch.save(dict(sched=SCHED, x_t=x_t, pred=pred, noise=noise, t=t, out=out, buffers=buffers),
+               os.path.join(OUT, "sched.pt"))
+    print("sched ok")
+
+
+@torch.no_grad()
+def sample_fixture():
+    pipe = DiffusionPipeline(noise_scheduler=GaussianNoiseScheduler, noise_estimator=UNet, latent_embedder=None,
+                             noise_scheduler_kwargs=dict(SCHED),
+                             noise_estimator_kwargs=dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder,
+                                                         **fresh(UNET_SMALL)),
+                             estimator_objective="x_T", estimate_variance=False, use_self_conditioning=False,
+                             use_ema=False, do_input_centering=False, clip_x0=False).eval()
+    fill_(pipe.noise_estimator)
+    pipe.latent_embedder = fill_(VAE(loss=torch.nn.MSELoss, **VAE_SMALL).eval())
+    cases = {
+        "ddim5": dict(n=2, kw=dict(steps=5, use_ddim=True)),
+        "ddpm4": dict(n=2, kw=dict(steps=4, use_ddim=False)),
+        "cfg_ddim3": dict(n=2, kw=dict(steps=3, use_ddim=True, guidance_scale=3.0), cond=torch.tensor([0, 1])),
+        "cond_ddim3_g1": dict(n=2, kw=dict(steps=3, use_ddim=True, guidance_scale=1.0), cond=torch.tensor([1, 0])),
+    }
+    out = {}
+    orig = torch.randn_like
+    for name, c in cases.items():
+        g = gen(100 + len(out))
+        rec = []
+
+        def fake(x, **k):
+            n = torch.randn(x.shape, generator=g, dtype=x.dtype)
+            rec.append(n)
+            return n.clone()
+
+        torch.randn_like = fake
+        try:
+            img = pipe.sample(c["n"], (8, 32, 32), condition=c.get("cond"), **c["kw"])
+        finally:
+            torch.randn_like = orig
+        out[name] = dict(kw=c["kw"], cond=c.get("cond"), noises=torch.stack(rec), image=img)
+        print("sample", name, len(rec), "draws", float(img.abs().max()))
+    torch.save(dict(unet_cfg=UNET_SMALL, vae_cfg=VAE_SMALL, sched=SCHED, cases=out),
+               os.path.join(OUT, "sample_small.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    unet_fixture("unet_small.pt", UNET_SMALL, 1)
+    unet_fixture("unet_canonical.pt", UNET_CANON, 2)
+    vae_fixture()
+    sched_fixture()
+    sample_fixture()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

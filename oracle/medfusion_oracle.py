@@ -1,0 +1,221 @@
+"""CPU ORACLE — test infrastructure, NOT product code.
+
+A plain-PyTorch (CPU, fp32) restatement of the reference's sampling hot path, written as pure
+functions over a reference-format state_dict.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this file; the product package never does.
+
+The arithmetic of the reference lives in torch ops (ATen/oneDNN), so the restatement uses the same
+functional ops (F.conv2d, F.group_norm, F.linear, F.interpolate); every function cites the reference
+lines it follows (paths relative to /root/reference/medical_diffusion/).  Pinned by tests/golden/*:
+fixtures produced by running the UNMODIFIED reference in the build container (oracle/make_golden.py)
+— the reference's own tests contain no assertions or golden vectors, so this is the only
+pin available.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def swish(x):
+    # monai Swish: x * sigmoid(alpha*x), alpha = 1 (models/utils/conv_blocks.py:191 via get_act_layer)
+    return x * torch.sigmoid(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# conv blocks
+# ------------------------------------------------------------------------------------------------
+def conv2d(sd, pre, x, stride=1):
+    w = sd[pre + ".weight"]
+    k = w.shape[-1]
+    # padding = get_padding(k, stride) = (k - stride + 1) // 2   (conv_blocks.py:168, :47)
+    return F.conv2d(x, w, sd[pre + ".bias"], stride=stride, padding=(k - stride + 1) // 2)
+
+
+def basic_block(sd, pre, x, groups):
+    """BasicBlock.forward: conv -> GroupNorm -> (Dropout p=0) -> Swish   (models/utils/conv_blocks.py:184-192)"""
+    out = conv2d(sd, pre + ".conv", x)
+    if pre + ".norm.weight" in sd:
+        out = F.group_norm(out, groups, sd[pre + ".norm.weight"], sd[pre + ".norm.bias"], eps=1e-5)
+        out = swish(out)
+    return out
+
+
+def basic_res_block(sd, pre, x, groups):
+    """BasicResBlock.forward: basic_block(x) + (conv_res(x) | x)   (models/utils/conv_blocks.py:236-240)"""
+    out = basic_block(sd, pre + ".basic_block", x, groups)
+    res = conv2d(sd, pre + ".conv_res", x) if pre + ".conv_res.weight" in sd else x
+    return out + res
+
+
+def unet_res_block(sd, pre, x, emb, groups):
+    """UnetResBlock.forward (models/utils/conv_blocks.py:347-364): emb added after the first half only."""
+    e = None
+    if emb is not None and pre + ".local_embedder.1.weight" in sd:
+        e = F.linear(swish(emb), sd[pre + ".local_embedder.1.weight"], sd[pre + ".local_embedder.1.bias"])
+        e = e[:, :, None, None]
+    x = basic_res_block(sd, pre + ".block_seq.0", x, groups)
+    if e is not None:
+        x = x + e
+    x = basic_res_block(sd, pre + ".block_seq.1", x, groups)
+    return x
+
+
+def basic_up(sd, pre, x, factor=2):
+    """BasicUp.forward: F.interpolate(nearest-exact, x2) then conv3x3 s1 p1  (models/utils/conv_blocks.py:121-131)"""
+    if factor != 1:
+        x = F.interpolate(x, size=(x.shape[2] * factor, x.shape[3] * factor), mode="nearest-exact")
+    return conv2d(sd, pre, x)
+
+
+# ------------------------------------------------------------------------------------------------
+# embedders
+# ------------------------------------------------------------------------------------------------
+def sinusoidal(t, dim, max_period=10000, shift=1):
+    """SinusoidalPosEmb.forward (models/embedders/time_embedder.py:15-28)"""
+    half = dim // 2
+    e = math.log(max_period) / (half - shift)
+    e = torch.exp(-e * torch.arange(half))
+    e = t[:, None] * e[None, :]
+    return torch.cat((e.sin(), e.cos()), dim=-1)
+
+
+def time_embedding(sd, t, pos_dim):
+    """TimeEmbbeding.forward: sinus -> Linear -> Swish -> Linear (models/embedders/time_embedder.py:67-75)"""
+    h = sinusoidal(t, pos_dim)
+    h = F.linear(h, sd["time_embedder.time_emb.1.weight"], sd["time_embedder.time_emb.1.bias"])
+    h = swish(h)
+    return F.linear(h, sd["time_embedder.time_emb.3.weight"], sd["time_embedder.time_emb.3.bias"])
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet (models/estimators/unet2.py:222-269), attention 'none'
+# ------------------------------------------------------------------------------------------------
+def unet_forward(sd, cfg, x_t, t, cond=None):
+    """cfg: dict(hid_chs, strides, num_res_blocks, groups, pos_emb_dim). Returns y (y_ver is empty)."""
+    hid, strides, nrb, G = cfg["hid_chs"], cfg["strides"], cfg.get("num_res_blocks", 2), cfg.get("groups", 32)
+    depth = len(hid)
+    emb = time_embedding(sd, t, cfg["pos_emb_dim"])                                   # unet2.py:233
+    if cond is not None and "cond_embedder.embedding.weight" in sd:
+        emb = emb + F.embedding(cond, sd["cond_embedder.embedding.weight"])            # unet2.py:239-241
+    xs = [conv2d(sd, "in_conv.conv", x_t, stride=strides[0])]                          # unet2.py:249
+    idx = 0
+    for i in range(1, depth):                                                          # unet2.py:250-251
+        for _ in range(nrb):
+            xs.append(unet_res_block(sd, f"in_blocks.{idx}.0", xs[-1], emb, G))
+            idx += 1
+        if i < depth - 1:
+            xs.append(conv2d(sd, f"in_blocks.{idx}.down_op", xs[-1], stride=strides[i]))  # conv_blocks.py:66-70
+            idx += 1
+    h = unet_res_block(sd, "middle_block.0", xs[-1], emb, G)                           # unet2.py:254
+    h = unet_res_block(sd, "middle_block.2", h, emb, G)
+    n_out = (depth - 1) * (nrb + 1)
+    for i in range(n_out, 0, -1):                                                      # unet2.py:258-264
+        h = torch.cat([h, xs.pop()], dim=1)
+        pre = f"out_blocks.{i - 1}"
+        h = unet_res_block(sd, pre + ".0", h, emb, G)
+        if pre + ".2.up_op.weight" in sd:
+            level = (i - 1) // (nrb + 1) + 1
+            h = basic_up(sd, pre + ".2.up_op", h, strides[level])
+    return conv2d(sd, "outc.conv.conv", h)                                             # unet2.py:267
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE.decode (models/embedders/latent_embedders.py:764-769; UpBlock.forward conv_blocks.py:510-528)
+# ------------------------------------------------------------------------------------------------
+def vae_decode(sd, cfg, z):
+    G, depth = cfg.get("groups", 8), len(cfg["hid_chs"])
+    h = unet_res_block(sd, "inc_dec", z, None, G)
+    for i in range(depth - 1, 0, -1):
+        pre = f"decoders.{i - 1}"
+        h = basic_up(sd, pre + ".up_op.up_op", h, cfg["strides"][i])
+        h = unet_res_block(sd, pre + ".conv_block", h, None, G)
+    return conv2d(sd, "outc.conv", h)
+
+
+# ------------------------------------------------------------------------------------------------
+# scheduler (models/noise_schedulers/gaussian_scheduler.py)
+# ------------------------------------------------------------------------------------------------
+def scheduler_tables(timesteps=1000, schedule="scaled_linear", beta_start=0.002, beta_end=0.02):
+    """gaussian_scheduler.py:22-58 (fp64 tables cast to fp32)"""
+    f64 = torch.float64
+    if schedule == "linear":
+        betas = torch.linspace(beta_start, beta_end, timesteps, dtype=f64)
+    elif schedule == "scaled_linear":
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, timesteps, dtype=f64) ** 2
+    elif schedule == "cosine":
+        s = 0.008
+        x = torch.linspace(0, timesteps, timesteps + 1, dtype=f64)
+        ac = torch.cos(((x / timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    else:
+        raise NotImplementedError(schedule)
+    alphas = 1 - betas
+    ac = torch.cumprod(alphas, dim=0)
+    ac_prev = F.pad(ac[:-1], (1, 0), value=1.)
+    tabs = dict(
+        betas=betas, alphas=alphas, alphas_cumprod=ac, alphas_cumprod_prev=ac_prev,
+        sqrt_alphas_cumprod=torch.sqrt(ac), sqrt_one_minus_alphas_cumprod=torch.sqrt(1. - ac),
+        sqrt_recip_alphas_cumprod=torch.sqrt(1. / ac), sqrt_recipm1_alphas_cumprod=torch.sqrt(1. / ac - 1),
+        posterior_mean_coef1=betas * torch.sqrt(ac_prev) / (1. - ac),
+        posterior_mean_coef2=(1. - ac_prev) * torch.sqrt(alphas) / (1. - ac),
+        posterior_variance=betas * (1. - ac_prev) / (1. - ac))
+    return {k: v.to(torch.float32) for k, v in tabs.items()}
+
+
+def _ext(tab, t, ndim):
+    return tab.gather(0, t).reshape(-1, *((1,) * (ndim - 1)))  # scheduler_base.py:43-46
+
+
+def sched_step(tabs, x_t, t, pred, noise, objective="x_T", clip_x0=False):
+    """estimate_x_t_prior_from_x_T/_x_0 with var_scale = 0 (gaussian_scheduler.py:80-124). Returns (prior, x_0, x_T)."""
+    nd = x_t.ndim
+    if objective == "x_T":
+        x_0 = _ext(tabs["sqrt_recip_alphas_cumprod"], t, nd) * x_t - _ext(tabs["sqrt_recipm1_alphas_cumprod"], t, nd) * pred
+        x_0 = x_0.clamp(-1, 1) if clip_x0 else x_0
+        x_T = pred
+    else:
+        x_0 = pred.clamp(-1, 1) if clip_x0 else pred
+        x_T = (_ext(tabs["sqrt_recip_alphas_cumprod"], t, nd) * x_t - x_0) / _ext(tabs["sqrt_recipm1_alphas_cumprod"], t, nd)
+    mean = _ext(tabs["posterior_mean_coef1"], t, nd) * x_0 + _ext(tabs["posterior_mean_coef2"], t, nd) * x_t
+    logvar = torch.log(_ext(tabs["posterior_variance"], t, nd).clamp(min=1e-20))
+    std = torch.exp(0.5 * logvar)
+    std[t == 0] = 0.0
+    return mean + std * noise, x_0, x_T
+
+
+def ddim_renoise(tabs, x_0, x_T, t, t_next, noise):
+    """diffusion_pipeline.py:297-304 with eta == 1 (t, t_next: 0-dim long tensors)"""
+    a, an = tabs["alphas_cumprod"][t], tabs["alphas_cumprod"][t_next]
+    sigma = ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
+    c = (1 - an - sigma ** 2).sqrt()
+    return x_0 * an.sqrt() + c * x_T + sigma * noise
+
+
+def denoise(unet_fn, tabs, x_T, noises, steps, use_ddim=True, guidance_scale=1.0, cond=None, un_cond=None,
+            objective="x_T", clip_x0=False, T=1000):
+    """DiffusionPipeline.denoise without the latent decode (diffusion_pipeline.py:278-304).
+    `noises` is an iterator yielding the successive randn_like draws (scheduler draw, then DDIM draw)."""
+    noises = iter(noises)
+    if use_ddim:
+        ts_arr = torch.linspace(0, T - 1, steps, dtype=torch.long)
+    else:
+        ts_arr = torch.linspace(0, T - 1, T, dtype=torch.long)[:steps]
+        steps = len(ts_arr)
+    x_t = x_T
+    B = x_t.shape[0]
+    for i, t in enumerate(ts_arr.flip(0)):
+        tb = t.expand(B)
+        if cond is not None and guidance_scale != 1.0:                  # diffusion_pipeline.py:240-244
+            pu = unet_fn(x_t, tb, un_cond)
+            pc = unet_fn(x_t, tb, cond)
+            pred = pu + guidance_scale * (pc - pu)
+        else:
+            pred = unet_fn(x_t, tb, cond)
+        x_t, x_0, x_Te = sched_step(tabs, x_t, tb, pred, next(noises), objective, clip_x0)
+        if use_ddim and (steps - i - 1 > 0):
+            x_t = ddim_renoise(tabs, x_0, x_Te, t, ts_arr[steps - i - 2], next(noises))
+    return x_t

@@ -1,0 +1,165 @@
+"""GPU: kernel-level parity through the C ABI against the CPU oracle ops (rtol=1e-3, atol=1e-5)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rnd(g, *shape, scale=1.0):
+    return torch.randn(*shape, generator=g) * scale
+
+
+# every distinct conv shape of the canonical UNet + the VAE decoder levels, small batch
+TC_SHAPES = [
+    # (N, H, W, C0, C1, Cout, k)
+    (2, 32, 32, 256, 0, 256, 3), (2, 32, 32, 256, 256, 256, 3), (2, 32, 32, 256, 256, 256, 1),
+    (2, 16, 16, 256, 0, 512, 3), (2, 16, 16, 256, 0, 256, 3), (2, 16, 16, 512, 0, 512, 3),
+    (2, 16, 16, 512, 256, 256, 3), (2, 16, 16, 512, 512, 512, 3), (2, 16, 16, 256, 0, 512, 1),
+    (2, 16, 16, 512, 256, 256, 1), (2, 16, 16, 512, 512, 512, 1),
+    (3, 8, 8, 512, 0, 1024, 3), (3, 8, 8, 512, 0, 512, 3), (3, 8, 8, 1024, 0, 1024, 3),
+    (3, 8, 8, 1024, 512, 512, 3), (3, 8, 8, 1024, 1024, 1024, 3), (3, 8, 8, 512, 0, 1024, 1),
+    (3, 8, 8, 1024, 512, 512, 1), (3, 8, 8, 1024, 1024, 1024, 1),
+    (1, 32, 32, 512, 0, 512, 3), (1, 64, 64, 512, 0, 256, 3), (1, 64, 64, 256, 0, 256, 3),
+    (1, 128, 128, 256, 0, 128, 3), (1, 128, 128, 128, 0, 128, 3), (1, 256, 256, 128, 0, 64, 3),
+    (1, 256, 256, 64, 0, 64, 3),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_matches_oracle(shape):
+    from medfusion_b200 import ops
+    N, H, W, C0, C1, Cout, k = shape
+    g = torch.Generator().manual_seed(hash(shape) % 2 ** 31)
+    C = C0 + C1
+    x = _rnd(g, N, C, H, W)
+    w = _rnd(g, Cout, C, k, k, scale=1.0 / (C * k * k) ** 0.5)
+    b = _rnd(g, Cout, scale=0.1)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    s0 = ops.pack_split(xd[:, :C0].contiguous())
+    s1 = ops.pack_split(xd[:, C0:].contiguous()) if C1 else None
+    assert ops.conv_tc_supported(N, H, W, C0, C1, Cout, k)
+    out, stats = ops.conv_tc(s0, ops.prep_weight_tc(wd), bd, k, src1=s1, want_stats=True)
+    assert_close(ops.unpack_nchw(out).cpu(), ref, what=f"conv_tc {shape}")
+    # GroupNorm partial sums written by the epilogue: (sum, sumsq) over 8-channel slabs
+    r8 = ref.double().view(N, Cout // 8, 8, -1)
+    st = stats.double().sum(dim=1).cpu()
+    assert_close(st[..., 0], r8.sum(dim=(2, 3)), 1e-3, 1e-2, "stats sum")
+    assert_close(st[..., 1], (r8 * r8).sum(dim=(2, 3)), 1e-4, 1e-3, "stats sumsq")
+    # split-plane output variant reconstructs the same values
+    out2, _ = ops.conv_tc(s0, ops.prep_weight_tc(wd), bd, k, src1=s1, split_out=True)
+    assert torch.equal(ops.unpack_nchw(out2), ops.unpack_nchw(out))
+
+
+def test_conv_tc_ragged_batch_tail():
+    """8x8 maps pack two samples per 128-row tile; an odd batch exercises the zero-filled / masked tail."""
+    from medfusion_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x, w, b = _rnd(g, 5, 64, 8, 8), _rnd(g, 64, 64, 3, 3, scale=0.05), _rnd(g, 64)
+    ref = F.conv2d(x, w, b, padding=1)
+    out, stats = ops.conv_tc(ops.pack_split(x.to(DEV)), ops.prep_weight_tc(w.to(DEV)), b.to(DEV), 3, want_stats=True)
+    assert_close(ops.unpack_nchw(out).cpu(), ref, what="ragged tail")
+    assert_close(stats.sum(dim=1)[..., 0].cpu().double(), ref.double().view(5, 8, 8, -1).sum(dim=(2, 3)), 1e-3, 1e-2)
+
+
+SIMT_SHAPES = [
+    # (N, Cin, H, W, Cout, k, stride, in_layout, out_layout)
+    (2, 8, 32, 32, 256, 3, 1, 0, 2), (2, 256, 32, 32, 256, 3, 2, 2, 2), (2, 512, 16, 16, 512, 3, 2, 2, 2),
+    (2, 256, 32, 32, 8, 1, 1, 2, 0), (1, 8, 32, 32, 512, 3, 1, 0, 1), (1, 8, 32, 32, 512, 1, 1, 0, 1),
+    (1, 64, 64, 64, 3, 1, 1, 2, 0), (3, 24, 7, 5, 40, 3, 1, 0, 1),
+]
+
+
+@pytest.mark.parametrize("shape", SIMT_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_simt_matches_oracle(shape):
+    from medfusion_b200 import ops
+    N, Cin, H, W, Cout, k, stride, inl, outl = shape
+    g = torch.Generator().manual_seed(7)
+    x = _rnd(g, N, Cin, H, W)
+    w = _rnd(g, Cout, Cin, k, k, scale=1.0 / (Cin * k * k) ** 0.5)
+    b = _rnd(g, Cout, scale=0.1)
+    ref = F.conv2d(x, w, b, stride=stride, padding=(k - stride + 1) // 2 if k > 1 else 0)
+    xd = x.to(DEV)
+    xin = xd if inl == 0 else ops.pack_split(xd)
+    out = ops.conv_simt(xin, inl, ops.prep_weight_simt(w.to(DEV)), b.to(DEV), Cin, k, stride, outl)
+    got = out if outl == 0 else ops.unpack_nchw(out)
+    assert_close(got.cpu(), ref, what=f"conv_simt {shape}")
+
+
+@pytest.mark.parametrize("C,G,H,W", [(256, 32, 32, 32), (1024, 32, 8, 8), (512, 8, 32, 32), (64, 8, 64, 64)])
+def test_groupnorm_swish_residual_emb(C, G, H, W):
+    from medfusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    N = 2
+    x = _rnd(g, N, C, H, W) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * _rnd(g, C), 0.1 * _rnd(g, C)
+    r, emb = _rnd(g, N, C, H, W), _rnd(g, N, C)
+    y = F.group_norm(x, G, gamma, beta, 1e-5)
+    ref = y * torch.sigmoid(y) + r + emb[:, :, None, None]
+    raw = x.to(DEV).permute(0, 2, 3, 1).contiguous()
+    mr = ops.gn_finalize(ops.gn_partial(raw), C, G, H * W)
+    out = ops.gn_apply(raw, mr, gamma.to(DEV), beta.to(DEV), G, res=ops.pack_split(r.to(DEV)), emb=emb.to(DEV))
+    assert_close(ops.unpack_nchw(out).cpu(), ref, what="gn+swish+res+emb")
+    out = ops.gn_apply(raw, mr, gamma.to(DEV), beta.to(DEV), G, res=None, emb=None)
+    assert_close(ops.unpack_nchw(out).cpu(), y * torch.sigmoid(y), what="gn+swish")
+
+
+def test_upsample_nearest_exact():
+    from medfusion_b200 import ops
+    x = _rnd(torch.Generator().manual_seed(4), 2, 64, 8, 16)
+    ref = F.interpolate(x, size=(16, 32), mode="nearest-exact")
+    assert torch.equal(ops.unpack_nchw(ops.upsample2x(ops.pack_split(x.to(DEV)))).cpu(), ref)
+
+
+def test_split_planes_are_exact():
+    from medfusion_b200 import ops
+    x = _rnd(torch.Generator().manual_seed(9), 1, 32, 4, 8) * 1e3
+    p = ops.pack_split(x.to(DEV))
+    assert torch.equal(ops.unpack_nchw(p).cpu(), x)                   # hi + lo == x bit for bit
+    assert int((p[0].view(torch.int32) & 0x1FFF).abs().sum()) == 0   # hi plane is TF32-representable
+
+
+def test_scheduler_step_matches_reference_fixture():
+    from medfusion_b200.models import GaussianNoiseScheduler
+    g = load_golden("sched.pt")
+    s = GaussianNoiseScheduler(**g["sched"]).to(DEV)
+    x_t, pred, noise, t = (g[k].to(DEV) for k in ("x_t", "pred", "noise", "t"))
+    for clip in (False, True):
+        ref = g["out"][f"xT_clip{int(clip)}"]
+        o = s.step(x_t, t, pred, noise=noise, objective="x_T", clip_x0=clip, want=("x_prior", "x_0"))
+        assert_close(o["x_prior"].cpu(), ref["prior"], what="prior (x_T objective)")
+        assert_close(o["x_0"].cpu(), ref["x_0"], what="x_0 (x_T objective)")
+        ref = g["out"][f"x0_clip{int(clip)}"]
+        o = s.step(x_t, t, pred, noise=noise, objective="x_0", clip_x0=clip, want=("x_prior", "x_0", "x_T"))
+        assert_close(o["x_prior"].cpu(), ref["prior"], what="prior (x_0 objective)")
+        assert_close(o["x_T"].cpu(), ref["x_T"], what="x_T (x_0 objective)")
+    # t == 0 rows carry no noise (std[t==0] = 0, gaussian_scheduler.py:98)
+    o = s.step(x_t, t, pred, noise=noise * 1e6, objective="x_T", clip_x0=False, want=("x_prior",))
+    o2 = s.step(x_t, t, pred, noise=None, objective="x_T", clip_x0=False, want=("x_prior",))
+    assert torch.equal(o["x_prior"][4], o2["x_prior"][4])
+
+
+def test_scheduler_cfg_and_ddim_against_oracle():
+    import medfusion_oracle as O
+    from medfusion_b200.models import GaussianNoiseScheduler
+    g = load_golden("sched.pt")
+    sc = g["sched"]
+    tabs = O.scheduler_tables(sc["timesteps"], sc["schedule_strategy"], sc["beta_start"], sc["beta_end"])
+    s = GaussianNoiseScheduler(**sc).to(DEV)
+    gen = torch.Generator().manual_seed(8)
+    x_t, pu, pc, n1, n2 = (torch.randn(4, 8, 16, 16, generator=gen) for _ in range(5))
+    for tval, tnext in ((999, 749), (500, 250), (250, 0)):
+        t = torch.full((4,), tval)
+        pred = pu + 3.0 * (pc - pu)
+        prior, x0, xT = O.sched_step(tabs, x_t, t, pred, n1, "x_T", False)
+        nxt = O.ddim_renoise(tabs, x0, xT, torch.tensor(tval), torch.tensor(tnext), n2)
+        o = s.step(x_t.to(DEV), t.to(DEV), pc.to(DEV), pred_uncond=pu.to(DEV), guidance_scale=3.0, noise=n1.to(DEV),
+                   t_next=torch.tensor(tnext), noise_ddim=n2.to(DEV), objective="x_T", clip_x0=False,
+                   want=("x_prior", "x_0", "x_next"))
+        assert_close(o["x_prior"].cpu(), prior, what="cfg prior")
+        assert_close(o["x_0"].cpu(), x0, what="cfg x_0")
+        assert_close(o["x_next"].cpu(), nxt, what="ddim re-noise")
