@@ -76,6 +76,12 @@ size_t mf_unet_workspace_bytes(mf_unet* h, int B, int H, int W);
 /* y[B,out_ch,H,W] = UNet(x_t[B,in_ch,H,W], t[B] (int64), cond[B] (int64) or NULL).  NCHW fp32. */
 int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
                     int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream);
+/* Same as mf_unet_forward but with a CUDA-event pair around every kernel launch of the plan (synchronises).
+ * ms[i]: device time of launch i; kinds[i]: 0 conv_tc, 1 conv_simt, 2 GroupNorm family, 3 other;
+ * flops[i]: algorithmic FLOPs of launch i (2*MACs of the reference formulation; 0 for non-GEMM work). */
+int mf_unet_profile(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B, int H,
+                    int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds,
+                    double* flops, int max_ops, int* n_ops);
 /* Path census of the last prepared plan: number of convs on the tcgen05 path / on the SIMT path. */
 int mf_unet_plan_info(const mf_unet* h, int* n_tc_convs, int* n_simt_convs, int* n_launches);
 
@@ -104,6 +110,9 @@ size_t mf_vae_workspace_bytes(mf_vae* h, int B, int H, int W);
 /* x[B,out_channels,H*2^(depth-1),W*2^(depth-1)] = decode(z[B,emb_channels,H,W]) */
 int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
                   size_t workspace_bytes, mf_stream_t stream);
+int mf_vae_profile(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
+                   size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds, double* flops, int max_ops,
+                   int* n_ops);
 int mf_vae_plan_info(const mf_vae* h, int* n_tc_convs, int* n_simt_convs, int* n_launches);
 
 /* -------------------------------------------------------------------------------------------------

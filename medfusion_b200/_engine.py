@@ -96,6 +96,16 @@ class EngineModule(nn.Module):
         off = (-ws.data_ptr()) % 1024
         return ws.data_ptr() + off, ws.numel() - off
 
+    def _profile_call(self, fn_name, head_args, tail_args, max_ops=4096):
+        """Run one engine call with a CUDA-event pair around every launch -> list of (ms, kind, flops)."""
+        ms = (ctypes.c_float * max_ops)()
+        kinds = (ctypes.c_int * max_ops)()
+        flops = (ctypes.c_double * max_ops)()
+        n = ctypes.c_int()
+        _lib.check(getattr(_lib.load(), fn_name)(self._h, *head_args, *tail_args, cuda_stream_ptr(), ms, kinds, flops,
+                                                 max_ops, ctypes.byref(n)), fn_name)
+        return [(ms[i], kinds[i], flops[i]) for i in range(n.value)]
+
     def plan_info(self):
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         getattr(_lib.load(), f"{self._prefix}_plan_info")(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))

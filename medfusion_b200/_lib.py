@@ -56,6 +56,8 @@ SIGNATURES = {
     "mf_unet_set_time_freqs": (c_int, [_P, _P, c_int, _P]),
     "mf_unet_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_unet_profile": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float),
+                                POINTER(c_int), POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "mf_unet_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "mf_vae_create": (c_int, [POINTER(VAEConfig), POINTER(_P)]),
     "mf_vae_destroy": (None, [_P]),
@@ -65,6 +67,8 @@ SIGNATURES = {
     "mf_vae_set_param": (c_int, [_P, c_char_p, _P, POINTER(c_int64), c_int, _P]),
     "mf_vae_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_vae_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_vae_profile": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float), POINTER(c_int),
+                               POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "mf_vae_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "mf_sched_step": (c_int, [POINTER(SchedTables), _P, _P, _P, c_float, _P, _P, _P, _P, c_int, c_int,
                               _P, _P, _P, _P, c_int, c_int, _P]),

@@ -126,6 +126,7 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
   prep_stream = s;
   arena = Arena();
   ops.clear();
+  op_meta.clear();
   tc_plans.clear();
   n_tc = n_simt = 0;
   const int E = cfg.emb_dim, G = cfg.norm_groups;
@@ -151,27 +152,27 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
       LinearDesc l1{};
       l1.in_mode = 1; l1.freqs = freqs.p; l1.W = t_w1->data.p; l1.bias = t_b1->data.p;
       l1.out = h1.ptr; l1.post = 1; l1.B = B; l1.J = E; l1.K = cfg.pos_emb_dim;
-      ops.push_back([this, l1](cudaStream_t st) {
+      push_op([this, l1](cudaStream_t st) {
         LinearDesc d = l1;
         d.t = io_t;
         return linear_small(d, st);
-      });
+      }, kOpOther, 2.0 * B * E * cfg.pos_emb_dim);
       LinearDesc l2{};
       l2.in_mode = 0; l2.in = h1.ptr; l2.W = t_w2->data.p; l2.bias = t_b2->data.p;
       l2.out = emb.ptr; l2.out2 = semb.ptr; l2.post = 0; l2.B = B; l2.J = E; l2.K = E;
       const float* table = cond_table ? cond_table->data.p : nullptr;
-      ops.push_back([this, l2, table](cudaStream_t st) {
+      push_op([this, l2, table](cudaStream_t st) {
         LinearDesc d = l2;
         if (io_cond != nullptr && table != nullptr) {
           d.add_table = table;
           d.add_idx = io_cond;
         }
         return linear_small(d, st);
-      });
+      }, kOpOther, 2.0 * B * E * E);
       LinearDesc l3{};
       l3.in_mode = 0; l3.in = semb.ptr; l3.W = loc_w.p; l3.bias = loc_b.p;
       l3.out = embT.ptr; l3.post = 0; l3.B = B; l3.J = emb_total; l3.K = E;
-      ops.push_back([l3](cudaStream_t st) { return linear_small(l3, st); });
+      push_op([l3](cudaStream_t st) { return linear_small(l3, st); }, kOpOther, 2.0 * B * emb_total * E);
     }
     free_tensor(h1);
     free_tensor(emb);
@@ -226,9 +227,9 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
           const float* ip = o.ptr; float* op = up.ptr;
           const long long ipl = o.plane, opl = up.plane;
           const int oh = o.H, ow = o.W, oc = o.C;
-          ops.push_back([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
+          push_op([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
             return upsample2x_split(ip, ipl, op, opl, B, oh, ow, oc, st);
-          });
+          }, kOpOther);
         }
         free_tensor(o);
         src = up;
@@ -290,6 +291,7 @@ int mf_vae::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
   prep_stream = s;
   arena = Arena();
   ops.clear();
+  op_meta.clear();
   tc_plans.clear();
   n_tc = n_simt = 0;
   int rc = 0;
@@ -332,9 +334,9 @@ int mf_vae::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
       const float* ip = hcur.ptr; float* op = up.ptr;
       const long long ipl = hcur.plane, opl = up.plane;
       const int oh = hcur.H, ow = hcur.W, oc = hcur.C;
-      ops.push_back([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
+      push_op([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
         return upsample2x_split(ip, ipl, op, opl, B, oh, ow, oc, st);
-      });
+      }, kOpOther);
     }
     free_tensor(hcur);
     Tens uo = new_tensor(B, up.H, up.W, u.up.Cout, kNHWCSplit);
@@ -446,6 +448,18 @@ int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const in
   h->io_y = d_y;
   return h->run(s);
 }
+int mf_unet_profile(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B, int H,
+                    int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds,
+                    double* flops, int max_ops, int* n_ops) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_x = d_x_t;
+  h->io_t = reinterpret_cast<const long long*>(d_t);
+  h->io_cond = reinterpret_cast<const long long*>(d_cond);
+  h->io_y = d_y;
+  return h->run_profiled(s, ms, kinds, flops, max_ops, n_ops);
+}
 int mf_unet_plan_info(const mf_unet* h, int* n_tc_convs, int* n_simt_convs, int* n_launches) {
   if (n_tc_convs) *n_tc_convs = h->n_tc;
   if (n_simt_convs) *n_simt_convs = h->n_simt;
@@ -493,6 +507,16 @@ int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, 
   h->io_z = d_z;
   h->io_x = d_x;
   return h->run(s);
+}
+int mf_vae_profile(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
+                   size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds, double* flops, int max_ops,
+                   int* n_ops) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_z = d_z;
+  h->io_x = d_x;
+  return h->run_profiled(s, ms, kinds, flops, max_ops, n_ops);
 }
 int mf_vae_plan_info(const mf_vae* h, int* n_tc_convs, int* n_simt_convs, int* n_launches) {
   if (n_tc_convs) *n_tc_convs = h->n_tc;

