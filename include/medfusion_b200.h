@@ -144,12 +144,13 @@ int mf_op_unpack_nchw(const float* d_in, int64_t plane, int layout, float* d_out
 int mf_op_prep_weight_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
 int mf_op_prep_weight_simt(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
 int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
-/* stride-1 'same' conv on the tcgen05 path; src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL.
+/* 'same'-padded conv on the tcgen05 path (N,H,W = input size); stride 1 (1x1 / 3x3, optional second source
+ * src1 concatenated along channels) or stride 2 (3x3, single source, even H/W).  src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL.
  * drain_interval: K blocks (of 32 channels) summed inside TMEM before the round-to-nearest fp32 register
  * accumulation; 0 = library default (1, the most exact). */
 int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
                   int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
-                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, mf_stream_t s);
+                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, int stride, mf_stream_t s);
 int mf_op_conv_tc_stats_chunks(int H, int W);
 int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
                     const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,

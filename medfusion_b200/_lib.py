@@ -79,7 +79,7 @@ SIGNATURES = {
     "mf_op_conv_tc_supported": (c_int, [c_int] * 8),
     "mf_op_conv_tc_stats_chunks": (c_int, [c_int, c_int]),
     "mf_op_conv_tc": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P,
-                              _P, c_int64, c_int, _P, c_int, _P]),
+                              _P, c_int64, c_int, _P, c_int, c_int, _P]),
     "mf_op_conv_simt": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P,
                                 c_int64, c_int, _P]),
     "mf_op_gn_partial": (c_int, [_P, _P, c_int, c_int, c_int, _P]),

@@ -570,12 +570,12 @@ int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int k
 int mf_op_conv_tc_stats_chunks(int H, int W) { return conv_tc_stats_chunks(H, W); }
 int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
                   int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
-                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, mf_stream_t s) {
+                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, int stride, mf_stream_t s) {
   MF_REQUIRE(out_layout == kNHWCRaw || out_layout == kNHWCSplit, "conv_tc writes NHWC");
   ConvTcDesc d{};
   d.src0 = d_src0; d.src0_plane = src0_plane; d.C0 = C0;
   d.src1 = d_src1; d.src1_plane = src1_plane; d.C1 = C1;
-  d.N = N; d.H = H; d.W = W;
+  d.N = N; d.H = H; d.W = W; d.stride = stride;
   d.w_planes = d_w_planes; d.Cout = Cout; d.ksize = ksize; d.bias = d_bias;
   d.out = d_out; d.out_plane = out_plane; d.out_mode = out_layout == kNHWCSplit ? kOutSplit : kOutRaw;
   d.stats = d_stats;

@@ -31,8 +31,7 @@ struct TcCfg {
 // round-to-nearest fp32 running sums held in registers while the next K block is being multiplied.
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
   constexpr int CPW = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -63,9 +62,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a0);
-    tma_prefetch_desc(&map_a1);
-    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.a[1]);
+    tma_prefetch_desc(&maps.w);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -94,19 +93,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * Cfg::kStageBytes;
         mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        const int tap = kb / cblks;
-        const int c = (kb - tap * cblks) * kTcBlockK;
-        const int x = w0 * p.in_stride + p.dx[tap];
-        const int y = h0 * p.in_stride + p.dy[tap];
-        if (c < p.C0) {
-          tma_load_5d(st, &map_a0, &full_bar[s], c, x, y, n0, 0);
-          tma_load_5d(st + Cfg::kABytes, &map_a0, &full_bar[s], c, x, y, n0, 1);
+        // K order is channel-block major, tap minor: the 9 taps of one 32-channel slab are consecutive, so the
+        // shifted re-reads of the same activation lines hit in L2 (tap-major order thrashed it: 1.9 GB of DRAM
+        // reads for a 134 MB input at Cin=1024, profiles/r01_conv_tc_ncu.md).
+        const int cb = kb / p.ntaps;
+        const int tap = kb - cb * p.ntaps;
+        const int c = cb * kTcBlockK;
+        const int x = w0 + p.dx[tap];
+        const int y = h0 + p.dy[tap];
+        const CUtensorMap* ma;
+        int cc = c;
+        if (p.per_tap_map) {
+          ma = &maps.a[p.tap_map[tap]];
+        } else if (c < p.C0) {
+          ma = &maps.a[0];
         } else {
-          tma_load_5d(st, &map_a1, &full_bar[s], c - p.C0, x, y, n0, 0);
-          tma_load_5d(st + Cfg::kABytes, &map_a1, &full_bar[s], c - p.C0, x, y, n0, 1);
+          ma = &maps.a[1];
+          cc = c - p.C0;
         }
-        tma_load_3d(st + 2 * Cfg::kABytes, &map_w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 0);
-        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &map_w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 1);
+        tma_load_5d(st, ma, &full_bar[s], cc, x, y, n0, 0);
+        tma_load_5d(st + Cfg::kABytes, ma, &full_bar[s], cc, x, y, n0, 1);
+        tma_load_3d(st + 2 * Cfg::kABytes, &maps.w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 0);
+        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 1);
       }
     }
   } else if (warp == 1) {
@@ -339,9 +347,11 @@ int conv_tc_stats_chunks(int H, int W) {
   return hw >= kTcBlockM ? hw / kTcBlockM : 1;
 }
 
+// N, H, W: OUTPUT geometry
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride) {
   int bw, bh, bn;
-  if (stride != 1) return 0;
+  if (stride != 1 && stride != 2) return 0;
+  if (stride == 2 && (ksize != 3 || C1 != 0)) return 0;
   if (ksize != 1 && ksize != 3) return 0;
   if (C0 <= 0 || C0 % kTcBlockK || C1 % kTcBlockK || Cout % 64) return 0;
   if (!pick_box(H, W, &bw, &bh, &bn)) return 0;
@@ -351,10 +361,13 @@ int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, 
   return 1;
 }
 
+// View of an NHWC split tensor sub-sampled by `sub` in H and W starting at (ph, pw): sub = 1 is the tensor itself,
+// sub = 2 selects one of the four input-parity grids a stride-2 convolution reads.
 static int encode_act_map(CUtensorMap* m, const float* base, long long plane, int N, int H, int W, int C, int bw,
-                          int bh, int bn) {
-  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4,
+                          int bh, int bn, int sub = 1, int ph = 0, int pw = 0) {
+  base += (static_cast<long long>(ph) * W + pw) * C;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(W / sub), (cuuint64_t)(H / sub), (cuuint64_t)N, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)sub * C * 4, (cuuint64_t)sub * W * C * 4, (cuuint64_t)H * W * C * 4,
                            (cuuint64_t)plane * 4};
   cuuint32_t box[5] = {(cuuint32_t)kTcBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -362,49 +375,73 @@ static int encode_act_map(CUtensorMap* m, const float* base, long long plane, in
 }
 
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
-  MF_REQUIRE(conv_tc_supported(d.N, d.H, d.W, d.C0, d.C1, d.Cout, d.ksize, 1), "shape not supported by conv_tc");
+  const int stride = d.stride == 2 ? 2 : 1;
+  MF_REQUIRE(d.H % stride == 0 && d.W % stride == 0, "stride-2 conv_tc needs even input height/width");
+  const int Ho = d.H / stride, Wo = d.W / stride;
+  MF_REQUIRE(conv_tc_supported(d.N, Ho, Wo, d.C0, d.C1, d.Cout, d.ksize, stride), "shape not supported by conv_tc");
   MF_REQUIRE((reinterpret_cast<uintptr_t>(d.src0) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.w_planes) & 15) == 0,
              "TMA sources must be 16-byte aligned");
   ConvTcParams& p = plan->p;
-  p.N = d.N; p.H = d.H; p.W = d.W;
-  pick_box(d.H, d.W, &p.bw, &p.bh, &p.bn);
-  p.tiles_w = d.W / p.bw;
-  p.tiles_h = d.H / p.bh;
+  p.N = d.N; p.H = Ho; p.W = Wo;
+  pick_box(Ho, Wo, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = Wo / p.bw;
+  p.tiles_h = Ho / p.bh;
   p.tiles_n = (d.N + p.bn - 1) / p.bn;
   p.C0 = d.C0; p.C1 = d.C1; p.Cout = d.Cout;
   p.ntaps = d.ksize * d.ksize;
+  p.per_tap_map = stride == 2;
   for (int t = 0; t < p.ntaps; ++t) {
-    p.dy[t] = t / d.ksize - d.ksize / 2;
-    p.dx[t] = t % d.ksize - d.ksize / 2;
+    const int r = t / d.ksize, sx = t % d.ksize;
+    if (stride == 1) {
+      p.dy[t] = r - d.ksize / 2;
+      p.dx[t] = sx - d.ksize / 2;
+      p.tap_map[t] = 0;
+    } else {
+      // input row 2*ho + r - 1:  r=0 -> odd grid row ho-1,  r=1 -> even grid row ho,  r=2 -> odd grid row ho
+      const int phr = (r == 1) ? 0 : 1, pwc = (sx == 1) ? 0 : 1;
+      p.dy[t] = (r == 0) ? -1 : 0;
+      p.dx[t] = (sx == 0) ? -1 : 0;
+      p.tap_map[t] = 2 * phr + pwc;
+    }
   }
-  p.in_stride = 1;
   p.drain_interval = d.drain_interval > 0 ? d.drain_interval : g_default_drain_interval;
   p.bias = d.bias;
   p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
   p.stats = d.stats;
-  p.chunks_per_sample = conv_tc_stats_chunks(d.H, d.W);
-  p.rows_per_sample = d.H * d.W >= kTcBlockM ? kTcBlockM : d.H * d.W;
+  p.chunks_per_sample = conv_tc_stats_chunks(Ho, Wo);
+  p.rows_per_sample = Ho * Wo >= kTcBlockM ? kTcBlockM : Ho * Wo;
 
   plan->block_n = (d.Cout % 256 == 0) ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
   plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.Cout / plan->block_n, 1);
   plan->smem_bytes = plan->block_n == 256 ? TcCfg<256>::kSmemBytes
                                           : (plan->block_n == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes);
 
-  int rc = encode_act_map(&plan->map_a0, d.src0, d.src0_plane, d.N, d.H, d.W, d.C0, p.bw, p.bh, p.bn);
-  if (rc) return rc;
-  if (d.C1 > 0) {
-    MF_REQUIRE((reinterpret_cast<uintptr_t>(d.src1) & 15) == 0, "TMA sources must be 16-byte aligned");
-    rc = encode_act_map(&plan->map_a1, d.src1, d.src1_plane, d.N, d.H, d.W, d.C1, p.bw, p.bh, p.bn);
+  int rc = 0;
+  if (stride == 2) {
+    for (int ph = 0; ph < 2 && rc == 0; ++ph)
+      for (int pw = 0; pw < 2 && rc == 0; ++pw)
+        rc = encode_act_map(&plan->maps.a[2 * ph + pw], d.src0, d.src0_plane, d.N, d.H, d.W, d.C0, p.bw, p.bh, p.bn, 2,
+                            ph, pw);
     if (rc) return rc;
   } else {
-    plan->map_a1 = plan->map_a0;
+    rc = encode_act_map(&plan->maps.a[0], d.src0, d.src0_plane, d.N, d.H, d.W, d.C0, p.bw, p.bh, p.bn);
+    if (rc) return rc;
+    if (d.C1 > 0) {
+      MF_REQUIRE((reinterpret_cast<uintptr_t>(d.src1) & 15) == 0, "TMA sources must be 16-byte aligned");
+      rc = encode_act_map(&plan->maps.a[1], d.src1, d.src1_plane, d.N, d.H, d.W, d.C1, p.bw, p.bh, p.bn);
+      if (rc) return rc;
+    } else {
+      plan->maps.a[1] = plan->maps.a[0];
+    }
+    plan->maps.a[2] = plan->maps.a[0];
+    plan->maps.a[3] = plan->maps.a[0];
   }
   const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
   cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
   cuuint64_t ws[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * d.Cout * 4};
   cuuint32_t wb[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)plan->block_n, 1};
   cuuint32_t we[3] = {1, 1, 1};
-  return encode_map(&plan->map_w, d.w_planes, 3, wd, ws, wb, we);
+  return encode_map(&plan->maps.w, d.w_planes, 3, wd, ws, wb, we);
 }
 
 template <int BLOCK_N>
@@ -415,8 +452,7 @@ static int launch_t(const ConvTcPlan& plan, cudaStream_t stream) {
                                     TcCfg<BLOCK_N>::kSmemBytes));
     attr_set = true;
   }
-  conv_tc_kernel<BLOCK_N><<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.map_a0, plan.map_a1, plan.map_w,
-                                                                              plan.p);
+  conv_tc_kernel<BLOCK_N><<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.maps, plan.p);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }

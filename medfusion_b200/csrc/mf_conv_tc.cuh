@@ -8,7 +8,7 @@
 //
 // GEMM view:  D[M = N*H*W output pixels][Cout] = sum_{tap, c} A[pixel shifted by tap][c] * Wt[Cout][tap*Cin + c]
 // Activations live in HBM as NHWC fp32 in two planes (TF32 hi, fp32 residual lo); weights as
-// [plane][Cout][K] with K = tap-major, channel-minor.  One CTA computes a 128-pixel x BLOCK_N tile:
+// [plane][Cout][K] with K = 32-channel-slab major, tap minor.  One CTA computes a 128-pixel x BLOCK_N tile:
 //   warp 0      : TMA producer  (5-D activation boxes with zero-filled halo, 3-D weight boxes)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per K-step: hi*hi, hi*lo, lo*hi)
 //   warps 2..9  : drain (tcgen05.ld of each finished TMEM partial sum -> round-to-nearest fp32 register
@@ -31,14 +31,15 @@ enum ConvOutMode : int {
 };
 
 struct ConvTcParams {
-  int N, H, W;                   // output geometry (== input geometry, stride 1)
+  int N, H, W;                   // OUTPUT geometry
   int bw, bh, bn;                // pixel box of one tile, bw*bh*bn == 128
   int tiles_w, tiles_h, tiles_n;
   int C0, C1;                    // channels of source 0 / 1 (C1 == 0: single source)
   int Cout;
   int ntaps;
   int dy[kTcMaxTaps], dx[kTcMaxTaps];
-  int in_stride;                 // spatial stride of the conv (1; 2 uses strided tensor maps)
+  int per_tap_map;               // 0: source chosen by channel (concat); 1: source map chosen per tap (stride 2)
+  int tap_map[kTcMaxTaps];       // stride 2: which input-parity tensor map a tap reads
   int drain_interval;            // K blocks accumulated inside TMEM before the fp32 register add (1 = most exact)
   const float* bias;             // [Cout] or nullptr
   float* out;                    // NHWC [N,H,W,Cout]; split mode: hi plane
@@ -49,8 +50,13 @@ struct ConvTcParams {
   int rows_per_sample;           // min(128, H*W)
 };
 
+struct TcMaps {
+  CUtensorMap a[4];  // stride 1: a[0] = source 0, a[1] = source 1 (concat);  stride 2: a[2*ph + pw] = input parity grid
+  CUtensorMap w;
+};
+
 struct ConvTcPlan {
-  CUtensorMap map_a0, map_a1, map_w;
+  TcMaps maps;
   ConvTcParams p;
   int block_n;
   dim3 grid;
@@ -62,7 +68,8 @@ struct ConvTcDesc {
   // sources: NHWC split tensors (hi plane pointer, lo = hi + plane elements)
   const float* src0; long long src0_plane; int C0;
   const float* src1; long long src1_plane; int C1;  // C1 == 0 -> none
-  int N, H, W;              // input == output spatial size
+  int N, H, W;              // INPUT spatial size; output is H/stride x W/stride
+  int stride;               // 1 (default when 0) or 2 (3x3, single source, even H and W)
   const float* w_planes;    // [2][Cout][K] prepared by prep_weight_tc
   int Cout, ksize;          // ksize 1 or 3 (pad = ksize/2, stride 1)
   const float* bias;

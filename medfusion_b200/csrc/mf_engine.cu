@@ -158,18 +158,19 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
   const int C1 = in1 ? in1->C : 0;
   MF_REQUIRE(in0.C + C1 == L.Cin, "conv input channels do not match the weight (" + L.w->name + ")");
   MF_REQUIRE(out.C == L.Cout, "conv output channels do not match the weight (" + L.w->name + ")");
-  const bool tc = L.stride == 1 && in0.layout == kNHWCSplit && (!in1 || in1->layout == kNHWCSplit) &&
-                  out.layout != kNCHW && conv_tc_supported(in0.N, in0.H, in0.W, in0.C, C1, L.Cout, L.k, 1);
+  const bool tc = in0.layout == kNHWCSplit && (!in1 || in1->layout == kNHWCSplit) && out.layout != kNCHW &&
+                  (L.stride == 1 || (in0.H % 2 == 0 && in0.W % 2 == 0)) &&
+                  conv_tc_supported(in0.N, out.H, out.W, in0.C, C1, L.Cout, L.k, L.stride);
   if (tc) {
     ++n_tc;
-    if (chunks) *chunks = conv_tc_stats_chunks(in0.H, in0.W);
+    if (chunks) *chunks = conv_tc_stats_chunks(out.H, out.W);
     if (dry) return 0;
     int rc = ensure_w_tc(L);
     if (rc) return rc;
     ConvTcDesc d{};
     d.src0 = in0.ptr; d.src0_plane = in0.plane; d.C0 = in0.C;
     d.src1 = in1 ? in1->ptr : nullptr; d.src1_plane = in1 ? in1->plane : 0; d.C1 = C1;
-    d.N = in0.N; d.H = in0.H; d.W = in0.W;
+    d.N = in0.N; d.H = in0.H; d.W = in0.W; d.stride = L.stride;
     d.w_planes = L.w_tc.p; d.Cout = L.Cout; d.ksize = L.k;
     d.bias = L.b->data.p;
     d.out = out.ptr; d.out_plane = out.plane; d.out_mode = out.layout == kNHWCSplit ? kOutSplit : kOutRaw;
@@ -179,7 +180,7 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
     rc = conv_tc_build(d, plan);
     if (rc) return rc;
     push_op([plan](cudaStream_t s) { return conv_tc_launch(*plan, s); }, kOpConvTc,
-            2.0 * in0.N * in0.H * in0.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
+            2.0 * out.N * out.H * out.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
     return 0;
   }
   // exact fp32 SIMT path (single source only)

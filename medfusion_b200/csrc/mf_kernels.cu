@@ -74,8 +74,12 @@ __global__ void prep_weight_tc_kernel(const float* __restrict__ w, float* __rest
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long k = i % K;
     const int o = static_cast<int>(i / K);
-    const int c = static_cast<int>(k % Cin);
-    const int tap = static_cast<int>(k / Cin);
+    // K = ((c / 32) * taps + tap) * 32 + c % 32 : channel-block major, tap minor (matches conv_tc's K loop)
+    const int taps = kh * kw;
+    const int cb = static_cast<int>(k / (taps * 32));
+    const int rem = static_cast<int>(k % (taps * 32));
+    const int tap = rem / 32;
+    const int c = cb * 32 + rem % 32;
     const float v = w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap];
     float hi, lo;
     tf32_split(v, hi, lo);

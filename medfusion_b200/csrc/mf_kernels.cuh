@@ -18,7 +18,7 @@ enum ActLayout : int {
 int pack_nchw_to_split(const float* x, float* out, long long plane, int N, int C, int H, int W, cudaStream_t s);
 int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
                    cudaStream_t s);
-// OIHW -> [2][Cout][K], K = (r*kw+s)*Cin + c  (tensor-core path)
+// OIHW -> [2][Cout][K], K = ((c/32)*kh*kw + r*kw+s)*32 + c%32  (tensor-core path; Cin % 32 == 0)
 int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
 // OIHW -> [K][Cout] fp32 (SIMT path)
 int prep_weight_simt(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);

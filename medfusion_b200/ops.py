@@ -58,21 +58,22 @@ def conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride=1) -> bool:
     return bool(_lib.load().mf_op_conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride))
 
 
-def conv_tc(src0, w_planes, bias, ksize, src1=None, split_out=False, want_stats=False, drain_interval=0):
+def conv_tc(src0, w_planes, bias, ksize, src1=None, split_out=False, want_stats=False, drain_interval=0, stride=1):
     """src*: split tensors [2,N,H,W,C]; returns (out, stats or None)."""
     _, N, H, W, C0 = src0.shape
     C1 = 0 if src1 is None else src1.shape[-1]
     Cout = w_planes.shape[1]
     dev = src0.device
-    out = torch.empty(((2, N, H, W, Cout) if split_out else (N, H, W, Cout)), device=dev, dtype=torch.float32)
+    Ho, Wo = H // stride, W // stride
+    out = torch.empty(((2, N, Ho, Wo, Cout) if split_out else (N, Ho, Wo, Cout)), device=dev, dtype=torch.float32)
     stats = None
     if want_stats:
-        chunks = _lib.load().mf_op_conv_tc_stats_chunks(H, W)
+        chunks = _lib.load().mf_op_conv_tc_stats_chunks(Ho, Wo)
         stats = torch.zeros((N, chunks, Cout // 8, 2), device=dev, dtype=torch.float32)
     _lib.check(_lib.load().mf_op_conv_tc(
         _p(src0), src0[0].numel(), C0, _p(src1), 0 if src1 is None else src1[0].numel(), C1, N, H, W,
         _p(w_planes), Cout, ksize, _p(bias), _p(out), out[0].numel() if split_out else 0,
-        NHWC_SPLIT if split_out else NHWC_RAW, _p(stats), drain_interval, _stream()), "conv_tc")
+        NHWC_SPLIT if split_out else NHWC_RAW, _p(stats), drain_interval, stride, _stream()), "conv_tc")
     return out, stats
 
 

@@ -55,6 +55,24 @@ def test_conv_tc_matches_oracle(shape):
     assert torch.equal(ops.unpack_nchw(out2), ops.unpack_nchw(out))
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32, 256, 256), (3, 16, 16, 512, 512), (1, 64, 64, 64, 128)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_stride2_matches_oracle(shape):
+    """BasicDown (conv_blocks.py:43-52,66-70): 3x3, stride 2, pad 1 — four input-parity TMA views, same kernel."""
+    from medfusion_b200 import ops
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = _rnd(g, N, Cin, H, W)
+    w = _rnd(g, Cout, Cin, 3, 3, scale=1.0 / (Cin * 9) ** 0.5)
+    b = _rnd(g, Cout, scale=0.1)
+    ref = F.conv2d(x, w, b, stride=2, padding=1)
+    out, stats = ops.conv_tc(ops.pack_split(x.to(DEV)), ops.prep_weight_tc(w.to(DEV)), b.to(DEV), 3, stride=2,
+                             want_stats=True)
+    assert_close(ops.unpack_nchw(out).cpu(), ref, what=f"conv_tc stride 2 {shape}")
+    r8 = ref.double().view(N, Cout // 8, 8, -1)
+    assert_close(stats.double().sum(dim=1)[..., 0].cpu(), r8.sum(dim=(2, 3)), 1e-3, 1e-2, "stats sum")
+
+
 def test_conv_tc_ragged_batch_tail():
     """8x8 maps pack two samples per 128-row tile; an odd batch exercises the zero-filled / masked tail."""
     from medfusion_b200 import ops
