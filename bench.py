@@ -47,6 +47,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def usable_cores():
+    """Host threads this process can actually run: CPU affinity, capped by the cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -114,7 +126,7 @@ def cpu_reference_images_per_sec(timesteps, n_steps_sample=2, b=4):
     from medfusion_b200.synthetic import synth_tensor
     from util import unet_oracle_cfg, vae_oracle_cfg
     from golden_keys import unet_keys, vae_keys
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     usd = {k: synth_tensor(k, s) for k, s in unet_keys(UNET_CFG)}
     vsd = {k: synth_tensor(k, s) for k, s in vae_keys(VAE_CFG)}

@@ -38,6 +38,9 @@ const char* mf_last_error(void);
 int mf_abi_version(void);
 /* Default TMEM drain interval used by the engines' tensor-core convolutions (see mf_op_conv_tc). */
 int mf_set_drain_interval(int k_blocks);
+/* tcgen05 convolutions: 1 = one CTA per 128-pixel tile, 2 = CTA pairs (cta_group::2, 256-row MMA), 0 = auto.
+ * Affects plans built afterwards. */
+int mf_set_cta_group(int cta_group);
 
 /* -------------------------------------------------------------------------------------------------
  * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block

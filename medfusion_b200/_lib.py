@@ -47,6 +47,7 @@ SIGNATURES = {
     "mf_last_error": (c_char_p, []),
     "mf_abi_version": (c_int, []),
     "mf_set_drain_interval": (c_int, [c_int]),
+    "mf_set_cta_group": (c_int, [c_int]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),
     "mf_unet_param_count": (c_int, [_P]),
@@ -109,6 +110,11 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # tuning knobs (defaults are the parity-safe, fastest-known settings)
+    if os.environ.get("MF_CTA_GROUP"):
+        lib.mf_set_cta_group(int(os.environ["MF_CTA_GROUP"]))
+    if os.environ.get("MF_DRAIN_INTERVAL"):
+        lib.mf_set_drain_interval(int(os.environ["MF_DRAIN_INTERVAL"]))
     _lib = lib
     return lib
 

@@ -387,6 +387,11 @@ extern "C" {
 
 const char* mf_last_error(void) { return mf::get_error(); }
 int mf_abi_version(void) { return 1; }
+int mf_set_cta_group(int cta_group) {
+  MF_REQUIRE(cta_group >= 0 && cta_group <= 2, "cta_group must be 0 (auto), 1 or 2");
+  mf::g_default_cta_group = cta_group;
+  return 0;
+}
 int mf_set_drain_interval(int k_blocks) {
   MF_REQUIRE(k_blocks >= 1, "drain interval must be >= 1");
   mf::g_default_drain_interval = k_blocks;

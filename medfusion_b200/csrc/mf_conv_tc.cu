@@ -6,20 +6,24 @@
 namespace mf {
 
 int g_default_drain_interval = 1;
+int g_default_cta_group = 0;  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
 // Device side
 // =================================================================================================
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 struct TcCfg {
-  static constexpr int kABytes = kTcBlockM * 128;  // one 128-row x 128-byte plane tile
-  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kABytes = kTcBlockM * 128;        // one 128-row x 128-byte plane tile
+  static constexpr int kBRows = BLOCK_N / CG;            // weight rows this CTA stages (a CTA pair splits B)
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
-  static constexpr int kAuxBytes = 2560;  // barriers, TMEM slot, stats scratch
+  static constexpr int kAuxBytes = 2560;                 // barriers, TMEM slot, stats scratch
+  static constexpr int kStagesFit = (225 * 1024 - kAuxBytes - 1024) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // +1024: manual alignment slack
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // two chunk accumulators (ping-pong)
-  static constexpr int kColsPerWarp = BLOCK_N / 2;  // 8 drain warps: 4 lane quarters x 2 column halves
+  static constexpr int kTmemCols = 2 * BLOCK_N;          // two partial-sum accumulators (ping-pong)
+  static constexpr int kColsPerWarp = BLOCK_N / 2;       // 8 drain warps: 4 lane quarters x 2 column halves
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(4 * (BLOCK_N / 8) * 2 * 4 + 512 <= kAuxBytes, "aux region too small");
 };
 
@@ -29,30 +33,37 @@ struct TcCfg {
 // tensor core produce SHORT partial sums (one 32-channel K block: 8 tiny cross-term MMAs first, then the
 // 4 hi*hi MMAs) into one of two TMEM buffers, and the drain warps add each finished partial into
 // round-to-nearest fp32 running sums held in registers while the next K block is being multiplied.
-template <int BLOCK_N>
+//
+// CG == 2: two CTAs of a cluster (one TPC) form a pair.  Each stages its own 128 pixel rows of A and HALF of the
+// weight tile; the leader CTA issues 256-row tcgen05.mma.cta_group::2 instructions that read both CTAs' shared
+// memory and write both CTAs' TMEM.  Per CTA a stage shrinks from 96 KB to 64 KB (3 stages in flight instead of 2)
+// and the weight traffic per SM halves.
+template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, CG>;
   constexpr int CPW = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* acc_full_bar = empty_bar + Cfg::kStages;   // [2] MMA -> drain
-  uint64_t* acc_empty_bar = acc_full_bar + 2;          // [2] drain -> MMA
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);  // [kStages] TMA -> MMA (leader CTA's are the live ones)
+  uint64_t* empty_bar = full_bar + Cfg::kStages;           // [kStages] MMA -> TMA (every CTA)
+  uint64_t* acc_full_bar = empty_bar + Cfg::kStages;       // [2] MMA -> drain (every CTA)
+  uint64_t* acc_empty_bar = acc_full_bar + 2;              // [2] drain -> MMA (leader CTA's)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
-  float* red = reinterpret_cast<float*>(aux + 512);  // [4 quarters][BLOCK_N/8][2]
+  float* red = reinterpret_cast<float*>(aux + 512);        // [4 quarters][BLOCK_N/8][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   // ---- tile coordinates -------------------------------------------------------------------------
   const int mt = blockIdx.x;
   const int nt = blockIdx.y;
   const int tw = mt % p.tiles_w;
   const int th = (mt / p.tiles_w) % p.tiles_h;
-  const int tn = mt / (p.tiles_w * p.tiles_h);
+  const int tn = mt / (p.tiles_w * p.tiles_h);   // may run past tiles_n for the padding CTA of an odd pair
   const int n0 = tn * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
   const int cin = p.C0 + p.C1;
   const int cblks = cin / kTcBlockK;
@@ -71,31 +82,30 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full_bar[b], 1);
-      mbar_init(&acc_empty_bar[b], kTcDrainWarps);
+      mbar_init(&acc_empty_bar[b], kTcDrainWarps * CG);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % Cfg::kStages;
         const uint32_t ph = (kb / Cfg::kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * Cfg::kStageBytes;
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
         // K order is channel-block major, tap minor: the 9 taps of one 32-channel slab are consecutive, so the
         // shifted re-reads of the same activation lines hit in L2 (tap-major order thrashed it: 1.9 GB of DRAM
-        // reads for a 134 MB input at Cin=1024, profiles/r01_conv_tc_ncu.md).
+        // reads for a 134 MB input at Cin=1024, profiles/r01_conv_tc_ncu_raw.md).
         const int cb = kb / p.ntaps;
         const int tap = kb - cb * p.ntaps;
         const int c = cb * kTcBlockK;
@@ -111,16 +121,28 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           ma = &maps.a[1];
           cc = c - p.C0;
         }
-        tma_load_5d(st, ma, &full_bar[s], cc, x, y, n0, 0);
-        tma_load_5d(st + Cfg::kABytes, ma, &full_bar[s], cc, x, y, n0, 1);
-        tma_load_3d(st + 2 * Cfg::kABytes, &maps.w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 0);
-        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, &full_bar[s], kb * kTcBlockK, nt * BLOCK_N, 1);
+        const int brow = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
+        if (CG == 2) {
+          // all bytes of the pair are credited to the LEADER's full barrier
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+          tma_load_5d_2sm(st, ma, fb, cc, x, y, n0, 0);
+          tma_load_5d_2sm(st + Cfg::kABytes, ma, fb, cc, x, y, n0, 1);
+          tma_load_3d_2sm(st + 2 * Cfg::kABytes, &maps.w, fb, kb * kTcBlockK, brow, 0);
+          tma_load_3d_2sm(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, fb, kb * kTcBlockK, brow, 1);
+        } else {
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_5d(st, ma, &full_bar[s], cc, x, y, n0, 0);
+          tma_load_5d(st + Cfg::kABytes, ma, &full_bar[s], cc, x, y, n0, 1);
+          tma_load_3d(st + 2 * Cfg::kABytes, &maps.w, &full_bar[s], kb * kTcBlockK, brow, 0);
+          tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, &full_bar[s], kb * kTcBlockK, brow, 1);
+        }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM, BLOCK_N);
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM * CG, BLOCK_N);
       int kb = 0;
       for (int j = 0; j < nchunks; ++j) {
         const int buf = j & 1;
@@ -144,18 +166,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
 #pragma unroll
           for (int k = 0; k < kTcBlockK / 8; ++k) {
             const uint64_t koff = static_cast<uint64_t>(k * 2);
-            umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+            if (CG == 2) {
+              umma_tf32_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+              umma_tf32_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+            }
             first = false;
-            umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
           }
 #pragma unroll
           for (int k = 0; k < kTcBlockK / 8; ++k) {
             const uint64_t koff = static_cast<uint64_t>(k * 2);
-            umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            if (CG == 2) umma_tf32_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            else umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+          if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full_bar[buf]);  // partial sum complete -> drain warps
+        // partial sum complete -> drain warps (of both CTAs)
+        if (CG == 2) umma_commit_2sm(&acc_full_bar[buf]); else umma_commit(&acc_full_bar[buf]);
       }
     }
   } else {
@@ -167,6 +197,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     float acc[CPW];
 #pragma unroll
     for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
+    uint32_t acc_empty_addr[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+      acc_empty_addr[b] = (CG == 2) ? mapa_u32(smem_u32(&acc_empty_bar[b]), 0) : smem_u32(&acc_empty_bar[b]);
 
     for (int j = 0; j < nchunks; ++j) {
       const int buf = j & 1;
@@ -182,7 +216,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(acc_empty_addr[buf]);
+        else mbar_arrive(&acc_empty_bar[buf]);
+      }
     }
 
     // ---- epilogue from registers
@@ -279,10 +316,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
 
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -412,9 +450,13 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   p.rows_per_sample = Ho * Wo >= kTcBlockM ? kTcBlockM : Ho * Wo;
 
   plan->block_n = (d.Cout % 256 == 0) ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
-  plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, d.Cout / plan->block_n, 1);
-  plan->smem_bytes = plan->block_n == 256 ? TcCfg<256>::kSmemBytes
-                                          : (plan->block_n == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes);
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int cg = d.cta_group > 0 ? d.cta_group : g_default_cta_group;
+  if (cg != 1 && cg != 2) cg = (m_tiles >= 2) ? 2 : 1;  // auto
+  plan->cta_group = cg;
+  // a CTA pair owns two consecutive M tiles; an odd tile count gets one padding CTA (all loads out of range -> zeros,
+  // all stores masked)
+  plan->grid = dim3(cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles, d.Cout / plan->block_n, 1);
 
   int rc = 0;
   if (stride == 2) {
@@ -439,31 +481,45 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
   cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
   cuuint64_t ws[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * d.Cout * 4};
-  cuuint32_t wb[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)plan->block_n, 1};
+  cuuint32_t wb[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(plan->block_n / plan->cta_group), 1};
   cuuint32_t we[3] = {1, 1, 1};
   return encode_map(&plan->maps.w, d.w_planes, 3, wd, ws, wb, we);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 static int launch_t(const ConvTcPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    TcCfg<BLOCK_N>::kSmemBytes));
+    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    TcCfg<BLOCK_N, CG>::kSmemBytes));
     attr_set = true;
   }
-  conv_tc_kernel<BLOCK_N><<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.maps, plan.p);
-  MF_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = plan.grid;
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = TcCfg<BLOCK_N, CG>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MF_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG>, plan.maps, plan.p));
   return 0;
 }
 
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
-  switch (plan.block_n) {
-    case 256: return launch_t<256>(plan, stream);
-    case 128: return launch_t<128>(plan, stream);
-    case 64: return launch_t<64>(plan, stream);
+  switch (plan.block_n * 10 + plan.cta_group) {
+    case 2561: return launch_t<256, 1>(plan, stream);
+    case 2562: return launch_t<256, 2>(plan, stream);
+    case 1281: return launch_t<128, 1>(plan, stream);
+    case 1282: return launch_t<128, 2>(plan, stream);
+    case 641: return launch_t<64, 1>(plan, stream);
+    case 642: return launch_t<64, 2>(plan, stream);
   }
-  set_error("conv_tc_launch: bad block_n");
+  set_error("conv_tc_launch: bad block_n / cta_group");
   return 2;
 }
 

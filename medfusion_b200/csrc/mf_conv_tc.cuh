@@ -59,8 +59,8 @@ struct ConvTcPlan {
   TcMaps maps;
   ConvTcParams p;
   int block_n;
+  int cta_group;  // 1: one CTA per tile; 2: CTA pairs (cluster of 2) sharing the weight tile
   dim3 grid;
-  size_t smem_bytes;
 };
 
 // Host API -------------------------------------------------------------------------------------
@@ -76,9 +76,11 @@ struct ConvTcDesc {
   float* out; long long out_plane; int out_mode;
   float* stats;             // optional
   int drain_interval;       // 0 -> default (1)
+  int cta_group;            // 0 -> default (auto), 1 or 2
 };
 
 extern int g_default_drain_interval;
+extern int g_default_cta_group;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
