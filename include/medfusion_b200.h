@@ -41,6 +41,8 @@ int mf_set_drain_interval(int k_blocks);
 /* tcgen05 convolutions: 1 = one CTA per 128-pixel tile, 2 = CTA pairs (cta_group::2, 256-row MMA), 0 = auto.
  * Affects plans built afterwards. */
 int mf_set_cta_group(int cta_group);
+/* Output channels per tcgen05 tile (0 = auto, 64, 128, 256; reduced automatically until it divides Cout). */
+int mf_set_block_n(int block_n);
 
 /* -------------------------------------------------------------------------------------------------
  * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mf_abi_version": (c_int, []),
     "mf_set_drain_interval": (c_int, [c_int]),
     "mf_set_cta_group": (c_int, [c_int]),
+    "mf_set_block_n": (c_int, [c_int]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),
     "mf_unet_param_count": (c_int, [_P]),
@@ -113,6 +114,8 @@ def load():
     # tuning knobs (defaults are the parity-safe, fastest-known settings)
     if os.environ.get("MF_CTA_GROUP"):
         lib.mf_set_cta_group(int(os.environ["MF_CTA_GROUP"]))
+    if os.environ.get("MF_BLOCK_N"):
+        lib.mf_set_block_n(int(os.environ["MF_BLOCK_N"]))
     if os.environ.get("MF_DRAIN_INTERVAL"):
         lib.mf_set_drain_interval(int(os.environ["MF_DRAIN_INTERVAL"]))
     _lib = lib

@@ -387,6 +387,11 @@ extern "C" {
 
 const char* mf_last_error(void) { return mf::get_error(); }
 int mf_abi_version(void) { return 1; }
+int mf_set_block_n(int block_n) {
+  MF_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 0, 64, 128 or 256");
+  mf::g_default_block_n = block_n;
+  return 0;
+}
 int mf_set_cta_group(int cta_group) {
   MF_REQUIRE(cta_group >= 0 && cta_group <= 2, "cta_group must be 0 (auto), 1 or 2");
   mf::g_default_cta_group = cta_group;

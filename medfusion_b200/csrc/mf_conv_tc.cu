@@ -6,7 +6,8 @@
 namespace mf {
 
 int g_default_drain_interval = 1;
-int g_default_cta_group = 0;  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
+int g_default_cta_group = 0;
+int g_default_block_n = 0;    // 0 = auto  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
 // Device side
@@ -21,7 +22,8 @@ struct TcCfg {
   static constexpr int kStagesFit = (225 * 1024 - kAuxBytes - 1024) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // +1024: manual alignment slack
-  static constexpr int kTmemCols = 2 * BLOCK_N;          // two partial-sum accumulators (ping-pong)
+  static constexpr int kAccBufs = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);  // ring of partial-sum accumulators
+  static constexpr int kTmemCols = kAccBufs * BLOCK_N;   // 512 columns for BLOCK_N >= 128
   static constexpr int kColsPerWarp = BLOCK_N / 2;       // 8 drain warps: 4 lane quarters x 2 column halves
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(4 * (BLOCK_N / 8) * 2 * 4 + 512 <= kAuxBytes, "aux region too small");
@@ -48,9 +50,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);  // [kStages] TMA -> MMA (leader CTA's are the live ones)
   uint64_t* empty_bar = full_bar + Cfg::kStages;           // [kStages] MMA -> TMA (every CTA)
-  uint64_t* acc_full_bar = empty_bar + Cfg::kStages;       // [2] MMA -> drain (every CTA)
-  uint64_t* acc_empty_bar = acc_full_bar + 2;              // [2] drain -> MMA (leader CTA's)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+  constexpr int NB = Cfg::kAccBufs;
+  uint64_t* acc_full_bar = empty_bar + Cfg::kStages;       // [NB] MMA -> drain (every CTA)
+  uint64_t* acc_empty_bar = acc_full_bar + NB;             // [NB] drain -> MMA (leader CTA's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + NB);
   float* red = reinterpret_cast<float*>(aux + 512);        // [4 quarters][BLOCK_N/8][2]
 
   const int warp = threadIdx.x >> 5;
@@ -80,7 +83,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NB; ++b) {
       mbar_init(&acc_full_bar[b], 1);
       mbar_init(&acc_empty_bar[b], kTcDrainWarps * CG);
     }
@@ -145,8 +148,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM * CG, BLOCK_N);
       int kb = 0;
       for (int j = 0; j < nchunks; ++j) {
-        const int buf = j & 1;
-        mbar_wait(&acc_empty_bar[buf], ((j >> 1) & 1) ^ 1);  // drained two chunks ago (first use: free)
+        const int buf = j % NB;
+        mbar_wait(&acc_empty_bar[buf], ((j / NB) & 1) ^ 1);  // drained NB chunks ago (first use: free)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
         const int kb_end = min(nkb, kb + drain);
@@ -197,14 +200,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     float acc[CPW];
 #pragma unroll
     for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
-    uint32_t acc_empty_addr[2];
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-      acc_empty_addr[b] = (CG == 2) ? mapa_u32(smem_u32(&acc_empty_bar[b]), 0) : smem_u32(&acc_empty_bar[b]);
+    const uint32_t acc_empty_base =
+        (CG == 2) ? mapa_u32(smem_u32(&acc_empty_bar[0]), 0) : smem_u32(&acc_empty_bar[0]);
 
     for (int j = 0; j < nchunks; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&acc_full_bar[buf], (j >> 1) & 1);
+      const int buf = j % NB;
+      mbar_wait(&acc_full_bar[buf], (j / NB) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + col0;
 #pragma unroll
@@ -217,7 +218,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(acc_empty_addr[buf]);
+        if (CG == 2) mbar_arrive_cluster(acc_empty_base + buf * 8);
         else mbar_arrive(&acc_empty_bar[buf]);
       }
     }
@@ -449,11 +450,14 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   p.chunks_per_sample = conv_tc_stats_chunks(Ho, Wo);
   p.rows_per_sample = Ho * Wo >= kTcBlockM ? kTcBlockM : Ho * Wo;
 
-  plan->block_n = (d.Cout % 256 == 0) ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int cg = d.cta_group > 0 ? d.cta_group : g_default_cta_group;
   if (cg != 1 && cg != 2) cg = (m_tiles >= 2) ? 2 : 1;  // auto
   plan->cta_group = cg;
+  int bn = d.block_n > 0 ? d.block_n : g_default_block_n;
+  if (bn != 64 && bn != 128 && bn != 256) bn = 256;     // auto: widest tile the channel count allows
+  while (d.Cout % bn) bn /= 2;
+  plan->block_n = bn;
   // a CTA pair owns two consecutive M tiles; an odd tile count gets one padding CTA (all loads out of range -> zeros,
   // all stores masked)
   plan->grid = dim3(cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles, d.Cout / plan->block_n, 1);

@@ -77,10 +77,12 @@ struct ConvTcDesc {
   float* stats;             // optional
   int drain_interval;       // 0 -> default (1)
   int cta_group;            // 0 -> default (auto), 1 or 2
+  int block_n;              // 0 -> default (auto), 64 / 128 / 256 output channels per tile
 };
 
 extern int g_default_drain_interval;
 extern int g_default_cta_group;
+extern int g_default_block_n;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
