@@ -43,6 +43,12 @@ int mf_set_drain_interval(int k_blocks);
 int mf_set_cta_group(int cta_group);
 /* Output channels per tcgen05 tile (0 = auto, 64, 128, 256; reduced automatically until it divides Cout). */
 int mf_set_block_n(int block_n);
+/* Relative correction applied to every drained TMEM partial sum, per K block of the drain interval, compensating the
+ * round-toward-zero bias of the tcgen05 accumulator (0 disables). */
+int mf_set_debias_eps(float eps_per_kblock);
+/* BasicUp (nearest x2 + conv3x3, conv_blocks.py:121-131): 1 = four 2x2 phase convolutions on the low-resolution
+ * input with pre-summed weights (default), 0 = explicit upsample kernel followed by the 3x3 convolution. */
+int mf_set_fold_upsample(int enable);
 
 /* -------------------------------------------------------------------------------------------------
  * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block
@@ -157,6 +163,10 @@ int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* 
                   int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
                   int64_t out_plane, int out_layout, float* d_stats, int drain_interval, int stride, mf_stream_t s);
 int mf_op_conv_tc_stats_chunks(int H, int W);
+/* conv3x3(nearest_x2(src)) + bias -> split [N,2H,2W,Cout]; weights from mf_op_prep_weight_up_tc ([2][4*Cout][4*C]) */
+int mf_op_prep_weight_up_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, mf_stream_t s);
+int mf_op_upconv_tc(const float* d_src, int64_t src_plane, int C, int N, int H, int W, const float* d_w_up_planes,
+                    int Cout, const float* d_bias, float* d_out, int64_t out_plane, mf_stream_t s);
 int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
                     const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,
                     int64_t out_plane, int out_layout, mf_stream_t s);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mf_set_drain_interval": (c_int, [c_int]),
     "mf_set_cta_group": (c_int, [c_int]),
     "mf_set_block_n": (c_int, [c_int]),
+    "mf_set_fold_upsample": (c_int, [c_int]),
+    "mf_set_debias_eps": (c_int, [c_float]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),
     "mf_unet_param_count": (c_int, [_P]),
@@ -82,6 +84,8 @@ SIGNATURES = {
     "mf_op_conv_tc_stats_chunks": (c_int, [c_int, c_int]),
     "mf_op_conv_tc": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P,
                               _P, c_int64, c_int, _P, c_int, c_int, _P]),
+    "mf_op_prep_weight_up_tc": (c_int, [_P, _P, c_int, c_int, _P]),
+    "mf_op_upconv_tc": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int64, _P]),
     "mf_op_conv_simt": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P,
                                 c_int64, c_int, _P]),
     "mf_op_gn_partial": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
@@ -114,6 +118,10 @@ def load():
     # tuning knobs (defaults are the parity-safe, fastest-known settings)
     if os.environ.get("MF_CTA_GROUP"):
         lib.mf_set_cta_group(int(os.environ["MF_CTA_GROUP"]))
+    if os.environ.get("MF_FOLD_UPSAMPLE"):
+        lib.mf_set_fold_upsample(int(os.environ["MF_FOLD_UPSAMPLE"]))
+    if os.environ.get("MF_DEBIAS_EPS"):
+        lib.mf_set_debias_eps(float(os.environ["MF_DEBIAS_EPS"]))
     if os.environ.get("MF_BLOCK_N"):
         lib.mf_set_block_n(int(os.environ["MF_BLOCK_N"]))
     if os.environ.get("MF_DRAIN_INTERVAL"):

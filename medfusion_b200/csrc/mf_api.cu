@@ -220,24 +220,15 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
     free_tensor(skip);
     if (d.has_up) {
       // BasicUp: nearest x2 then conv3x3 (conv_blocks.py:121-131)
-      Tens src = o;
+      Tens u;
       if (d.up_factor == 2) {
-        Tens up = new_tensor(B, o.H * 2, o.W * 2, o.C, kNHWCSplit);
-        if (!dry) {
-          const float* ip = o.ptr; float* op = up.ptr;
-          const long long ipl = o.plane, opl = up.plane;
-          const int oh = o.H, ow = o.W, oc = o.C;
-          push_op([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
-            return upsample2x_split(ip, ipl, op, opl, B, oh, ow, oc, st);
-          }, kOpOther);
-        }
-        free_tensor(o);
-        src = up;
+        rc = add_upconv2x(d.up, o, &u);
+      } else {
+        u = new_tensor(B, o.H, o.W, d.up.Cout, kNHWCSplit);
+        rc = add_conv(d.up, o, nullptr, u, nullptr, nullptr);
       }
-      Tens u = new_tensor(B, src.H, src.W, d.up.Cout, kNHWCSplit);
-      rc = add_conv(d.up, src, nullptr, u, nullptr, nullptr);
       if (rc) return rc;
-      free_tensor(src);
+      free_tensor(o);
       o = u;
     }
     hcur = o;
@@ -329,20 +320,10 @@ int mf_vae::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
   // ---- decoders[depth-2 .. 0]: nearest x2 + conv3x3, then UnetResBlock
   for (int i = cfg.depth - 2; i >= 0; --i) {
     Up& u = *decoders[i];
-    Tens up = new_tensor(B, hcur.H * 2, hcur.W * 2, hcur.C, kNHWCSplit);
-    if (!dry) {
-      const float* ip = hcur.ptr; float* op = up.ptr;
-      const long long ipl = hcur.plane, opl = up.plane;
-      const int oh = hcur.H, ow = hcur.W, oc = hcur.C;
-      push_op([ip, ipl, op, opl, B, oh, ow, oc](cudaStream_t st) {
-        return upsample2x_split(ip, ipl, op, opl, B, oh, ow, oc, st);
-      }, kOpOther);
-    }
-    free_tensor(hcur);
-    Tens uo = new_tensor(B, up.H, up.W, u.up.Cout, kNHWCSplit);
-    rc = add_conv(u.up, up, nullptr, uo, nullptr, nullptr);
+    Tens uo;
+    rc = add_upconv2x(u.up, hcur, &uo);
     if (rc) return rc;
-    free_tensor(up);
+    free_tensor(hcur);
     Tens o;
     rc = add_resblock(u.rb, G, uo, nullptr, nullptr, 0, &o);
     if (rc) return rc;
@@ -387,6 +368,14 @@ extern "C" {
 
 const char* mf_last_error(void) { return mf::get_error(); }
 int mf_abi_version(void) { return 1; }
+int mf_set_debias_eps(float eps_per_kblock) {
+  mf::g_debias_eps_per_kblock = eps_per_kblock;
+  return 0;
+}
+int mf_set_fold_upsample(int enable) {
+  mf::g_fold_upsample = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_block_n(int block_n) {
   MF_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 0, 64, 128 or 256");
   mf::g_default_block_n = block_n;
@@ -590,6 +579,21 @@ int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* 
   d.out = d_out; d.out_plane = out_plane; d.out_mode = out_layout == kNHWCSplit ? kOutSplit : kOutRaw;
   d.stats = d_stats;
   d.drain_interval = drain_interval;
+  ConvTcPlan plan;
+  int rc = conv_tc_build(d, &plan);
+  if (rc) return rc;
+  return conv_tc_launch(plan, static_cast<cudaStream_t>(s));
+}
+int mf_op_prep_weight_up_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, mf_stream_t s) {
+  return prep_weight_up_tc(d_w_oihw, d_out, Cout, Cin, static_cast<cudaStream_t>(s));
+}
+int mf_op_upconv_tc(const float* d_src, int64_t src_plane, int C, int N, int H, int W, const float* d_w_up_planes,
+                    int Cout, const float* d_bias, float* d_out, int64_t out_plane, mf_stream_t s) {
+  ConvTcDesc d{};
+  d.src0 = d_src; d.src0_plane = src_plane; d.C0 = C;
+  d.N = N; d.H = H; d.W = W; d.stride = 1; d.up2 = 1;
+  d.w_planes = d_w_up_planes; d.Cout = Cout; d.ksize = 3; d.bias = d_bias;
+  d.out = d_out; d.out_plane = out_plane; d.out_mode = kOutSplit;
   ConvTcPlan plan;
   int rc = conv_tc_build(d, &plan);
   if (rc) return rc;

@@ -7,7 +7,8 @@ namespace mf {
 
 int g_default_drain_interval = 1;
 int g_default_cta_group = 0;
-int g_default_block_n = 0;    // 0 = auto  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
+int g_default_block_n = 0;    // 0 = auto
+float g_debias_eps_per_kblock = 0.0f;  // calibrated on B200, see profiles/r01_debias_calibration.md  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
 // Device side
@@ -71,6 +72,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   const int cin = p.C0 + p.C1;
   const int cblks = cin / kTcBlockK;
   const int nkb = p.ntaps * cblks;
+  // nearest-x2 + conv3x3 folded into four 2x2 phase convolutions on the low-resolution input (blockIdx.z = phase):
+  // output pixel (2h+oa, 2w+ob) reads input rows {h+oa-1, h+oa} and cols {w+ob-1, w+ob} with pre-summed weights.
+  const int phase = p.up2 ? static_cast<int>(blockIdx.z) : 0;
+  const int oa = phase >> 1, ob = phase & 1;
+  const int osf = p.up2 ? 2 : 1;
   const int drain = p.drain_interval < 1 ? 1 : p.drain_interval;  // K blocks per TMEM partial sum
   const int nchunks = (nkb + drain - 1) / drain;
 
@@ -112,8 +118,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
         const int cb = kb / p.ntaps;
         const int tap = kb - cb * p.ntaps;
         const int c = cb * kTcBlockK;
-        const int x = w0 + p.dx[tap];
-        const int y = h0 + p.dy[tap];
+        const int x = p.up2 ? (w0 + ob - 1 + (tap & 1)) : (w0 + p.dx[tap]);
+        const int y = p.up2 ? (h0 + oa - 1 + (tap >> 1)) : (h0 + p.dy[tap]);
         const CUtensorMap* ma;
         int cc = c;
         if (p.per_tap_map) {
@@ -124,7 +130,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           ma = &maps.a[1];
           cc = c - p.C0;
         }
-        const int brow = nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
+        const int brow = phase * p.Cout + nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
         if (CG == 2) {
           // all bytes of the pair are credited to the LEADER's full barrier
           if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
@@ -213,7 +219,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
         float v[32];
         tmem_ld_32x32(taddr + ch * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] += v[i];
+        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(v[i], p.partial_scale, acc[ch * 32 + i]);
       }
       tc_fence_before();
       __syncwarp();
@@ -229,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     const int in = row / (p.bw * p.bh);
     const int n = n0 + in, h = h0 + ih, w = w0 + iw;
     const bool valid = n < p.N;
-    const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+    const long long pix = (static_cast<long long>(n) * (p.H * osf) + h * osf + oa) * (p.W * osf) + w * osf + ob;
     float* orow = p.out + pix * p.Cout + nt * BLOCK_N + col0;
 
 #pragma unroll
@@ -415,6 +421,8 @@ static int encode_act_map(CUtensorMap* m, const float* base, long long plane, in
 
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   const int stride = d.stride == 2 ? 2 : 1;
+  MF_REQUIRE(!d.up2 || (stride == 1 && d.ksize == 3 && d.C1 == 0 && d.stats == nullptr),
+             "folded upsample conv: 3x3, stride 1, single source, no GroupNorm statistics");
   MF_REQUIRE(d.H % stride == 0 && d.W % stride == 0, "stride-2 conv_tc needs even input height/width");
   const int Ho = d.H / stride, Wo = d.W / stride;
   MF_REQUIRE(conv_tc_supported(d.N, Ho, Wo, d.C0, d.C1, d.Cout, d.ksize, stride), "shape not supported by conv_tc");
@@ -427,7 +435,8 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   p.tiles_h = Ho / p.bh;
   p.tiles_n = (d.N + p.bn - 1) / p.bn;
   p.C0 = d.C0; p.C1 = d.C1; p.Cout = d.Cout;
-  p.ntaps = d.ksize * d.ksize;
+  p.ntaps = d.up2 ? 4 : d.ksize * d.ksize;
+  p.up2 = d.up2 ? 1 : 0;
   p.per_tap_map = stride == 2;
   for (int t = 0; t < p.ntaps; ++t) {
     const int r = t / d.ksize, sx = t % d.ksize;
@@ -444,6 +453,10 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
     }
   }
   p.drain_interval = d.drain_interval > 0 ? d.drain_interval : g_default_drain_interval;
+  // Each TMEM partial sum went through ~4*drain (+8*(drain-1)) truncating (round-toward-zero) accumulations, i.e. it
+  // is biased towards zero by about half an ulp per accumulation.  Multiplying it by (1 + eps) on the way into the
+  // round-to-nearest register sum removes the mean of that bias for free (the add becomes an FMA).
+  p.partial_scale = 1.0f + g_debias_eps_per_kblock * static_cast<float>(p.drain_interval);
   p.bias = d.bias;
   p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
   p.stats = d.stats;
@@ -460,7 +473,7 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   plan->block_n = bn;
   // a CTA pair owns two consecutive M tiles; an odd tile count gets one padding CTA (all loads out of range -> zeros,
   // all stores masked)
-  plan->grid = dim3(cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles, d.Cout / plan->block_n, 1);
+  plan->grid = dim3(cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles, d.Cout / plan->block_n, d.up2 ? 4 : 1);
 
   int rc = 0;
   if (stride == 2) {
@@ -483,8 +496,9 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
     plan->maps.a[3] = plan->maps.a[0];
   }
   const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
-  cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
-  cuuint64_t ws[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * d.Cout * 4};
+  const long long wrows = static_cast<long long>(d.Cout) * (d.up2 ? 4 : 1);  // up2: four phase matrices stacked
+  cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)wrows, 2};
+  cuuint64_t ws[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * wrows * 4};
   cuuint32_t wb[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(plan->block_n / plan->cta_group), 1};
   cuuint32_t we[3] = {1, 1, 1};
   return encode_map(&plan->maps.w, d.w_planes, 3, wd, ws, wb, we);

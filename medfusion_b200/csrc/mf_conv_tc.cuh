@@ -40,7 +40,9 @@ struct ConvTcParams {
   int dy[kTcMaxTaps], dx[kTcMaxTaps];
   int per_tap_map;               // 0: source chosen by channel (concat); 1: source map chosen per tap (stride 2)
   int tap_map[kTcMaxTaps];       // stride 2: which input-parity tensor map a tap reads
+  int up2;                       // 1: nearest-x2 upsample folded in (4 phases in blockIdx.z, 2x2 taps each)
   int drain_interval;            // K blocks accumulated inside TMEM before the fp32 register add (1 = most exact)
+  float partial_scale;           // (1 + eps): de-biases the truncating TMEM accumulation when a partial is drained
   const float* bias;             // [Cout] or nullptr
   float* out;                    // NHWC [N,H,W,Cout]; split mode: hi plane
   long long out_plane;           // elements between hi and lo plane (split mode)
@@ -78,11 +80,13 @@ struct ConvTcDesc {
   int drain_interval;       // 0 -> default (1)
   int cta_group;            // 0 -> default (auto), 1 or 2
   int block_n;              // 0 -> default (auto), 64 / 128 / 256 output channels per tile
+  int up2;                  // 1: input is HxW, output 2Hx2W = conv3x3(nearest_x2(input)); w_planes from prep_weight_up_tc
 };
 
 extern int g_default_drain_interval;
 extern int g_default_cta_group;
 extern int g_default_block_n;
+extern float g_debias_eps_per_kblock;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);

@@ -4,6 +4,8 @@
 
 namespace mf {
 
+int g_fold_upsample = 1;  // BasicUp as four phase convolutions (0: explicit nearest-x2 kernel + conv3x3)
+
 // ---- error string --------------------------------------------------------------------------------
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
@@ -206,6 +208,50 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
     push_op([raw, part, N, HW, C](cudaStream_t s) { return gn_partial_from_raw(raw, part, N, HW, C, s); }, kOpNorm);
   }
   return 0;
+}
+
+int EngineBase::add_upconv2x(ConvLayer& L, const Tens& in, Tens* out) {
+  MF_REQUIRE(in.C == L.Cin && L.k == 3 && L.stride == 1, "BasicUp conv must be 3x3 stride 1 (" + L.w->name + ")");
+  const bool fold = g_fold_upsample && in.layout == kNHWCSplit &&
+                    conv_tc_supported(in.N, in.H, in.W, in.C, 0, L.Cout, 3, 1);
+  Tens o = new_tensor(in.N, in.H * 2, in.W * 2, L.Cout, kNHWCSplit);
+  *out = o;
+  if (fold) {
+    ++n_tc;
+    if (dry) return 0;
+    if (L.up_version != version) {
+      if (L.w_up.alloc(2 * 16 * static_cast<size_t>(L.Cout) * L.Cin)) return 1;
+      int rc = prep_weight_up_tc(L.w->data.p, L.w_up.p, L.Cout, L.Cin, prep_stream);
+      if (rc) return rc;
+      L.up_version = version;
+    }
+    ConvTcDesc d{};
+    d.src0 = in.ptr; d.src0_plane = in.plane; d.C0 = in.C;
+    d.N = in.N; d.H = in.H; d.W = in.W; d.stride = 1; d.up2 = 1;
+    d.w_planes = L.w_up.p; d.Cout = L.Cout; d.ksize = 3;
+    d.bias = L.b->data.p;
+    d.out = o.ptr; d.out_plane = o.plane; d.out_mode = kOutSplit;
+    tc_plans.emplace_back(new ConvTcPlan());
+    ConvTcPlan* plan = tc_plans.back().get();
+    int rc = conv_tc_build(d, plan);
+    if (rc) return rc;
+    // algorithmic FLOPs are those of the reference formulation (9 taps at the high resolution); the fold issues 4/9
+    push_op([plan](cudaStream_t s) { return conv_tc_launch(*plan, s); }, kOpConvTc,
+            2.0 * o.N * o.H * o.W * L.Cout * static_cast<double>(L.Cin) * 9);
+    return 0;
+  }
+  Tens up = new_tensor(in.N, in.H * 2, in.W * 2, in.C, in.layout);
+  if (!dry) {
+    MF_REQUIRE(in.layout == kNHWCSplit, "explicit upsample expects a split tensor");
+    const float* ip = in.ptr; float* op = up.ptr;
+    const long long ipl = in.plane, opl = up.plane;
+    const int N = in.N, H = in.H, W = in.W, C = in.C;
+    push_op([ip, ipl, op, opl, N, H, W, C](cudaStream_t st) { return upsample2x_split(ip, ipl, op, opl, N, H, W, C, st); },
+            kOpOther);
+  }
+  int rc = add_conv(L, up, nullptr, o, nullptr, nullptr);
+  free_tensor(up);
+  return rc;
 }
 
 int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, int Cin, int H, int W, const Tens& out,

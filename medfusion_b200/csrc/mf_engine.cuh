@@ -53,8 +53,8 @@ struct ConvLayer {
   Param* w = nullptr;
   Param* b = nullptr;
   int Cout = 0, Cin = 0, k = 1, stride = 1;
-  DevBuf w_tc, w_simt;  // derived layouts, built lazily by the plan builder
-  int tc_version = -1, simt_version = -1;
+  DevBuf w_tc, w_simt, w_up;  // derived layouts, built lazily by the plan builder
+  int tc_version = -1, simt_version = -1, up_version = -1;
 };
 struct NormLayer {
   Param* g = nullptr;
@@ -89,6 +89,7 @@ struct Tens {
   long long elems() const { return static_cast<long long>(N) * H * W * C; }
 };
 
+extern int g_fold_upsample;
 using Launch = std::function<int(cudaStream_t)>;
 enum OpKind : int { kOpConvTc = 0, kOpConvSimt = 1, kOpNorm = 2, kOpOther = 3 };
 struct OpMeta { int kind; double flops; };
@@ -133,6 +134,9 @@ class EngineBase {
                        const Tens* stats, int* chunks);
   // conv writing an external NCHW fp32 pointer only known at call time
   int add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst);
+  // BasicUp: out[2H,2W] = conv3x3(nearest_x2(in)) as four 2x2 phase convolutions on the tensor-core path, or
+  // (shapes the tensor-core path cannot take) an explicit upsample followed by add_conv.
+  int add_upconv2x(ConvLayer& L, const Tens& in, Tens* out);
   int add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks, const Tens* res,
                    const float* emb, int emb_stride, const Tens& out);
   // full res block: in0 (+in1 concat) -> returns output tensor (split)

@@ -96,6 +96,48 @@ int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, i
   return 0;
 }
 
+// BasicUp fold: conv3x3(nearest_x2(x)) == four 2x2 convolutions on x, one per output parity (a, b):
+//   rows: a=0 -> {h-1: w[r=0], h: w[1]+w[2]}   a=1 -> {h: w[0]+w[1], h+1: w[2]}   (same for columns)
+// out[2][4*Cout][4*Cin] in conv_tc's K order (32-channel slab major, tap (u,v) minor).
+__global__ void prep_weight_up_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
+  const long long K = 4LL * Cin;
+  const long long total = K * Cout * 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long k = i % K;
+    const long long row = i / K;
+    const int o = static_cast<int>(row % Cout);
+    const int phase = static_cast<int>(row / Cout);
+    const int a = phase >> 1, b = phase & 1;
+    const int cb = static_cast<int>(k / 128);
+    const int rem = static_cast<int>(k % 128);
+    const int tap = rem / 32, c = cb * 32 + rem % 32;
+    const int u = tap >> 1, v = tap & 1;
+    const float* wk = w + (static_cast<long long>(o) * Cin + c) * 9;
+    // rows/cols of the 3x3 kernel that land on low-res offset u (resp. v) for output parity a (resp. b)
+    const int r_lo = (a == 0) ? (u == 0 ? 0 : 1) : (u == 0 ? 0 : 2);
+    const int r_hi = (a == 0) ? (u == 0 ? 0 : 2) : (u == 0 ? 1 : 2);
+    const int s_lo = (b == 0) ? (v == 0 ? 0 : 1) : (v == 0 ? 0 : 2);
+    const int s_hi = (b == 0) ? (v == 0 ? 0 : 2) : (v == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int r = r_lo; r <= r_hi; ++r)
+      for (int sx = s_lo; sx <= s_hi; ++sx) acc += wk[r * 3 + sx];
+    float hi, lo;
+    tf32_split(acc, hi, lo);
+    out[i] = hi;
+    out[total + i] = lo;
+  }
+}
+
+int prep_weight_up_tc(const float* w_oihw, float* out, int Cout, int Cin, cudaStream_t s) {
+  MF_REQUIRE(Cin % 32 == 0, "prep_weight_up_tc needs Cin % 32 == 0");
+  const long long total = 16LL * Cout * Cin;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  prep_weight_up_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, Cout, Cin);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 __global__ void prep_weight_simt_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
                                         int kw) {
   const long long K = static_cast<long long>(kh) * kw * Cin;

@@ -20,6 +20,8 @@ int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, 
                    cudaStream_t s);
 // OIHW -> [2][Cout][K], K = ((c/32)*kh*kw + r*kw+s)*32 + c%32  (tensor-core path; Cin % 32 == 0)
 int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+// OIHW 3x3 -> [2][4*Cout][4*Cin]: the four 2x2 phase kernels of conv3x3(nearest_x2(.)) with pre-summed taps
+int prep_weight_up_tc(const float* w_oihw, float* out, int Cout, int Cin, cudaStream_t s);
 // OIHW -> [K][Cout] fp32 (SIMT path)
 int prep_weight_simt(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
 

@@ -135,3 +135,16 @@ def upsample2x(x_split):
     _lib.check(_lib.load().mf_op_upsample2x(_p(x_split), x_split[0].numel(), _p(out), out[0].numel(), N, H, W, C,
                                             _stream()), "upsample2x")
     return out
+
+
+def upconv_tc(src_split, w_oihw, bias):
+    """conv3x3(nearest_x2(src)) + bias via the folded four-phase tensor-core kernel -> split [2,N,2H,2W,Cout]"""
+    _, N, H, W, C = src_split.shape
+    Cout = w_oihw.shape[0]
+    w = w_oihw.contiguous().float()
+    wup = torch.empty((2, 4 * Cout, 4 * C), device=w.device, dtype=torch.float32)
+    _lib.check(_lib.load().mf_op_prep_weight_up_tc(_p(w), _p(wup), Cout, C, _stream()), "prep_weight_up_tc")
+    out = torch.empty((2, N, 2 * H, 2 * W, Cout), device=w.device, dtype=torch.float32)
+    _lib.check(_lib.load().mf_op_upconv_tc(_p(src_split), src_split[0].numel(), C, N, H, W, _p(wup), Cout, _p(bias),
+                                           _p(out), out[0].numel(), _stream()), "upconv_tc")
+    return out

@@ -73,6 +73,21 @@ def test_conv_tc_stride2_matches_oracle(shape):
     assert_close(stats.double().sum(dim=1)[..., 0].cpu(), r8.sum(dim=(2, 3)), 1e-3, 1e-2, "stats sum")
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256, 256), (3, 8, 8, 512, 512), (1, 64, 64, 128, 64), (1, 32, 32, 512, 256)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_upconv_fold_matches_oracle(shape):
+    """BasicUp (conv_blocks.py:121-131): conv3x3(nearest-exact x2) as four 2x2 phase convolutions with pre-summed taps."""
+    from medfusion_b200 import ops
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    x = _rnd(g, N, Cin, H, W)
+    w = _rnd(g, Cout, Cin, 3, 3, scale=1.0 / (Cin * 9) ** 0.5)
+    b = _rnd(g, Cout, scale=0.1)
+    ref = F.conv2d(F.interpolate(x, size=(2 * H, 2 * W), mode="nearest-exact"), w, b, padding=1)
+    out = ops.upconv_tc(ops.pack_split(x.to(DEV)), w.to(DEV), b.to(DEV))
+    assert_close(ops.unpack_nchw(out).cpu(), ref, what=f"folded upconv {shape}")
+
+
 def test_conv_tc_ragged_batch_tail():
     """8x8 maps pack two samples per 128-row tile; an odd batch exercises the zero-filled / masked tail."""
     from medfusion_b200 import ops
