@@ -44,7 +44,7 @@ int mf_set_cta_group(int cta_group);
 /* Output channels per tcgen05 tile (0 = auto, 64, 128, 256; reduced automatically until it divides Cout). */
 int mf_set_block_n(int block_n);
 /* Relative correction applied to every drained TMEM partial sum, per K block of the drain interval, compensating the
- * round-toward-zero bias of the tcgen05 accumulator (0 disables). */
+ * round-toward-zero bias of the tcgen05 accumulator (0 disables, negative = built-in calibrated table, the default). */
 int mf_set_debias_eps(float eps_per_kblock);
 /* BasicUp (nearest x2 + conv3x3, conv_blocks.py:121-131): 1 = four 2x2 phase convolutions on the low-resolution
  * input with pre-summed weights (default), 0 = explicit upsample kernel followed by the 3x3 convolution. */
@@ -158,7 +158,7 @@ int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int k
 /* 'same'-padded conv on the tcgen05 path (N,H,W = input size); stride 1 (1x1 / 3x3, optional second source
  * src1 concatenated along channels) or stride 2 (3x3, single source, even H/W).  src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL.
  * drain_interval: K blocks (of 32 channels) summed inside TMEM before the round-to-nearest fp32 register
- * accumulation; 0 = library default (1, the most exact). */
+ * accumulation; 0 = library default (2; 1 is the most exact, larger is faster). */
 int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
                   int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
                   int64_t out_plane, int out_layout, float* d_stats, int drain_interval, int stride, mf_stream_t s);

@@ -1,14 +1,15 @@
 // See mf_conv_tc.cuh for the design.  sm_100a only: TMA + mbarrier pipeline + tcgen05.mma (TMEM accumulators).
 #include "mf_conv_tc.cuh"
 
+#include <cmath>
 #include <mutex>
 
 namespace mf {
 
-int g_default_drain_interval = 1;
+int g_default_drain_interval = 2;
 int g_default_cta_group = 0;
 int g_default_block_n = 0;    // 0 = auto
-float g_debias_eps_per_kblock = 0.0f;  // calibrated on B200, see profiles/r01_debias_calibration.md  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
+float g_debias_eps_per_kblock = -1.0f;  // < 0: calibrated table (default); 0: off; > 0: explicit relative correction per K block  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
 // Device side
@@ -272,6 +273,29 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           }
         }
       }
+      if (valid && p.res_kind != 0) {
+        // fused residual add: out = conv + bias + residual(same pixel, same channels)   (attention / transformer blocks)
+        const float* rrow = p.res + pix * p.Cout + nt * BLOCK_N + col0 + ch * 32;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float4 r = *reinterpret_cast<const float4*>(rrow + 4 * jj);
+          if (p.res_kind == 1) {
+            const float4 rl = *reinterpret_cast<const float4*>(rrow + p.res_plane + 4 * jj);
+            r.x += rl.x; r.y += rl.y; r.z += rl.z; r.w += rl.w;
+          }
+          v[4 * jj + 0] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
+        }
+      }
+      if (valid && p.emb != nullptr) {
+        // per-sample channel vector (degenerate one-token cross-attention collapses to this, attention_blocks.py:160-195)
+        const float4* e4 = reinterpret_cast<const float4*>(p.emb + static_cast<long long>(n) * p.emb_stride +
+                                                            nt * BLOCK_N + col0 + ch * 32);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 e = __ldg(e4 + jj);
+          v[4 * jj + 0] += e.x; v[4 * jj + 1] += e.y; v[4 * jj + 2] += e.z; v[4 * jj + 3] += e.w;
+        }
+      }
       if (valid) {
         if (p.out_mode == kOutRaw) {
           float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
@@ -456,10 +480,20 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   // Each TMEM partial sum went through ~4*drain (+8*(drain-1)) truncating (round-toward-zero) accumulations, i.e. it
   // is biased towards zero by about half an ulp per accumulation.  Multiplying it by (1 + eps) on the way into the
   // round-to-nearest register sum removes the mean of that bias for free (the add becomes an FMA).
-  p.partial_scale = 1.0f + g_debias_eps_per_kblock * static_cast<float>(p.drain_interval);
+  // Calibrated on B200 against fp64 (profiles/r01_debias_calibration.jsonl): the relative bias of a drained partial is
+  // -0.87e-7 / -2.7e-7 / -6.3e-7 for drain = 1 / 2 / 4, the same for Gaussian, all-positive and Swish-like operands.
+  if (g_debias_eps_per_kblock < 0.f) {
+    const long ulps = std::max(1L, std::lround(0.73 * std::pow(static_cast<double>(p.drain_interval), 1.43)));
+    p.partial_scale = 1.0f + static_cast<float>(ulps) * 1.1920929e-7f;
+  } else {
+    p.partial_scale = 1.0f + g_debias_eps_per_kblock * static_cast<float>(p.drain_interval);
+  }
   p.bias = d.bias;
   p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
   p.stats = d.stats;
+  p.res = d.res; p.res_plane = d.res_plane; p.res_kind = d.res ? d.res_kind : 0;
+  p.emb = d.emb; p.emb_stride = d.emb_stride;
+  MF_REQUIRE(!(d.up2 && (d.res || d.emb)), "folded upsample conv has no fused residual");
   p.chunks_per_sample = conv_tc_stats_chunks(Ho, Wo);
   p.rows_per_sample = Ho * Wo >= kTcBlockM ? kTcBlockM : Ho * Wo;
 

@@ -48,6 +48,11 @@ struct ConvTcParams {
   long long out_plane;           // elements between hi and lo plane (split mode)
   int out_mode;
   float* stats;                  // [N][chunks][Cout/8][2] partial (sum, sumsq) or nullptr
+  const float* res;              // optional residual with the output's geometry; res_kind 1: split planes, 2: raw
+  long long res_plane;
+  int res_kind;
+  const float* emb;              // optional per-sample channel vector emb[n*emb_stride + c]
+  int emb_stride;
   int chunks_per_sample;         // tiles per sample (1 if a tile spans >= 1 whole samples)
   int rows_per_sample;           // min(128, H*W)
 };
@@ -77,6 +82,8 @@ struct ConvTcDesc {
   const float* bias;
   float* out; long long out_plane; int out_mode;
   float* stats;             // optional
+  const float* res; long long res_plane; int res_kind;  // optional fused residual add (1 split, 2 raw)
+  const float* emb; int emb_stride;                     // optional fused per-sample channel add
   int drain_interval;       // 0 -> default (1)
   int cta_group;            // 0 -> default (auto), 1 or 2
   int block_n;              // 0 -> default (auto), 64 / 128 / 256 output channels per tile
