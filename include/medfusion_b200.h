@@ -66,7 +66,7 @@ typedef struct {
   int pos_emb_dim;                 /* sinusoidal width (emb_dim // 4 by default, time_embedder.py:62) */
   int num_classes;                 /* LabelEmbedder num_classes (cond_embedders.py:6); 0 = none */
   int norm_groups;                 /* GroupNorm groups (32) */
-  int attention[MF_MAX_LEVELS];    /* 0 = 'none' (only value supported in this round) */
+  int attention[MF_MAX_LEVELS];    /* per level: 0 = 'none', 1 = 'linear', 2 = 'spatial' (attention_blocks.py:291-335) */
 } mf_unet_config;
 
 typedef struct mf_unet mf_unet;
@@ -177,6 +177,14 @@ int mf_op_gn_apply(const float* d_raw, const float* d_mean_rstd, const float* d_
                    const float* d_res, int64_t res_plane, int res_kind /* 0 none, 1 split, 2 raw */,
                    const float* d_emb, int emb_stride, float* d_out, int64_t out_plane, int N, int HW, int C, int G,
                    mf_stream_t s);
+/* attention-block kernels (attention_blocks.py): softmax((q s)^T (k s)) v per head with s = d^-0.25, q/k/v raw rows of
+ * row_stride floats per token, out split [B*N][heads*d]; LayerNorm over channels (split -> split); GEGLU gate
+ * (raw [tokens][2*Ch] -> split [tokens][Ch]) */
+int mf_op_attention(const float* d_q, const float* d_k, const float* d_v, int row_stride, float* d_out, int64_t out_plane,
+                    int B, int N, int heads, int d, mf_stream_t s);
+int mf_op_layernorm(const float* d_in, int64_t in_plane, const float* d_gamma, const float* d_beta, float* d_out,
+                    int64_t out_plane, int64_t tokens, int C, float eps, mf_stream_t s);
+int mf_op_geglu(const float* d_in, float* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s);
 int mf_op_upsample2x(const float* d_in, int64_t in_plane, float* d_out, int64_t out_plane, int N, int H, int W, int C,
                      mf_stream_t s);
 

@@ -92,6 +92,9 @@ SIGNATURES = {
     "mf_op_gn_finalize": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "mf_op_gn_apply": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, c_int, _P, c_int64, c_int, c_int, c_int,
                                c_int, _P]),
+    "mf_op_attention": (c_int, [_P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_layernorm": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, c_float, _P]),
+    "mf_op_geglu": (c_int, [_P, _P, c_int64, c_int64, c_int, _P]),
     "mf_op_upsample2x": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
 }
 

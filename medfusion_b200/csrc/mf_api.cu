@@ -15,10 +15,11 @@ struct mf_unet : public EngineBase {
   mf_unet_config cfg{};
   // layers in reference module order
   ConvLayer in_conv;
-  struct EncEntry { bool is_down = false; ResBlockLayer rb; ConvLayer down; };
+  struct EncEntry { bool is_down = false; ResBlockLayer rb; ConvLayer down; SpatialAttnLayer attn; };
   std::vector<std::unique_ptr<EncEntry>> enc;          // in_blocks
   ResBlockLayer mid0, mid2;                            // middle_block.{0,2}
-  struct DecEntry { ResBlockLayer rb; bool has_up = false; ConvLayer up; int up_factor = 1; };
+  SpatialAttnLayer mid_attn;                           // middle_block.1
+  struct DecEntry { ResBlockLayer rb; SpatialAttnLayer attn; bool has_up = false; ConvLayer up; int up_factor = 1; };
   std::vector<std::unique_ptr<DecEntry>> dec;          // out_blocks (module index order)
   ConvLayer outc;
   Param *t_w1 = nullptr, *t_b1 = nullptr, *t_w2 = nullptr, *t_b2 = nullptr, *cond_table = nullptr;
@@ -45,7 +46,8 @@ int mf_unet::init(const mf_unet_config& c) {
   cfg = c;
   MF_REQUIRE(c.depth >= 2 && c.depth <= MF_MAX_LEVELS, "depth must be in [2, 8]");
   MF_REQUIRE(c.num_res_blocks >= 1, "num_res_blocks >= 1");
-  for (int i = 0; i < c.depth; ++i) MF_REQUIRE(c.attention[i] == 0, "attention != 'none' is not built in this round");
+  for (int i = 0; i < c.depth; ++i)
+    MF_REQUIRE(c.attention[i] >= 0 && c.attention[i] <= 2, "attention must be 0 ('none'), 1 ('linear') or 2 ('spatial')");
   const int E = c.emb_dim;
   if (E > 0) {
     MF_REQUIRE(c.pos_emb_dim > 0 && c.pos_emb_dim % 64 == 0, "pos_emb_dim must be a multiple of 64");
@@ -64,6 +66,8 @@ int mf_unet::init(const mf_unet_config& c) {
       const std::string pre = "in_blocks." + std::to_string(enc.size() - 1) + ".0";
       init_resblock(*this, enc.back()->rb, pre, hid[k == 0 ? i - 1 : i], hid[i], c.kernel_sizes[i], E);
       all_rb.push_back(&enc.back()->rb);
+      init_attention(*this, enc.back()->attn, "in_blocks." + std::to_string(enc.size() - 1) + ".1.attention",
+                     c.attention[i], hid[i], E);
     }
     if (i < c.depth - 1) {
       enc.emplace_back(new EncEntry());
@@ -74,6 +78,7 @@ int mf_unet::init(const mf_unet_config& c) {
   }
   // middle (unet2.py:117-153)
   init_resblock(*this, mid0, "middle_block.0", hid[c.depth - 1], hid[c.depth - 1], c.kernel_sizes[c.depth - 1], E);
+  init_attention(*this, mid_attn, "middle_block.1.attention", c.attention[c.depth - 1], hid[c.depth - 1], E);
   init_resblock(*this, mid2, "middle_block.2", hid[c.depth - 1], hid[c.depth - 1], c.kernel_sizes[c.depth - 1], E);
   all_rb.push_back(&mid0);
   all_rb.push_back(&mid2);
@@ -86,6 +91,7 @@ int mf_unet::init(const mf_unet_config& c) {
       const std::string pre = "out_blocks." + std::to_string(dec.size() - 1);
       init_resblock(*this, d.rb, pre + ".0", hid[i] + oc, oc, c.kernel_sizes[i], E);
       all_rb.push_back(&d.rb);
+      init_attention(*this, d.attn, pre + ".1.attention", c.attention[i], oc, E);
       if (i > 1 && k == 0) {
         d.has_up = true;
         d.up_factor = c.strides[i];
@@ -140,6 +146,8 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
   }
 
   // ---- embeddings (time_embedder.py:67-75, cond_embedders.py:18-23, conv_blocks.py:16-18, :350)
+  Tens emb_raw;
+  bool have_emb = false;
   Tens embT;
   const Tens* embTp = nullptr;
   if (E > 0) {
@@ -175,8 +183,9 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
       push_op([l3](cudaStream_t st) { return linear_small(l3, st); }, kOpOther, 2.0 * B * emb_total * E);
     }
     free_tensor(h1);
-    free_tensor(emb);
     free_tensor(semb);
+    emb_raw = emb;          // raw time(+label) embedding: the key/value token of the cross-attention blocks
+    have_emb = true;
   }
 
   // ---- encoder
@@ -197,6 +206,12 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
       rc = add_conv(e->down, cur, nullptr, nxt, nullptr, nullptr);
     } else {
       rc = add_resblock(e->rb, G, cur, nullptr, embTp, emb_total, &nxt);
+      if (rc == 0 && e->attn.kind != 0) {
+        Tens ao;
+        rc = add_attention(e->attn, G, nxt, have_emb ? &emb_raw : nullptr, &ao);
+        free_tensor(nxt);
+        nxt = ao;
+      }
     }
     if (rc) return rc;
     skips.push_back(nxt);
@@ -205,6 +220,13 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
   Tens hcur, tmp;
   rc = add_resblock(mid0, G, skips.back(), nullptr, embTp, emb_total, &tmp);
   if (rc) return rc;
+  if (mid_attn.kind != 0) {
+    Tens ao;
+    rc = add_attention(mid_attn, G, tmp, have_emb ? &emb_raw : nullptr, &ao);
+    if (rc) return rc;
+    free_tensor(tmp);
+    tmp = ao;
+  }
   rc = add_resblock(mid2, G, tmp, nullptr, embTp, emb_total, &hcur);
   if (rc) return rc;
   free_tensor(tmp);
@@ -218,6 +240,13 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
     if (rc) return rc;
     free_tensor(hcur);
     free_tensor(skip);
+    if (d.attn.kind != 0) {
+      Tens ao;
+      rc = add_attention(d.attn, G, o, have_emb ? &emb_raw : nullptr, &ao);
+      if (rc) return rc;
+      free_tensor(o);
+      o = ao;
+    }
     if (d.has_up) {
       // BasicUp: nearest x2 then conv3x3 (conv_blocks.py:121-131)
       Tens u;
@@ -238,6 +267,7 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
   if (rc) return rc;
   free_tensor(hcur);
   if (E > 0) free_tensor(embT);
+  if (have_emb) free_tensor(emb_raw);
   n_launches = static_cast<int>(ops.size());
   return 0;
 }
@@ -624,7 +654,19 @@ int mf_op_gn_apply(const float* d_raw, const float* d_mean_rstd, const float* d_
   d.res = d_res; d.res_plane = res_plane; d.res_kind = res_kind;
   d.emb = d_emb; d.emb_stride = emb_stride;
   d.out = d_out; d.out_plane = out_plane; d.N = N; d.HW = HW; d.C = C; d.G = G;
+  d.raw_plane = 0; d.act = 1;
   return gn_apply(d, static_cast<cudaStream_t>(s));
+}
+int mf_op_attention(const float* d_q, const float* d_k, const float* d_v, int row_stride, float* d_out, int64_t out_plane,
+                    int B, int N, int heads, int d, mf_stream_t s) {
+  return attention_core(d_q, d_k, d_v, row_stride, d_out, out_plane, B, N, heads, d, static_cast<cudaStream_t>(s));
+}
+int mf_op_layernorm(const float* d_in, int64_t in_plane, const float* d_gamma, const float* d_beta, float* d_out,
+                    int64_t out_plane, int64_t tokens, int C, float eps, mf_stream_t s) {
+  return layernorm_split(d_in, in_plane, d_gamma, d_beta, d_out, out_plane, tokens, C, eps, static_cast<cudaStream_t>(s));
+}
+int mf_op_geglu(const float* d_in, float* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s) {
+  return geglu_split(d_in, d_out, out_plane, tokens, Ch, static_cast<cudaStream_t>(s));
 }
 int mf_op_upsample2x(const float* d_in, int64_t in_plane, float* d_out, int64_t out_plane, int N, int H, int W, int C,
                      mf_stream_t s) {

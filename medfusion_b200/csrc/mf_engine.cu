@@ -95,6 +95,49 @@ void init_conv(EngineBase& e, ConvLayer& L, const std::string& prefix, int Cout,
   L.b = e.add_param(prefix + ".bias", {Cout});
   L.Cout = Cout; L.Cin = Cin; L.k = k; L.stride = stride;
 }
+// conv-like layer whose registered weight has a non-OIHW shape with the same memory layout
+// (Conv1d [Cout,Cin,1], Linear [Cout,Cin]); used as a 1x1 convolution
+void init_conv_shape(EngineBase& e, ConvLayer& L, const std::string& prefix, std::vector<int64_t> wshape, int Cout,
+                     int Cin) {
+  L.w = e.add_param(prefix + ".weight", std::move(wshape));
+  L.b = e.add_param(prefix + ".bias", {Cout});
+  L.Cout = Cout; L.Cin = Cin; L.k = 1; L.stride = 1;
+}
+static void init_lin_attn(EngineBase& e, LinAttnLayer& L, const std::string& prefix, int C, int kv_in) {
+  L.C = C; L.kv_in = kv_in;
+  init_norm(e, L.norm_x, prefix + ".norm_x", C);
+  init_conv_shape(e, L.to_q, prefix + ".to_q", {C, C, 1}, C, C);
+  init_conv_shape(e, L.to_k, prefix + ".to_k", {C, kv_in, 1}, C, kv_in);
+  init_conv_shape(e, L.to_v, prefix + ".to_v", {C, kv_in, 1}, C, kv_in);
+  init_conv_shape(e, L.to_out, prefix + ".to_out.0", {C, C, 1}, C, C);
+  if (kv_in == C) {  // self-attention: engine-owned fused q|k|v projection (not part of the state_dict)
+    L.qkv_w.reset(new Param());
+    L.qkv_b.reset(new Param());
+    L.qkv_w->name = prefix + ".to_qkv(fused).weight";
+    L.qkv_w->shape = {3 * C, C, 1, 1};
+    L.qkv_b->shape = {3 * C};
+    L.qkv.w = L.qkv_w.get(); L.qkv.b = L.qkv_b.get();
+    L.qkv.Cout = 3 * C; L.qkv.Cin = C; L.qkv.k = 1; L.qkv.stride = 1;
+  }
+}
+// reference: attention_blocks.py:291-335 (Attention dispatcher), :233-288 (SpatialTransformer), :128-195
+void init_attention(EngineBase& e, SpatialAttnLayer& A, const std::string& prefix, int kind, int C, int emb_dim) {
+  A.kind = kind; A.C = C; A.heads = 8; A.d = C / 8; A.emb_dim = emb_dim;
+  if (kind == 1) {
+    init_lin_attn(e, A.cros_atn, prefix, C, emb_dim > 0 ? emb_dim : C);
+  } else if (kind == 2) {
+    init_norm(e, A.norm, prefix + ".norm", C);
+    init_conv(e, A.proj_in, prefix + ".proj_in", C, C, 1, 1);
+    const std::string tb = prefix + ".transformer_blocks.0";
+    init_lin_attn(e, A.self_atn, tb + ".self_atn", C, C);
+    if (emb_dim > 0) init_lin_attn(e, A.cros_atn, tb + ".cros_atn", C, emb_dim);
+    init_norm(e, A.ln, tb + ".proj_out.0.norm", C);
+    init_conv_shape(e, A.ff_in, tb + ".proj_out.0.proj", {8 * C, C}, 8 * C, C);
+    init_conv(e, A.ff_out, tb + ".proj_out.2", C, 4 * C, 1, 1);
+    init_conv(e, A.proj_out, prefix + ".proj_out", C, C, 1, 1);
+  }
+}
+
 void init_norm(EngineBase& e, NormLayer& L, const std::string& prefix, int C) {
   L.g = e.add_param(prefix + ".weight", {C});
   L.b = e.add_param(prefix + ".bias", {C});
@@ -156,7 +199,7 @@ int EngineBase::ensure_w_simt(ConvLayer& L) {
 
 // ---- op builders ---------------------------------------------------------------------------------
 int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const Tens& out, const Tens* stats,
-                         int* chunks) {
+                         int* chunks, const Tens* res, const float* emb, int emb_stride) {
   const int C1 = in1 ? in1->C : 0;
   MF_REQUIRE(in0.C + C1 == L.Cin, "conv input channels do not match the weight (" + L.w->name + ")");
   MF_REQUIRE(out.C == L.Cout, "conv output channels do not match the weight (" + L.w->name + ")");
@@ -177,6 +220,10 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
     d.bias = L.b->data.p;
     d.out = out.ptr; d.out_plane = out.plane; d.out_mode = out.layout == kNHWCSplit ? kOutSplit : kOutRaw;
     d.stats = stats ? stats->ptr : nullptr;
+    if (res) {
+      d.res = res->ptr; d.res_plane = res->plane; d.res_kind = res->layout == kNHWCSplit ? 1 : 2;
+    }
+    d.emb = emb; d.emb_stride = emb_stride;
     tc_plans.emplace_back(new ConvTcPlan());
     ConvTcPlan* plan = tc_plans.back().get();
     rc = conv_tc_build(d, plan);
@@ -186,6 +233,8 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
     return 0;
   }
   // exact fp32 SIMT path (single source only)
+  MF_REQUIRE(res == nullptr && emb == nullptr,
+             "fused residual / embedding epilogues exist on the tensor-core path only (" + L.w->name + ")");
   MF_REQUIRE(in1 == nullptr, "two-source convolution is only available on the tensor-core path (" + L.w->name +
                                  "): channels must be multiples of 32/64 and H*W a power of two >= 32");
   ++n_simt;
@@ -302,7 +351,7 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
 }
 
 int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks,
-                             const Tens* res, const float* emb, int emb_stride, const Tens& out) {
+                             const Tens* res, const float* emb, int emb_stride, const Tens& out, int act) {
   MF_REQUIRE(raw.C % groups == 0 && (raw.C / groups) % 8 == 0,
              "GroupNorm: channels per group must be a multiple of 8 (" + nl.g->name + ")");
   Tens mr = new_floats(static_cast<size_t>(raw.N) * groups * 2);
@@ -315,6 +364,7 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     }, kOpNorm);
     GnApplyDesc d{};
     d.raw = raw.ptr; d.mean_rstd = mr.ptr; d.gamma = nl.g->data.p; d.beta = nl.b->data.p;
+    d.raw_plane = raw.layout == kNHWCSplit ? raw.plane : 0; d.act = act;
     if (res) {
       d.res = res->ptr; d.res_plane = res->plane;
       d.res_kind = res->layout == kNHWCSplit ? kResSplit : kResRaw;
@@ -327,6 +377,152 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     push_op([d](cudaStream_t s) { return gn_apply(d, s); }, kOpNorm);
   }
   free_tensor(mr);
+  return 0;
+}
+
+int EngineBase::add_group_norm_split(const NormLayer& nl, int groups, const Tens& x, const Tens& out) {
+  MF_REQUIRE(x.layout == kNHWCSplit && x.C % 8 == 0, "group norm input must be a split tensor");
+  Tens part = new_floats(static_cast<size_t>(x.N) * (x.C / 8) * 2);
+  if (!dry) {
+    const float* xp = x.ptr; float* pp = part.ptr;
+    const long long plane = x.plane;
+    const int N = x.N, HW = x.H * x.W, C = x.C;
+    push_op([xp, pp, N, HW, C, plane](cudaStream_t s) { return gn_partial_from_raw(xp, pp, N, HW, C, s, plane); }, kOpNorm);
+  }
+  int rc = add_gn_apply(nl, groups, x, part, 1, nullptr, nullptr, 0, out, /*act=*/0);
+  free_tensor(part);
+  return rc;
+}
+
+int EngineBase::ensure_qkv(LinAttnLayer& L) {
+  if (L.qkv_version == version) return 0;
+  const size_t C = L.C;
+  MF_REQUIRE(L.qkv_w != nullptr, "fused qkv projection exists for self-attention only");
+  if (L.qkv_w->data.alloc(3 * C * C) || L.qkv_b->data.alloc(3 * C)) return 1;
+  const ConvLayer* src[3] = {&L.to_q, &L.to_k, &L.to_v};
+  for (int i = 0; i < 3; ++i) {
+    MF_CUDA_OK(cudaMemcpyAsync(L.qkv_w->data.p + i * C * C, src[i]->w->data.p, C * C * 4, cudaMemcpyDeviceToDevice,
+                               prep_stream));
+    MF_CUDA_OK(cudaMemcpyAsync(L.qkv_b->data.p + i * C, src[i]->b->data.p, C * 4, cudaMemcpyDeviceToDevice,
+                               prep_stream));
+  }
+  L.qkv_w->is_set = L.qkv_b->is_set = true;
+  L.qkv_version = version;
+  L.qkv.tc_version = -1;
+  return 0;
+}
+
+// Attention dispatcher (attention_blocks.py:331-335): 'none' -> identity; 'linear' -> LinearTransformer with the
+// embedding as its single key/value token; 'spatial' -> SpatialTransformer.
+int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, const Tens* emb, Tens* out) {
+  MF_REQUIRE(A.kind == 1 || A.kind == 2, "add_attention on an identity block");
+  MF_REQUIRE(x.layout == kNHWCSplit && x.C == A.C, "attention input must be a split tensor with C channels");
+  const int B = x.N, H = x.H, W = x.W, C = A.C, HW = H * W;
+  // ---- one-token cross attention: softmax over a single key is 1, so the block adds W_o (W_v emb + b_v) + b_o to every
+  //      position (attention_blocks.py:160-195 with embedding [B, E, 1]); q, k and the norm do not influence the result
+  Tens cb;
+  bool have_cb = false;
+  if (emb != nullptr && (A.kind == 1 || A.emb_dim > 0)) {
+    LinAttnLayer& X = A.cros_atn;
+    MF_REQUIRE(X.kv_in % 32 == 0 && C % 32 == 0 && X.kv_in <= 2048 && C <= 2048, "cross-attention widths must be multiples of 32");
+    Tens vv = new_floats(static_cast<size_t>(B) * C);
+    cb = new_floats(static_cast<size_t>(B) * C);
+    have_cb = true;
+    if (!dry) {
+      LinearDesc l1{};
+      l1.in_mode = 0; l1.in = emb->ptr; l1.W = X.to_v.w->data.p; l1.bias = X.to_v.b->data.p;
+      l1.out = vv.ptr; l1.post = 0; l1.B = B; l1.J = C; l1.K = X.kv_in;
+      push_op([l1](cudaStream_t s) { return linear_small(l1, s); }, kOpOther, 2.0 * B * C * X.kv_in);
+      LinearDesc l2{};
+      l2.in_mode = 0; l2.in = vv.ptr; l2.W = X.to_out.w->data.p; l2.bias = X.to_out.b->data.p;
+      l2.out = cb.ptr; l2.post = 0; l2.B = B; l2.J = C; l2.K = C;
+      push_op([l2](cudaStream_t s) { return linear_small(l2, s); }, kOpOther, 2.0 * B * C * C);
+    }
+    free_tensor(vv);
+  }
+  if (A.kind == 1) {
+    MF_REQUIRE(have_cb, "'linear' attention without an embedding (self-attention form) is not implemented");
+    Tens o = new_tensor(B, H, W, C, kNHWCSplit);
+    if (!dry) {
+      const float* ip = x.ptr; const long long ipl = x.plane; const float* bp = cb.ptr;
+      float* op = o.ptr; const long long opl = o.plane;
+      push_op([ip, ipl, bp, C, op, opl, B, HW](cudaStream_t s) {
+        return add_channel_bias_split(ip, ipl, bp, C, op, opl, B, HW, C, s);
+      }, kOpOther);
+    }
+    free_tensor(cb);
+    *out = o;
+    return 0;
+  }
+  // ---- SpatialTransformer (attention_blocks.py:276-288)
+  int rc = 0;
+  Tens h0 = new_tensor(B, H, W, C, kNHWCSplit);
+  rc = add_group_norm_split(A.norm, groups, x, h0);
+  if (rc) return rc;
+  Tens h1 = new_tensor(B, H, W, C, kNHWCSplit);
+  rc = add_conv(A.proj_in, h0, nullptr, h1, nullptr, nullptr);
+  if (rc) return rc;
+  free_tensor(h0);
+  // self attention (attention_blocks.py:160-195 with embedding None)
+  Tens xn = new_tensor(B, H, W, C, kNHWCSplit);
+  rc = add_group_norm_split(A.self_atn.norm_x, groups, h1, xn);
+  if (rc) return rc;
+  if (!dry) {
+    rc = ensure_qkv(A.self_atn);
+    if (rc) return rc;
+  }
+  Tens qkv = new_tensor(B, H, W, 3 * C, kNHWCRaw);
+  rc = add_conv(A.self_atn.qkv, xn, nullptr, qkv, nullptr, nullptr);
+  if (rc) return rc;
+  free_tensor(xn);
+  Tens ao = new_tensor(B, H, W, C, kNHWCSplit);
+  if (!dry) {
+    const float* qp = qkv.ptr; float* op = ao.ptr; const long long opl = ao.plane;
+    const int heads = A.heads, d = A.d;
+    push_op([qp, C, op, opl, B, HW, heads, d](cudaStream_t s) {
+      return attention_core(qp, qp + C, qp + 2 * C, 3 * C, op, opl, B, HW, heads, d, s);
+    }, kOpOther, 4.0 * B * heads * static_cast<double>(HW) * HW * d);
+  }
+  free_tensor(qkv);
+  // h2 = h1 + to_out(attn)  (+ cross-attention contribution, a per-sample channel vector)
+  Tens h2 = new_tensor(B, H, W, C, kNHWCSplit);
+  rc = add_conv(A.self_atn.to_out, ao, nullptr, h2, nullptr, nullptr, &h1, have_cb && !dry ? cb.ptr : nullptr, C);
+  if (rc) return rc;
+  free_tensor(ao);
+  free_tensor(h1);
+  if (have_cb) free_tensor(cb);
+  // feed-forward: LayerNorm -> Linear C->8C -> x*gelu(gate) -> conv1x1 4C->C, + residual (attention_blocks.py:17-25,214-231)
+  Tens ln = new_tensor(B, H, W, C, kNHWCSplit);
+  if (!dry) {
+    const float* ip = h2.ptr; const long long ipl = h2.plane; float* op = ln.ptr; const long long opl = ln.plane;
+    const float* g = A.ln.g->data.p; const float* bt = A.ln.b->data.p;
+    const long long tokens = static_cast<long long>(B) * HW;
+    push_op([ip, ipl, g, bt, op, opl, tokens, C](cudaStream_t s) {
+      return layernorm_split(ip, ipl, g, bt, op, opl, tokens, C, 1e-5f, s);
+    }, kOpNorm);
+  }
+  Tens gg = new_tensor(B, H, W, 8 * C, kNHWCRaw);
+  rc = add_conv(A.ff_in, ln, nullptr, gg, nullptr, nullptr);
+  if (rc) return rc;
+  free_tensor(ln);
+  Tens ge = new_tensor(B, H, W, 4 * C, kNHWCSplit);
+  if (!dry) {
+    const float* ip = gg.ptr; float* op = ge.ptr; const long long opl = ge.plane;
+    const long long tokens = static_cast<long long>(B) * HW;
+    const int Ch = 4 * C;
+    push_op([ip, op, opl, tokens, Ch](cudaStream_t s) { return geglu_split(ip, op, opl, tokens, Ch, s); }, kOpOther);
+  }
+  free_tensor(gg);
+  Tens h4 = new_tensor(B, H, W, C, kNHWCSplit);
+  rc = add_conv(A.ff_out, ge, nullptr, h4, nullptr, nullptr, &h2);
+  if (rc) return rc;
+  free_tensor(ge);
+  free_tensor(h2);
+  Tens o = new_tensor(B, H, W, C, kNHWCSplit);
+  rc = add_conv(A.proj_out, h4, nullptr, o, nullptr, nullptr, &x);
+  if (rc) return rc;
+  free_tensor(h4);
+  *out = o;
   return 0;
 }
 

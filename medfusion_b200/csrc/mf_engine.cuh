@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "mf_attn.cuh"
 #include "mf_conv_tc.cuh"
 #include "mf_kernels.cuh"
 
@@ -71,6 +72,27 @@ struct ResBlockLayer {
   int Cin = 0, Cout = 0;
 };
 
+// LinearTransformer (attention_blocks.py:128-195): GroupNorm + q/k/v/out 1x1 projections
+struct LinAttnLayer {
+  NormLayer norm_x;
+  ConvLayer to_q, to_k, to_v, to_out;
+  int C = 0, kv_in = 0;                 // kv_in: channels feeding k/v (C for self-attention, emb_dim for cross)
+  // fused [3C][C] q|k|v projection (self-attention only), engine-owned copies of the three registered tensors
+  std::unique_ptr<Param> qkv_w, qkv_b;
+  ConvLayer qkv;
+  int qkv_version = -1;
+};
+// SpatialTransformer with one BasicTransformerBlock (attention_blocks.py:200-288)
+struct SpatialAttnLayer {
+  int kind = 0;                         // 0 none, 1 'linear', 2 'spatial'
+  int C = 0, heads = 8, d = 0, emb_dim = 0;
+  NormLayer norm;                       // .norm
+  ConvLayer proj_in, proj_out;          // .proj_in / .proj_out (1x1)
+  LinAttnLayer self_atn, cros_atn;      // .transformer_blocks.0.{self_atn,cros_atn}  ('linear': cros_atn only)
+  NormLayer ln;                         // .transformer_blocks.0.proj_out.0.norm (LayerNorm over C)
+  ConvLayer ff_in, ff_out;              // GEGLU Linear C -> 8C, then 1x1 conv 4C -> C
+};
+
 // ---- workspace arena (static planning; single-stream ordering makes reuse safe) ------------------
 struct Arena {
   struct Block { size_t off, size; };
@@ -128,7 +150,13 @@ class EngineBase {
 
   // conv: in0 (+ optional in1 channel-concatenated) -> out.  If stats != nullptr the (sum, sumsq)
   // partials of the output are produced too and *chunks receives their chunk count.
-  int add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const Tens& out, const Tens* stats, int* chunks);
+  int add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const Tens& out, const Tens* stats, int* chunks,
+               const Tens* res = nullptr, const float* emb = nullptr, int emb_stride = 0);
+  // GroupNorm (no activation) of a split tensor -> split
+  int add_group_norm_split(const NormLayer& nl, int groups, const Tens& x, const Tens& out);
+  // attention block applied to x (split) -> *out (split).  emb: raw [B, emb_dim] embedding (may be null)
+  int add_attention(SpatialAttnLayer& A, int groups, const Tens& x, const Tens* emb, Tens* out);
+  int ensure_qkv(LinAttnLayer& L);
   // conv reading an external NCHW fp32 pointer that is only known at call time
   int add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, int Cin, int H, int W, const Tens& out,
                        const Tens* stats, int* chunks);
@@ -138,7 +166,7 @@ class EngineBase {
   // (shapes the tensor-core path cannot take) an explicit upsample followed by add_conv.
   int add_upconv2x(ConvLayer& L, const Tens& in, Tens* out);
   int add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks, const Tens* res,
-                   const float* emb, int emb_stride, const Tens& out);
+                   const float* emb, int emb_stride, const Tens& out, int act = 1);
   // full res block: in0 (+in1 concat) -> returns output tensor (split)
   int add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, const Tens* in1, const Tens* embT, int emb_stride,
                    Tens* out);
@@ -151,6 +179,9 @@ class EngineBase {
 
 void init_conv(EngineBase& e, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int k, int stride);
 void init_norm(EngineBase& e, NormLayer& L, const std::string& prefix, int C);
+void init_conv_shape(EngineBase& e, ConvLayer& L, const std::string& prefix, std::vector<int64_t> wshape, int Cout,
+                     int Cin);
+void init_attention(EngineBase& e, SpatialAttnLayer& A, const std::string& prefix, int kind, int C, int emb_dim);
 void init_resblock(EngineBase& e, ResBlockLayer& rb, const std::string& prefix, int Cin, int Cout, int k, int emb_dim);
 
 }  // namespace mf

@@ -295,13 +295,20 @@ int conv_simt(const ConvSimtDesc& d, cudaStream_t s) {
 // GroupNorm (reference: conv_blocks.py:177,187 -> nn.GroupNorm(eps=1e-5, affine), biased variance)
 // =================================================================================================
 // One block per (n, 8-channel slab): sum / sumsq over all pixels.  Only used after SIMT convs.
-__global__ void gn_partial_from_raw_kernel(const float* __restrict__ raw, float* __restrict__ partial, int HW, int C) {
+__global__ void gn_partial_from_raw_kernel(const float* __restrict__ raw, long long plane, float* __restrict__ partial,
+                                           int HW, int C) {
   const int n = blockIdx.y, g8 = blockIdx.x;
   const float* base = raw + static_cast<long long>(n) * HW * C + g8 * 8;
   float s = 0.f, ss = 0.f;
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-    const float4 a = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C);
-    const float4 b = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C + 4);
+    float4 a = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C);
+    float4 b = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C + 4);
+    if (plane != 0) {  // split tensor: x = hi + lo
+      const float4 al = *reinterpret_cast<const float4*>(base + plane + static_cast<long long>(p) * C);
+      const float4 bl = *reinterpret_cast<const float4*>(base + plane + static_cast<long long>(p) * C + 4);
+      a.x += al.x; a.y += al.y; a.z += al.z; a.w += al.w;
+      b.x += bl.x; b.y += bl.y; b.z += bl.z; b.w += bl.w;
+    }
     s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
     ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
   }
@@ -329,10 +336,10 @@ __global__ void gn_partial_from_raw_kernel(const float* __restrict__ raw, float*
   }
 }
 
-int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s) {
+int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s, long long plane) {
   MF_REQUIRE(C % 8 == 0, "GroupNorm partial sums need C % 8 == 0");
   dim3 grid(C / 8, N);
-  gn_partial_from_raw_kernel<<<grid, 256, 0, s>>>(raw, partial, HW, C);
+  gn_partial_from_raw_kernel<<<grid, 256, 0, s>>>(raw, plane, partial, HW, C);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -388,14 +395,20 @@ __global__ void gn_apply_kernel(const GnApplyDesc d) {
     const long long pix = i / c4n;
     const int n = static_cast<int>(pix / d.HW);
     const long long off = pix * d.C + c;
-    const float4 x = *reinterpret_cast<const float4*>(d.raw + off);
+    float4 x = *reinterpret_cast<const float4*>(d.raw + off);
+    if (d.raw_plane != 0) {
+      const float4 xl = *reinterpret_cast<const float4*>(d.raw + d.raw_plane + off);
+      x.x += xl.x; x.y += xl.y; x.z += xl.z; x.w += xl.w;
+    }
     const float2 mr = *reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + c / cpg) * 2);
     const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
     const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + c));
     float y[4] = {(x.x - mr.x) * mr.y * ga.x + be.x, (x.y - mr.x) * mr.y * ga.y + be.y,
                   (x.z - mr.x) * mr.y * ga.z + be.z, (x.w - mr.x) * mr.y * ga.w + be.w};
+    if (d.act != 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
+      for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
+    }
     if (d.res_kind == kResSplit) {
       const float4 rh = *reinterpret_cast<const float4*>(d.res + off);
       const float4 rl = *reinterpret_cast<const float4*>(d.res + d.res_plane + off);

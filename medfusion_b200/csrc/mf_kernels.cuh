@@ -38,13 +38,16 @@ int conv_simt(const ConvSimtDesc& d, cudaStream_t s);
 
 // ---- GroupNorm ------------------------------------------------------------------------------------
 // partial stats layout (shared with conv_tc epilogue): [N][chunks][C/8][2] = (sum, sumsq) over 8 channels
-int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s);
+// plane != 0: `raw` is a split tensor (x = hi + lo)
+int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s, long long plane = 0);
 // partial -> (mean, rstd) per (n, group): out [N][G][2]
 int gn_finalize(const float* partial, float* mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
                 cudaStream_t s);
 enum ResKind : int { kResNone = 0, kResSplit = 1, kResRaw = 2 };
 struct GnApplyDesc {
   const float* raw;         // [N,HW,C] conv output (+bias)
+  long long raw_plane;      // != 0: input is a split tensor (hi + lo)
+  int act;                  // 1: Swish after the affine (conv blocks), 0: none (attention-block norms)
   const float* mean_rstd;   // [N][G][2]
   const float* gamma; const float* beta;  // [C]
   const float* res; long long res_plane; int res_kind;

@@ -3,8 +3,8 @@
 
 Same constructor keywords, same state_dict keys, same `forward(x_t, t, condition, self_cond) -> (y, y_ver)`
 contract; the arithmetic is a launch plan of sm_100a kernels inside libmedfusion_b200.so
-(mf_unet_forward).  Options of the reference that are outside the sampling hot path of the
-canonical model raise NotImplementedError instead of silently diverging.
+(mf_unet_forward).  Attention blocks ('linear' / 'spatial', attention_blocks.py) are supported; options of the reference that
+are outside the sampling hot path raise NotImplementedError instead of silently diverging.
 """
 from __future__ import annotations
 
@@ -63,8 +63,11 @@ class UNet(EngineModule):
         if _name_of(act_name) != "swish" or _name_of(norm_name) != "group":
             raise NotImplementedError("only Swish + GroupNorm are implemented")
         attn = list(use_attention) if isinstance(use_attention, (list, tuple)) else [use_attention] * len(strides)
-        if any(a != "none" for a in attn):
-            raise NotImplementedError("attention ('linear'/'spatial') is not implemented yet; use 'none'")
+        attn_codes = {"none": 0, "linear": 1, "spatial": 2}
+        if any(a not in attn_codes for a in attn) or len(attn) != len(strides):
+            raise ValueError("use_attention entries must be 'none', 'linear' or 'spatial' (one per level)")
+        if any(a != "none" for a in attn) and time_embedder is None:
+            raise NotImplementedError("attention blocks without a time embedder are not implemented")
         depth = len(strides)
         if not (len(hid_chs) == len(kernel_sizes) == depth) or depth > _lib.MF_MAX_LEVELS:
             raise ValueError("hid_chs, kernel_sizes and strides must have equal length <= 8")
@@ -87,7 +90,7 @@ class UNet(EngineModule):
         cfg.in_ch, cfg.out_ch, cfg.depth = in_ch, (out_ch * 2 if estimate_variance else out_ch), depth
         for i in range(depth):
             cfg.hid_chs[i], cfg.kernel_sizes[i], cfg.strides[i] = hid_chs[i], kernel_sizes[i], strides[i]
-            cfg.attention[i] = 0
+            cfg.attention[i] = attn_codes[attn[i]]
         cfg.num_res_blocks = num_res_blocks
         cfg.emb_dim = self.time_spec.emb_dim if self.time_spec is not None else 0
         cfg.pos_emb_dim = self.time_spec.pos_emb_dim if self.time_spec is not None else 0
@@ -97,7 +100,8 @@ class UNet(EngineModule):
         _lib.check(_lib.load().mf_unet_create(ctypes.byref(cfg), ctypes.byref(handle)), "mf_unet_create")
         # zero-initialised modules of the reference: 2nd conv of every res block (conv_blocks.py:336 -> :174)
         # and the output head (unet2.py:213)
-        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc."))
+        # ... plus every attention output projection (attention_blocks.py:149-152)
+        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc.", "*.to_out.0."))
 
     # ------------------------------------------------------------------------------------------
     def _after_param_sync(self, stream):

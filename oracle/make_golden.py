@@ -31,6 +31,10 @@ UNET_SMALL = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[64, 64, 128, 256],
                   strides=[1, 2, 2, 2], norm_name=("GROUP", {"num_groups": 8, "affine": True}),
                   time_embedder_kwargs={"emb_dim": 256}, cond_embedder_kwargs={"emb_dim": 256, "num_classes": 2},
                   deep_supervision=False, use_res_block=True, use_attention="none")
+UNET_ATTN = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[64, 64, 256, 256], kernel_sizes=[3, 3, 3, 3],
+                 strides=[1, 2, 2, 2], norm_name=("GROUP", {"num_groups": 8, "affine": True}),
+                 time_embedder_kwargs={"emb_dim": 256}, cond_embedder_kwargs={"emb_dim": 256, "num_classes": 2},
+                 deep_supervision=False, use_res_block=True, use_attention=["none", "linear", "none", "spatial"])
 UNET_CANON = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
                   strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
                   cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False,
@@ -155,6 +159,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     unet_fixture("unet_small.pt", UNET_SMALL, 1)
     unet_fixture("unet_canonical.pt", UNET_CANON, 2)
+    unet_fixture("unet_attn_small.pt", UNET_ATTN, 3)
     vae_fixture()
     sched_fixture()
     sample_fixture()

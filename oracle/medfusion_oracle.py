@@ -91,7 +91,73 @@ def time_embedding(sd, t, pos_dim):
 
 
 # ------------------------------------------------------------------------------------------------
-# UNet (models/estimators/unet2.py:222-269), attention 'none'
+# attention blocks (models/utils/attention_blocks.py)
+# ------------------------------------------------------------------------------------------------
+def compute_attention(q, k, v, heads, scale):
+    """attention_blocks.py:35-43 — q,k,v [B, heads*d, N]; softmax((q*s)^T (k*s)) v"""
+    b, c, n = q.shape
+    d = c // heads
+    q, k, v = (t.reshape(b * heads, d, -1) for t in (q, k, v))
+    attn = torch.einsum("bdi,bdj->bij", q * scale, k * scale).softmax(dim=-1)
+    out = torch.einsum("bij,bdj->bdi", attn, v)
+    return out.reshape(b, c, -1)
+
+
+def linear_transformer(sd, pre, x, groups, heads, embedding=None):
+    """LinearTransformer.forward (attention_blocks.py:160-195); embedding [B, E] -> one key/value token"""
+    b, c = x.shape[:2]
+    spatial = x.shape[2:]
+    x_n = F.group_norm(x, groups, sd[pre + ".norm_x.weight"], sd[pre + ".norm_x.bias"], eps=1e-5)
+    emb = x_n if embedding is None else embedding.reshape(*embedding.shape[:2], *([1] * (x.ndim - 2)))
+    x_n = x_n.reshape(b, c, -1)
+    emb = emb.reshape(*emb.shape[:2], -1)
+    q = F.conv1d(x_n, sd[pre + ".to_q.weight"], sd[pre + ".to_q.bias"])
+    k = F.conv1d(emb, sd[pre + ".to_k.weight"], sd[pre + ".to_k.bias"])
+    v = F.conv1d(emb, sd[pre + ".to_v.weight"], sd[pre + ".to_v.bias"])
+    scale = (c // heads) ** -0.25
+    out = compute_attention(q, k, v, heads, scale)
+    out = F.conv1d(out, sd[pre + ".to_out.0.weight"], sd[pre + ".to_out.0.bias"])
+    return x + out.reshape(b, c, *spatial)
+
+
+def geglu(sd, pre, x):
+    """GEGLU.forward (attention_blocks.py:17-25)"""
+    b, c = x.shape[:2]
+    spatial = x.shape[2:]
+    h = x.reshape(b, c, -1).transpose(1, 2)
+    h = F.layer_norm(h, (c,), sd[pre + ".norm.weight"], sd[pre + ".norm.bias"], eps=1e-5)
+    h, gate = F.linear(h, sd[pre + ".proj.weight"], sd[pre + ".proj.bias"]).chunk(2, dim=-1)
+    h = h * F.gelu(gate)
+    return h.transpose(1, 2).reshape(b, -1, *spatial)
+
+
+def spatial_transformer(sd, pre, x, groups, heads, embedding):
+    """SpatialTransformer.forward (attention_blocks.py:276-288) with one BasicTransformerBlock (:223-231)"""
+    h = F.group_norm(x, groups, sd[pre + ".norm.weight"], sd[pre + ".norm.bias"], eps=1e-5)
+    h = F.conv2d(h, sd[pre + ".proj_in.weight"], sd[pre + ".proj_in.bias"])
+    tb = pre + ".transformer_blocks.0"
+    h = linear_transformer(sd, tb + ".self_atn", h, groups, heads, None)
+    if embedding is not None and tb + ".cros_atn.to_q.weight" in sd:
+        h = linear_transformer(sd, tb + ".cros_atn", h, groups, heads, embedding)
+    o = geglu(sd, tb + ".proj_out.0", h)
+    o = F.conv2d(o, sd[tb + ".proj_out.2.weight"], sd[tb + ".proj_out.2.bias"])
+    h = o + h
+    h = F.conv2d(h, sd[pre + ".proj_out.weight"], sd[pre + ".proj_out.bias"])
+    return h + x
+
+
+def attention(sd, pre, x, emb, groups, heads=8):
+    """Attention.forward (attention_blocks.py:331-335): dispatch on which parameters exist"""
+    pre = pre + ".attention"
+    if pre + ".proj_in.weight" in sd:
+        return spatial_transformer(sd, pre, x, groups, heads, emb)
+    if pre + ".to_q.weight" in sd:
+        return linear_transformer(sd, pre, x, groups, heads, emb)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet (models/estimators/unet2.py:222-269)
 # ------------------------------------------------------------------------------------------------
 def unet_forward(sd, cfg, x_t, t, cond=None):
     """cfg: dict(hid_chs, strides, num_res_blocks, groups, pos_emb_dim). Returns y (y_ver is empty)."""
@@ -104,18 +170,21 @@ def unet_forward(sd, cfg, x_t, t, cond=None):
     idx = 0
     for i in range(1, depth):                                                          # unet2.py:250-251
         for _ in range(nrb):
-            xs.append(unet_res_block(sd, f"in_blocks.{idx}.0", xs[-1], emb, G))
+            h = unet_res_block(sd, f"in_blocks.{idx}.0", xs[-1], emb, G)
+            xs.append(attention(sd, f"in_blocks.{idx}.1", h, emb, G))                  # SequentialEmb, conv_blocks.py:21-25
             idx += 1
         if i < depth - 1:
             xs.append(conv2d(sd, f"in_blocks.{idx}.down_op", xs[-1], stride=strides[i]))  # conv_blocks.py:66-70
             idx += 1
     h = unet_res_block(sd, "middle_block.0", xs[-1], emb, G)                           # unet2.py:254
+    h = attention(sd, "middle_block.1", h, emb, G)
     h = unet_res_block(sd, "middle_block.2", h, emb, G)
     n_out = (depth - 1) * (nrb + 1)
     for i in range(n_out, 0, -1):                                                      # unet2.py:258-264
         h = torch.cat([h, xs.pop()], dim=1)
         pre = f"out_blocks.{i - 1}"
         h = unet_res_block(sd, pre + ".0", h, emb, G)
+        h = attention(sd, pre + ".1", h, emb, G)
         if pre + ".2.up_op.weight" in sd:
             level = (i - 1) // (nrb + 1) + 1
             h = basic_up(sd, pre + ".2.up_op", h, strides[level])

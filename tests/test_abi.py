@@ -34,7 +34,7 @@ def test_missing_library_fails_loudly(monkeypatch):
         _lib.load()
 
 
-@pytest.mark.parametrize("fixture", ["unet_small.pt", "unet_canonical.pt"])
+@pytest.mark.parametrize("fixture", ["unet_small.pt", "unet_canonical.pt", "unet_attn_small.pt"])
 def test_unet_state_dict_matches_reference(fixture):
     g = load_golden(fixture)
     m = make_unet(g["cfg"])
@@ -92,8 +92,8 @@ def test_unsupported_options_raise():
     from medfusion_b200.models import UNet, VAE, DiffusionPipeline, GaussianNoiseScheduler
     with pytest.raises(NotImplementedError):
         UNet(in_ch=8, out_ch=8, spatial_dims=3)
-    with pytest.raises(NotImplementedError):
-        UNet(in_ch=8, out_ch=8, spatial_dims=2, deep_supervision=False, use_attention="spatial")
+    with pytest.raises(ValueError):
+        UNet(in_ch=8, out_ch=8, spatial_dims=2, deep_supervision=False, use_attention="flash")
     with pytest.raises(NotImplementedError):
         VAE(spatial_dims=3)
     with pytest.raises(ValueError):

@@ -196,3 +196,43 @@ def test_scheduler_cfg_and_ddim_against_oracle():
         assert_close(o["x_prior"].cpu(), prior, what="cfg prior")
         assert_close(o["x_0"].cpu(), x0, what="cfg x_0")
         assert_close(o["x_next"].cpu(), nxt, what="ddim re-noise")
+
+
+@pytest.mark.parametrize("B,N,heads,d", [(2, 64, 8, 32), (1, 256, 8, 128), (3, 100, 4, 64)])
+def test_attention_core_matches_oracle(B, N, heads, d):
+    import ctypes
+    import medfusion_oracle as O
+    from medfusion_b200 import _lib, ops
+    g = torch.Generator().manual_seed(N + d)
+    C = heads * d
+    qkv = _rnd(g, B, N, 3 * C)
+    q, k, v = (qkv[..., i * C:(i + 1) * C].transpose(1, 2).contiguous() for i in range(3))   # [B, C, N]
+    ref = O.compute_attention(q, k, v, heads, d ** -0.25).transpose(1, 2)                      # [B, N, C]
+    dq = qkv.to(DEV).contiguous()
+    out = torch.empty((2, B, N, 1, C), device=DEV)
+    _lib.check(_lib.load().mf_op_attention(dq.data_ptr(), dq.data_ptr() + 4 * C, dq.data_ptr() + 8 * C, 3 * C,
+                                           out.data_ptr(), out[0].numel(), B, N, heads, d,
+                                           torch.cuda.current_stream().cuda_stream), "attention")
+    got = (out[0] + out[1]).reshape(B, N, C).cpu()
+    assert_close(got, ref, what="attention core")
+
+
+def test_layernorm_and_geglu_match_oracle():
+    from medfusion_b200 import _lib, ops
+    g = torch.Generator().manual_seed(12)
+    T, C = 192, 256
+    x = _rnd(g, T, C) * 3 + 1
+    gamma, beta = 1 + 0.1 * _rnd(g, C), 0.1 * _rnd(g, C)
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    xs = ops.pack_split(x.t().reshape(1, C, T, 1).contiguous().to(DEV))                      # [2,1,T,1,C]
+    out = torch.empty_like(xs)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.mf_op_layernorm(xs.data_ptr(), xs[0].numel(), gamma.to(DEV).data_ptr(), beta.to(DEV).data_ptr(),
+                                   out.data_ptr(), out[0].numel(), T, C, 1e-5, st), "layernorm")
+    assert_close((out[0] + out[1]).reshape(T, C).cpu(), ref, what="layernorm")
+    z = _rnd(g, T, 2 * C)
+    refg = z[:, :C] * F.gelu(z[:, C:])
+    zo = torch.empty((2, T, C), device=DEV)
+    _lib.check(lib.mf_op_geglu(z.to(DEV).data_ptr(), zo.data_ptr(), zo[0].numel(), T, C, st), "geglu")
+    assert_close((zo[0] + zo[1]).cpu(), refg, what="geglu")

@@ -17,6 +17,18 @@ def _vae_cfg(cfg):
     return {k: v for k, v in cfg.items() if k in VAE_KEEP}
 
 
+def test_unet_with_attention_matches_reference_fixture():
+    """use_attention=['none','linear','none','spatial']: LinearTransformer with the embedding token (level 1) and
+    SpatialTransformer blocks (level 3 + middle) — attention_blocks.py."""
+    g = load_golden("unet_attn_small.pt")
+    m = make_unet(g["cfg"], DEV)
+    x, t, c = g["x"].to(DEV), g["t"].to(DEV), g["cond"].to(DEV)
+    y, _ = m(x, t, c)
+    assert_close(y.cpu(), g["y_cond"], what="attention cond")
+    y, _ = m(x, t, None)
+    assert_close(y.cpu(), g["y_uncond"], what="attention uncond")
+
+
 @pytest.mark.parametrize("fixture", ["unet_small.pt", "unet_canonical.pt"])
 def test_unet_forward_matches_reference_fixture(fixture):
     g = load_golden(fixture)
