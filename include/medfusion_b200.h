@@ -43,6 +43,9 @@ int mf_set_drain_interval(int k_blocks);
 int mf_set_cta_group(int cta_group);
 /* Output channels per tcgen05 tile (0 = auto, 64, 128, 256; reduced automatically until it divides Cout). */
 int mf_set_block_n(int block_n);
+/* 1 (default): persistent stream-K schedule — one CTA group per SM, (tile, K block) units split evenly, split tiles
+ * reduced through a scratch buffer; 0: one output tile per CTA group. */
+int mf_set_stream_k(int enable);
 /* Relative correction applied to every drained TMEM partial sum, per K block of the drain interval, compensating the
  * round-toward-zero bias of the tcgen05 accumulator (0 disables, negative = built-in calibrated table, the default). */
 int mf_set_debias_eps(float eps_per_kblock);

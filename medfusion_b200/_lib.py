@@ -49,6 +49,7 @@ SIGNATURES = {
     "mf_set_drain_interval": (c_int, [c_int]),
     "mf_set_cta_group": (c_int, [c_int]),
     "mf_set_block_n": (c_int, [c_int]),
+    "mf_set_stream_k": (c_int, [c_int]),
     "mf_set_fold_upsample": (c_int, [c_int]),
     "mf_set_debias_eps": (c_int, [c_float]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
@@ -125,6 +126,8 @@ def load():
         lib.mf_set_fold_upsample(int(os.environ["MF_FOLD_UPSAMPLE"]))
     if os.environ.get("MF_DEBIAS_EPS"):
         lib.mf_set_debias_eps(float(os.environ["MF_DEBIAS_EPS"]))
+    if os.environ.get("MF_STREAM_K"):
+        lib.mf_set_stream_k(int(os.environ["MF_STREAM_K"]))
     if os.environ.get("MF_BLOCK_N"):
         lib.mf_set_block_n(int(os.environ["MF_BLOCK_N"]))
     if os.environ.get("MF_DRAIN_INTERVAL"):

@@ -406,6 +406,10 @@ int mf_set_fold_upsample(int enable) {
   mf::g_fold_upsample = enable ? 1 : 0;
   return 0;
 }
+int mf_set_stream_k(int enable) {
+  mf::g_stream_k = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_block_n(int block_n) {
   MF_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 0, 64, 128 or 256");
   mf::g_default_block_n = block_n;

@@ -1,6 +1,7 @@
 // See mf_conv_tc.cuh for the design.  sm_100a only: TMA + mbarrier pipeline + tcgen05.mma (TMEM accumulators).
 #include "mf_conv_tc.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 
@@ -9,6 +10,7 @@ namespace mf {
 int g_default_drain_interval = 2;
 int g_default_cta_group = 0;
 int g_default_block_n = 0;    // 0 = auto
+int g_stream_k = 1;           // persistent stream-K schedule (0: one tile per CTA group)
 float g_debias_eps_per_kblock = -1.0f;  // < 0: calibrated table (default); 0: off; > 0: explicit relative correction per K block  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
@@ -34,25 +36,32 @@ struct TcCfg {
 // Why the accumulation leaves the tensor core: tcgen05.mma adds into its fp32 TMEM accumulator with
 // truncation (round-toward-zero), so a long chain of MMAs drifts by ~0.5 ulp(|acc|) per instruction
 // (measured: 2e-4 abs at K=2304, i.e. far outside the 1e-5 parity budget).  We therefore let the
-// tensor core produce SHORT partial sums (one 32-channel K block: 8 tiny cross-term MMAs first, then the
-// 4 hi*hi MMAs) into one of two TMEM buffers, and the drain warps add each finished partial into
-// round-to-nearest fp32 running sums held in registers while the next K block is being multiplied.
+// tensor core produce SHORT partial sums (`drain_interval` 32-channel K blocks: the tiny cross-term MMAs first,
+// then the hi*hi MMAs) into a ring of TMEM buffers, and the drain warps add each finished partial (de-biased)
+// into round-to-nearest fp32 running sums held in registers while the next K blocks are being multiplied.
 //
 // CG == 2: two CTAs of a cluster (one TPC) form a pair.  Each stages its own 128 pixel rows of A and HALF of the
 // weight tile; the leader CTA issues 256-row tcgen05.mma.cta_group::2 instructions that read both CTAs' shared
 // memory and write both CTAs' TMEM.  Per CTA a stage shrinks from 96 KB to 64 KB (3 stages in flight instead of 2)
 // and the weight traffic per SM halves.
+//
+// Persistent stream-K schedule: the launch has at most one CTA group per SM (pair).  All (tile, K block) units of
+// the convolution are split EVENLY over the groups, so there is no partial last wave (512 tiles on 148 SMs used to
+// cost 4 waves for 3.46 waves of work).  A group whose range starts inside a tile writes that tile's partial sums
+// to a scratch buffer and raises a flag; the group that owns the tile's first K block waits for the flag(s), adds
+// the partials and runs the epilogue.  Partial writers always process that segment FIRST, finalizers process theirs
+// LAST, so nobody waits on work that has not been scheduled.
 template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, CG>;
   constexpr int CPW = Cfg::kColsPerWarp;
+  constexpr int NB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);  // [kStages] TMA -> MMA (leader CTA's are the live ones)
   uint64_t* empty_bar = full_bar + Cfg::kStages;           // [kStages] MMA -> TMA (every CTA)
-  constexpr int NB = Cfg::kAccBufs;
   uint64_t* acc_full_bar = empty_bar + Cfg::kStages;       // [NB] MMA -> drain (every CTA)
   uint64_t* acc_empty_bar = acc_full_bar + NB;             // [NB] drain -> MMA (leader CTA's)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + NB);
@@ -63,23 +72,32 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
 
-  // ---- tile coordinates -------------------------------------------------------------------------
-  const int mt = blockIdx.x;
-  const int nt = blockIdx.y;
-  const int tw = mt % p.tiles_w;
-  const int th = (mt / p.tiles_w) % p.tiles_h;
-  const int tn = mt / (p.tiles_w * p.tiles_h);   // may run past tiles_n for the padding CTA of an odd pair
-  const int n0 = tn * p.bn, h0 = th * p.bh, w0 = tw * p.bw;
+  // ---- work decomposition ---------------------------------------------------------------------------
   const int cin = p.C0 + p.C1;
   const int cblks = cin / kTcBlockK;
   const int nkb = p.ntaps * cblks;
-  // nearest-x2 + conv3x3 folded into four 2x2 phase convolutions on the low-resolution input (blockIdx.z = phase):
-  // output pixel (2h+oa, 2w+ob) reads input rows {h+oa-1, h+oa} and cols {w+ob-1, w+ob} with pre-summed weights.
-  const int phase = p.up2 ? static_cast<int>(blockIdx.z) : 0;
-  const int oa = phase >> 1, ob = phase & 1;
-  const int osf = p.up2 ? 2 : 1;
   const int drain = p.drain_interval < 1 ? 1 : p.drain_interval;  // K blocks per TMEM partial sum
-  const int nchunks = (nkb + drain - 1) / drain;
+  const int group = static_cast<int>(blockIdx.x) / CG;            // CTA group (pair) index
+  const int ngroups = static_cast<int>(gridDim.x) / CG;
+  const long long total_units = static_cast<long long>(p.num_tiles) * nkb;
+  const long long u_begin = total_units * group / ngroups;
+  const long long u_end = total_units * (group + 1) / ngroups;
+
+  // tile id -> coordinates.  tile = ((phase * n_tiles) + nt) * m_groups + mg   (M fastest: neighbours share weights)
+  struct TileCoord { int nt, phase, n0, h0, w0, th, tw; };
+  auto decode_tile = [&](int tile) {
+    TileCoord c;
+    const int mg = tile % p.m_groups;
+    const int rest = tile / p.m_groups;
+    c.nt = rest % p.n_tiles;
+    c.phase = rest / p.n_tiles;
+    const int mt = mg * CG + static_cast<int>(cta_rank);   // may run past the real tile count: padding CTA of an odd pair
+    c.tw = mt % p.tiles_w;
+    c.th = (mt / p.tiles_w) % p.tiles_h;
+    const int tn = mt / (p.tiles_w * p.tiles_h);
+    c.n0 = tn * p.bn; c.h0 = c.th * p.bh; c.w0 = c.tw * p.bw;
+    return c;
+  };
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -105,243 +123,325 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register re-partitioning (setmaxnreg): the TMA / MMA warpgroup needs a handful of registers, the two drain
+  // warpgroups hold 128 fp32 running sums per thread.  384 threads x 168 = 128 x 72 + 256 x 216.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        // K order is channel-block major, tap minor: the 9 taps of one 32-channel slab are consecutive, so the
-        // shifted re-reads of the same activation lines hit in L2 (tap-major order thrashed it: 1.9 GB of DRAM
-        // reads for a 134 MB input at Cin=1024, profiles/r01_conv_tc_ncu_raw.md).
-        const int cb = kb / p.ntaps;
-        const int tap = kb - cb * p.ntaps;
-        const int c = cb * kTcBlockK;
-        const int x = p.up2 ? (w0 + ob - 1 + (tap & 1)) : (w0 + p.dx[tap]);
-        const int y = p.up2 ? (h0 + oa - 1 + (tap >> 1)) : (h0 + p.dy[tap]);
-        const CUtensorMap* ma;
-        int cc = c;
-        if (p.per_tap_map) {
-          ma = &maps.a[p.tap_map[tap]];
-        } else if (c < p.C0) {
-          ma = &maps.a[0];
-        } else {
-          ma = &maps.a[1];
-          cc = c - p.C0;
+      int it = 0;  // running K-block count -> smem stage / phase
+      for (long long u = u_begin; u < u_end;) {
+        const int tile = static_cast<int>(u / nkb);
+        const int kb0 = static_cast<int>(u - static_cast<long long>(tile) * nkb);
+        const int kb1 = static_cast<int>(min(static_cast<long long>(nkb), kb0 + (u_end - u)));
+        const TileCoord tc = decode_tile(tile);
+        const int oa = tc.phase >> 1, ob = tc.phase & 1;
+        const int brow = tc.phase * p.Cout + tc.nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          // K order is channel-block major, tap minor: the 9 taps of one 32-channel slab are consecutive, so the
+          // shifted re-reads of the same activation lines hit in L2 (tap-major order thrashed it: 1.9 GB of DRAM
+          // reads for a 134 MB input at Cin=1024, profiles/r01_conv_tc_ncu_raw.md).
+          const int cb = kb / p.ntaps;
+          const int tap = kb - cb * p.ntaps;
+          const int c = cb * kTcBlockK;
+          // up2: nearest-x2 + conv3x3 folded into four 2x2 phase convolutions on the low-resolution input:
+          // output pixel (2h+oa, 2w+ob) reads input rows {h+oa-1, h+oa} and cols {w+ob-1, w+ob} (pre-summed weights)
+          const int x = p.up2 ? (tc.w0 + ob - 1 + (tap & 1)) : (tc.w0 + p.dx[tap]);
+          const int y = p.up2 ? (tc.h0 + oa - 1 + (tap >> 1)) : (tc.h0 + p.dy[tap]);
+          const CUtensorMap* ma;
+          int cc = c;
+          if (p.per_tap_map) {
+            ma = &maps.a[p.tap_map[tap]];
+          } else if (c < p.C0) {
+            ma = &maps.a[0];
+          } else {
+            ma = &maps.a[1];
+            cc = c - p.C0;
+          }
+          if (CG == 2) {
+            // all bytes of the pair are credited to the LEADER's full barrier
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+            tma_load_5d_2sm(st, ma, fb, cc, x, y, tc.n0, 0);
+            tma_load_5d_2sm(st + Cfg::kABytes, ma, fb, cc, x, y, tc.n0, 1);
+            tma_load_3d_2sm(st + 2 * Cfg::kABytes, &maps.w, fb, kb * kTcBlockK, brow, 0);
+            tma_load_3d_2sm(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, fb, kb * kTcBlockK, brow, 1);
+          } else {
+            mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_5d(st, ma, &full_bar[s], cc, x, y, tc.n0, 0);
+            tma_load_5d(st + Cfg::kABytes, ma, &full_bar[s], cc, x, y, tc.n0, 1);
+            tma_load_3d(st + 2 * Cfg::kABytes, &maps.w, &full_bar[s], kb * kTcBlockK, brow, 0);
+            tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, &full_bar[s], kb * kTcBlockK, brow, 1);
+          }
         }
-        const int brow = phase * p.Cout + nt * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
-        if (CG == 2) {
-          // all bytes of the pair are credited to the LEADER's full barrier
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
-          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
-          tma_load_5d_2sm(st, ma, fb, cc, x, y, n0, 0);
-          tma_load_5d_2sm(st + Cfg::kABytes, ma, fb, cc, x, y, n0, 1);
-          tma_load_3d_2sm(st + 2 * Cfg::kABytes, &maps.w, fb, kb * kTcBlockK, brow, 0);
-          tma_load_3d_2sm(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, fb, kb * kTcBlockK, brow, 1);
-        } else {
-          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_5d(st, ma, &full_bar[s], cc, x, y, n0, 0);
-          tma_load_5d(st + Cfg::kABytes, ma, &full_bar[s], cc, x, y, n0, 1);
-          tma_load_3d(st + 2 * Cfg::kABytes, &maps.w, &full_bar[s], kb * kTcBlockK, brow, 0);
-          tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &maps.w, &full_bar[s], kb * kTcBlockK, brow, 1);
-        }
+        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM * CG, BLOCK_N);
-      int kb = 0;
-      for (int j = 0; j < nchunks; ++j) {
-        const int buf = j % NB;
-        mbar_wait(&acc_empty_bar[buf], ((j / NB) & 1) ^ 1);  // drained NB chunks ago (first use: free)
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
-        const int kb_end = min(nkb, kb + drain);
-        bool first = true;
-        for (; kb < kb_end; ++kb) {
-          const int s = kb % Cfg::kStages;
-          const uint32_t ph = (kb / Cfg::kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+      int it = 0;  // running K-block count (smem ring)
+      int jc = 0;  // running chunk count (TMEM ring)
+      for (long long u = u_begin; u < u_end;) {
+        const int tile = static_cast<int>(u / nkb);
+        const int kb0 = static_cast<int>(u - static_cast<long long>(tile) * nkb);
+        const int kb1 = static_cast<int>(min(static_cast<long long>(nkb), kb0 + (u_end - u)));
+        for (int kb = kb0; kb < kb1; ++jc) {
+          const int buf = jc % NB;
+          mbar_wait(&acc_empty_bar[buf], ((jc / NB) & 1) ^ 1);  // drained NB chunks ago (first use: free)
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint64_t a_hi = umma_smem_desc_sw128(st);
-          const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
-          const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
-          const uint64_t b_lo = umma_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
-          // K advance inside the 128-byte swizzled row: 8 tf32 = 32 bytes = +2 in 16-byte units.
-          // Cross terms first (tiny magnitudes, truncation negligible), dominant hi*hi products last.
+          const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+          const int kb_end = min(kb1, kb + drain);
+          bool first = true;
+          for (; kb < kb_end; ++kb, ++it) {
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+            const uint64_t a_hi = umma_smem_desc_sw128(st);
+            const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
+            const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
+            const uint64_t b_lo = umma_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+            // K advance inside the 128-byte swizzled row: 8 tf32 = 32 bytes = +2 in 16-byte units.
+            // Cross terms first (tiny magnitudes, truncation negligible), dominant hi*hi products last.
 #pragma unroll
-          for (int k = 0; k < kTcBlockK / 8; ++k) {
-            const uint64_t koff = static_cast<uint64_t>(k * 2);
-            if (CG == 2) {
-              umma_tf32_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
-              umma_tf32_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
-              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+            for (int k = 0; k < kTcBlockK / 8; ++k) {
+              const uint64_t koff = static_cast<uint64_t>(k * 2);
+              if (CG == 2) {
+                umma_tf32_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+                umma_tf32_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+                umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+              }
+              first = false;
             }
-            first = false;
-          }
 #pragma unroll
-          for (int k = 0; k < kTcBlockK / 8; ++k) {
-            const uint64_t koff = static_cast<uint64_t>(k * 2);
-            if (CG == 2) umma_tf32_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
-            else umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            for (int k = 0; k < kTcBlockK / 8; ++k) {
+              const uint64_t koff = static_cast<uint64_t>(k * 2);
+              if (CG == 2) umma_tf32_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+              else umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+            if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
-          if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+          // partial sum complete -> drain warps (of both CTAs)
+          if (CG == 2) umma_commit_2sm(&acc_full_bar[buf]); else umma_commit(&acc_full_bar[buf]);
         }
-        // partial sum complete -> drain warps (of both CTAs)
-        if (CG == 2) umma_commit_2sm(&acc_full_bar[buf]); else umma_commit(&acc_full_bar[buf]);
+        u += kb1 - kb0;
       }
     }
+  }
   } else {
-    // ===================== drain + epilogue (8 warps: 4 TMEM lane quarters x 2 column halves) =========
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+    // ===================== drain + epilogue (warps 4..11: 4 TMEM lane quarters x 2 column halves) =========
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which BLOCK_N/2 column range
+    const int half = (warp - 4) >> 2;       // which BLOCK_N/2 column range
     const int col0 = half * CPW;
     const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile box
-    float acc[CPW];
-#pragma unroll
-    for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
+    const int te = threadIdx.x - 128;       // 0..255 among the drain threads
     const uint32_t acc_empty_base =
         (CG == 2) ? mapa_u32(smem_u32(&acc_empty_bar[0]), 0) : smem_u32(&acc_empty_bar[0]);
+    const int osf = p.up2 ? 2 : 1;
+    // stream-K scratch of THIS CTA: [128 rows][BLOCK_N] fp32 + one flag
+    float* my_partial = p.sk_partials + static_cast<long long>(blockIdx.x) * (kTcBlockM * 256);
+    int jc = 0;
 
-    for (int j = 0; j < nchunks; ++j) {
-      const int buf = j % NB;
-      mbar_wait(&acc_full_bar[buf], (j / NB) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + col0;
+    for (long long u = u_begin; u < u_end;) {
+      const int tile = static_cast<int>(u / nkb);
+      const int kb0 = static_cast<int>(u - static_cast<long long>(tile) * nkb);
+      const int kb1 = static_cast<int>(min(static_cast<long long>(nkb), kb0 + (u_end - u)));
+      const int nchunks = (kb1 - kb0 + drain - 1) / drain;
+      float acc[CPW];
 #pragma unroll
-      for (int ch = 0; ch < CPW / 32; ++ch) {
-        float v[32];
-        tmem_ld_32x32(taddr + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(v[i], p.partial_scale, acc[ch * 32 + i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(acc_empty_base + buf * 8);
-        else mbar_arrive(&acc_empty_bar[buf]);
-      }
-    }
+      for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
 
-    // ---- epilogue from registers
-    const int iw = row % p.bw;
-    const int ih = (row / p.bw) % p.bh;
-    const int in = row / (p.bw * p.bh);
-    const int n = n0 + in, h = h0 + ih, w = w0 + iw;
-    const bool valid = n < p.N;
-    const long long pix = (static_cast<long long>(n) * (p.H * osf) + h * osf + oa) * (p.W * osf) + w * osf + ob;
-    float* orow = p.out + pix * p.Cout + nt * BLOCK_N + col0;
+      for (int j = 0; j < nchunks; ++j, ++jc) {
+        const int buf = jc % NB;
+        mbar_wait(&acc_full_bar[buf], (jc / NB) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + col0;
+#pragma unroll
+        for (int ch = 0; ch < CPW / 32; ++ch) {
+          float v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(v[i], p.partial_scale, acc[ch * 32 + i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(acc_empty_base + buf * 8);
+          else mbar_arrive(&acc_empty_bar[buf]);
+        }
+      }
+
+      if (kb0 > 0) {
+        // ---- this group's range started inside the tile: publish the partial sums, the tile's owner finishes it
+        float* prow = my_partial + static_cast<long long>(row) * BLOCK_N + col0;
+#pragma unroll
+        for (int i = 0; i < CPW; i += 4)
+          __stcg(reinterpret_cast<float4*>(prow + i), make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (te == 0) {
+          int* flag = p.sk_flags + blockIdx.x;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+        }
+      } else {
+        if (kb1 < nkb) {
+          // ---- owner of a tile that other groups helped with: add their partial sums (they processed them first)
+          long long covered = static_cast<long long>(tile) * nkb + kb1;
+          const long long tile_end = static_cast<long long>(tile + 1) * nkb;
+          for (int g2 = group + 1; covered < tile_end; ++g2) {
+            const long long g2_end = total_units * (g2 + 1) / ngroups;
+            const int other_cta = g2 * CG + static_cast<int>(cta_rank);
+            if (te == 0) {
+              const int* flag = p.sk_flags + other_cta;
+              int v = 0, spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (++spins > (1 << 28)) { printf("mf: stream-K flag timeout cta=%d waits for %d\n", blockIdx.x, other_cta); __trap(); }
+              } while (v == 0);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float* orow = p.sk_partials + static_cast<long long>(other_cta) * (kTcBlockM * 256) +
+                                static_cast<long long>(row) * BLOCK_N + col0;
+#pragma unroll
+            for (int i = 0; i < CPW; i += 4) {
+              const float4 o = __ldcg(reinterpret_cast<const float4*>(orow + i));
+              acc[i] += o.x; acc[i + 1] += o.y; acc[i + 2] += o.z; acc[i + 3] += o.w;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (te == 0) p.sk_flags[other_cta] = 0;   // re-arm for the next launch (CUDA-graph replay safe)
+            covered = min(tile_end, g2_end);
+          }
+        }
+        // ---- epilogue from registers
+        const TileCoord tc = decode_tile(tile);
+        const int oa = tc.phase >> 1, ob = tc.phase & 1;
+        const int nt = tc.nt;
+        const int iw = row % p.bw;
+        const int ih = (row / p.bw) % p.bh;
+        const int in = row / (p.bw * p.bh);
+        const int n = tc.n0 + in, h = tc.h0 + ih, w = tc.w0 + iw;
+        const bool valid = n < p.N;
+        const long long pix = (static_cast<long long>(n) * (p.H * osf) + h * osf + oa) * (p.W * osf) + w * osf + ob;
+        float* orow = p.out + pix * p.Cout + nt * BLOCK_N + col0;
 
 #pragma unroll
-    for (int ch = 0; ch < CPW / 32; ++ch) {
-      float* v = &acc[ch * 32];
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + col0 + ch * 32);
+        for (int ch = 0; ch < CPW / 32; ++ch) {
+          float* v = &acc[ch * 32];
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + col0 + ch * 32);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float4 b = __ldg(b4 + jj);
-          v[4 * jj + 0] += b.x; v[4 * jj + 1] += b.y; v[4 * jj + 2] += b.z; v[4 * jj + 3] += b.w;
-        }
-      }
-      if (p.stats != nullptr) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float s = 0.f, ss = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float x = v[8 * g + jj];
-            s += x;
-            ss = fmaf(x, x, ss);
+            for (int jj = 0; jj < 8; ++jj) {
+              const float4 b = __ldg(b4 + jj);
+              v[4 * jj + 0] += b.x; v[4 * jj + 1] += b.y; v[4 * jj + 2] += b.z; v[4 * jj + 3] += b.w;
+            }
           }
-          if (!valid) { s = 0.f; ss = 0.f; }
+          if (p.stats != nullptr) {
 #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, off);
-            ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            for (int g = 0; g < 4; ++g) {
+              float s = 0.f, ss = 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float x = v[8 * g + jj];
+                s += x;
+                ss = fmaf(x, x, ss);
+              }
+              if (!valid) { s = 0.f; ss = 0.f; }
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, off);
+                ss += __shfl_xor_sync(0xffffffffu, ss, off);
+              }
+              if (lane == 0) {
+                float* r = red + ((q * (BLOCK_N / 8)) + (col0 + ch * 32) / 8 + g) * 2;
+                r[0] = s;
+                r[1] = ss;
+              }
+            }
           }
-          if (lane == 0) {
-            float* r = red + ((q * (BLOCK_N / 8)) + (col0 + ch * 32) / 8 + g) * 2;
-            r[0] = s;
-            r[1] = ss;
+          if (valid && p.res_kind != 0) {
+            // fused residual add: out = conv + bias + residual(same pixel, same channels)   (attention blocks)
+            const float* rrow = p.res + pix * p.Cout + nt * BLOCK_N + col0 + ch * 32;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              float4 r = *reinterpret_cast<const float4*>(rrow + 4 * jj);
+              if (p.res_kind == 1) {
+                const float4 rl = *reinterpret_cast<const float4*>(rrow + p.res_plane + 4 * jj);
+                r.x += rl.x; r.y += rl.y; r.z += rl.z; r.w += rl.w;
+              }
+              v[4 * jj + 0] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
+            }
+          }
+          if (valid && p.emb != nullptr) {
+            // per-sample channel vector (one-token cross-attention collapses to this, attention_blocks.py:160-195)
+            const float4* e4 = reinterpret_cast<const float4*>(p.emb + static_cast<long long>(n) * p.emb_stride +
+                                                                nt * BLOCK_N + col0 + ch * 32);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float4 e = __ldg(e4 + jj);
+              v[4 * jj + 0] += e.x; v[4 * jj + 1] += e.y; v[4 * jj + 2] += e.z; v[4 * jj + 3] += e.w;
+            }
+          }
+          if (valid) {
+            if (p.out_mode == kOutRaw) {
+              float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj)
+                o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+            } else {
+              float4* o4h = reinterpret_cast<float4*>(orow + ch * 32);
+              float4* o4l = reinterpret_cast<float4*>(orow + p.out_plane + ch * 32);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                float4 hi, lo;
+                tf32_split(v[4 * jj + 0], hi.x, lo.x);
+                tf32_split(v[4 * jj + 1], hi.y, lo.y);
+                tf32_split(v[4 * jj + 2], hi.z, lo.z);
+                tf32_split(v[4 * jj + 3], hi.w, lo.w);
+                o4h[jj] = hi;
+                o4l[jj] = lo;
+              }
+            }
           }
         }
-      }
-      if (valid && p.res_kind != 0) {
-        // fused residual add: out = conv + bias + residual(same pixel, same channels)   (attention / transformer blocks)
-        const float* rrow = p.res + pix * p.Cout + nt * BLOCK_N + col0 + ch * 32;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          float4 r = *reinterpret_cast<const float4*>(rrow + 4 * jj);
-          if (p.res_kind == 1) {
-            const float4 rl = *reinterpret_cast<const float4*>(rrow + p.res_plane + 4 * jj);
-            r.x += rl.x; r.y += rl.y; r.z += rl.z; r.w += rl.w;
-          }
-          v[4 * jj + 0] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
-        }
-      }
-      if (valid && p.emb != nullptr) {
-        // per-sample channel vector (degenerate one-token cross-attention collapses to this, attention_blocks.py:160-195)
-        const float4* e4 = reinterpret_cast<const float4*>(p.emb + static_cast<long long>(n) * p.emb_stride +
-                                                            nt * BLOCK_N + col0 + ch * 32);
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float4 e = __ldg(e4 + jj);
-          v[4 * jj + 0] += e.x; v[4 * jj + 1] += e.y; v[4 * jj + 2] += e.z; v[4 * jj + 3] += e.w;
-        }
-      }
-      if (valid) {
-        if (p.out_mode == kOutRaw) {
-          float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj)
-            o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-        } else {
-          float4* o4h = reinterpret_cast<float4*>(orow + ch * 32);
-          float4* o4l = reinterpret_cast<float4*>(orow + p.out_plane + ch * 32);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            float4 hi, lo;
-            tf32_split(v[4 * jj + 0], hi.x, lo.x);
-            tf32_split(v[4 * jj + 1], hi.y, lo.y);
-            tf32_split(v[4 * jj + 2], hi.z, lo.z);
-            tf32_split(v[4 * jj + 3], hi.w, lo.w);
-            o4h[jj] = hi;
-            o4l[jj] = lo;
-          }
-        }
-      }
-    }
 
-    if (p.stats != nullptr) {
-      // combine the lane quarters (named barrier 1: only the 256 drain/epilogue threads participate)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int te = threadIdx.x - 64;                 // 0..255
-      const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
-      const int wps = 4 / spt;                         // lane quarters per sample
-      constexpr int G8 = BLOCK_N / 8;
-      if (te < G8 * spt) {
-        const int j = te / G8, i = te - j * G8;
-        float s = 0.f, ss = 0.f;
-        for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
-          s += red[(wq * G8 + i) * 2 + 0];
-          ss += red[(wq * G8 + i) * 2 + 1];
-        }
-        const int ns = n0 + (spt > 1 ? j : 0);
-        const int chunk = (p.chunks_per_sample > 1) ? (th * p.tiles_w + tw) : 0;
-        if (ns < p.N) {
-          float* dst = p.stats + ((static_cast<long long>(ns) * p.chunks_per_sample + chunk) * (p.Cout / 8) +
-                                  nt * G8 + i) * 2;
-          dst[0] = s;
-          dst[1] = ss;
+        if (p.stats != nullptr) {
+          // combine the lane quarters (named barrier 1: only the 256 drain/epilogue threads participate)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
+          const int wps = 4 / spt;                         // lane quarters per sample
+          constexpr int G8 = BLOCK_N / 8;
+          if (te < G8 * spt) {
+            const int j = te / G8, i = te - j * G8;
+            float s = 0.f, ss = 0.f;
+            for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
+              s += red[(wq * G8 + i) * 2 + 0];
+              ss += red[(wq * G8 + i) * 2 + 1];
+            }
+            const int ns = tc.n0 + (spt > 1 ? j : 0);
+            const int chunk = (p.chunks_per_sample > 1) ? (tc.th * p.tiles_w + tc.tw) : 0;
+            if (ns < p.N) {
+              float* dst = p.stats + ((static_cast<long long>(ns) * p.chunks_per_sample + chunk) * (p.Cout / 8) +
+                                      nt * G8 + i) * 2;
+              dst[0] = s;
+              dst[1] = ss;
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // red[] is reused by the next tile
         }
       }
+      u += kb1 - kb0;
     }
   }
 
@@ -389,6 +489,29 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return 3;
   }
+  return 0;
+}
+
+// stream-K scratch: one [128][256] fp32 partial tile and one flag per CTA of the persistent grid
+struct StreamKScratch {
+  float* partials = nullptr;
+  int* flags = nullptr;
+  int max_ctas = 0;
+};
+static int get_streamk_scratch(StreamKScratch* out) {
+  static StreamKScratch sc;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (sc.partials == nullptr) {
+    int dev = 0, sms = 0;
+    MF_CUDA_OK(cudaGetDevice(&dev));
+    MF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sc.max_ctas = sms;
+    MF_CUDA_OK(cudaMalloc(&sc.partials, static_cast<size_t>(sms) * kTcBlockM * 256 * sizeof(float)));
+    MF_CUDA_OK(cudaMalloc(&sc.flags, static_cast<size_t>(sms) * sizeof(int)));
+    MF_CUDA_OK(cudaMemset(sc.flags, 0, static_cast<size_t>(sms) * sizeof(int)));
+  }
+  *out = sc;
   return 0;
 }
 
@@ -505,9 +628,27 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   if (bn != 64 && bn != 128 && bn != 256) bn = 256;     // auto: widest tile the channel count allows
   while (d.Cout % bn) bn /= 2;
   plan->block_n = bn;
-  // a CTA pair owns two consecutive M tiles; an odd tile count gets one padding CTA (all loads out of range -> zeros,
+  // a CTA pair owns two consecutive M tiles; an odd tile count gets a padding tile (all loads out of range -> zeros,
   // all stores masked)
-  plan->grid = dim3(cg == 2 ? (m_tiles + 1) / 2 * 2 : m_tiles, d.Cout / plan->block_n, d.up2 ? 4 : 1);
+  p.m_groups = (m_tiles + cg - 1) / cg;
+  p.n_tiles = d.Cout / bn;
+  p.num_tiles = p.m_groups * p.n_tiles * (d.up2 ? 4 : 1);
+  StreamKScratch sc;
+  {
+    int rcs = get_streamk_scratch(&sc);
+    if (rcs) return rcs;
+  }
+  p.sk_partials = sc.partials;
+  p.sk_flags = sc.flags;
+  // persistent grid: one CTA group per SM (pair); stream-K splits the (tile, K block) units evenly over the groups.
+  // With stream-K off every tile gets its own group (classic one-tile-per-CTA launch).
+  int groups = p.num_tiles;
+  if (g_stream_k) groups = std::min(p.num_tiles, sc.max_ctas / cg);
+  MF_REQUIRE(groups * cg <= sc.max_ctas || !g_stream_k, "stream-K grid exceeds the scratch allocation");
+  if (!g_stream_k && groups * cg > sc.max_ctas) {
+    // scratch is indexed by blockIdx.x; without stream-K no partials are ever written, any grid size is fine
+  }
+  plan->grid = dim3(groups * cg, 1, 1);
 
   int rc = 0;
   if (stride == 2) {

@@ -11,7 +11,7 @@
 // [plane][Cout][K] with K = 32-channel-slab major, tap minor.  One CTA computes a 128-pixel x BLOCK_N tile:
 //   warp 0      : TMA producer  (5-D activation boxes with zero-filled halo, 3-D weight boxes)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per K-step: hi*hi, hi*lo, lo*hi)
-//   warps 2..9  : drain (tcgen05.ld of each finished TMEM partial sum -> round-to-nearest fp32 register
+//   warps 4..11 : drain (tcgen05.ld of each finished TMEM partial sum -> round-to-nearest fp32 register
 //                 accumulation) and epilogue (+bias -> GroupNorm partial sums -> global store)
 #pragma once
 
@@ -22,7 +22,7 @@ namespace mf {
 constexpr int kTcBlockM = 128;  // output pixels per tile (UMMA M)
 constexpr int kTcBlockK = 32;   // fp32 elements per K block = 128 B = one swizzle row
 constexpr int kTcDrainWarps = 8;
-constexpr int kTcThreads = 64 + 32 * kTcDrainWarps;  // TMA warp + MMA warp + drain/epilogue warps
+constexpr int kTcThreads = 128 + 32 * kTcDrainWarps;  // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1-2: drain
 constexpr int kTcMaxTaps = 9;
 
 enum ConvOutMode : int {
@@ -34,6 +34,9 @@ struct ConvTcParams {
   int N, H, W;                   // OUTPUT geometry
   int bw, bh, bn;                // pixel box of one tile, bw*bh*bn == 128
   int tiles_w, tiles_h, tiles_n;
+  int m_groups, n_tiles, num_tiles;  // CTA-group tiles along M, tiles along N, total (x4 phases with up2)
+  float* sk_partials;            // stream-K scratch [grid CTAs][128][256] fp32
+  int* sk_flags;                 // stream-K flags   [grid CTAs]
   int C0, C1;                    // channels of source 0 / 1 (C1 == 0: single source)
   int Cout;
   int ntaps;
@@ -93,6 +96,7 @@ struct ConvTcDesc {
 extern int g_default_drain_interval;
 extern int g_default_cta_group;
 extern int g_default_block_n;
+extern int g_stream_k;
 extern float g_debias_eps_per_kblock;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);

@@ -20,6 +20,16 @@ import torch.nn as nn
 from ..._engine import require_cuda
 
 
+class _EMAWeights(nn.Module):
+    """Holder with the reference's attribute name (`EMAModel.averaged_model`, utils/train_utils.py:33)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.averaged_model = model
+        for p in self.averaged_model.parameters():
+            p.requires_grad = False
+
+
 class DiffusionPipeline(nn.Module):
     def __init__(
         self,
@@ -51,8 +61,6 @@ class DiffusionPipeline(nn.Module):
             raise NotImplementedError("estimate_variance=True (learned variance) is not implemented")
         if use_self_conditioning:
             raise NotImplementedError("use_self_conditioning=True is not implemented")
-        if use_ema:
-            raise NotImplementedError("use_ema=True: load the EMA weights into noise_estimator instead")
         if estimator_objective not in ("x_T", "x_0"):
             raise ValueError("Unknown Objective")
         est_kwargs = dict(noise_estimator_kwargs or {})
@@ -74,6 +82,10 @@ class DiffusionPipeline(nn.Module):
         self.estimate_variance = estimate_variance
         self.clip_x0 = clip_x0
         self.use_ema = use_ema
+        if use_ema:
+            # weight selection only (diffusion_pipeline.py:234-237): a second estimator holding the averaged weights under
+            # the reference's key prefix `ema_model.averaged_model.*`; the EMA *update* is training-side (train_utils.py).
+            self.ema_model = _EMAWeights(noise_estimator(**est_kwargs))
 
     @property
     def device(self):
@@ -87,14 +99,15 @@ class DiffusionPipeline(nn.Module):
         accepted = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
         model = cls(**{k: v for k, v in hp.items() if k in accepted})
         sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
-        sd = {k: v for k, v in sd.items() if not k.startswith(("ema_model.", "loss_fct."))}
+        drop = ("loss_fct.",) if model.use_ema else ("ema_model.", "loss_fct.")
+        sd = {k: v for k, v in sd.items() if not k.startswith(drop)}
         model.load_state_dict(sd)
         return model
 
     # ---------------------------------------------------------------------------------------------
     def _predict(self, x_t, t, condition, guidance_scale, un_cond):
         """Estimator pass(es); returns (pred, pred_uncond|None). CFG combine happens in the step kernel."""
-        est = self.noise_estimator
+        est = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
         if (condition is not None) and (guidance_scale != 1.0):
             pred_uncond, _ = est(x_t, t, condition=un_cond, self_cond=None)
             pred_cond, _ = est(x_t, t, condition=condition, self_cond=None)

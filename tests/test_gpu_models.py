@@ -143,3 +143,23 @@ def test_pipeline_forward_contract():
     assert len(out) == 4 and all(o.shape == x.shape for o in out)
     with pytest.raises(TypeError):
         pipe.denoise(x, steps=2, eta=0.0)  # the reference cannot take eta either
+
+
+def test_use_ema_selects_the_averaged_weights():
+    """diffusion_pipeline.py:234-237: with use_ema the estimator is ema_model.averaged_model."""
+    from medfusion_b200.models import (DiffusionPipeline, GaussianNoiseScheduler, LabelEmbedder, TimeEmbbeding, UNet)
+    from medfusion_b200.synthetic import fill_
+    g = load_golden("sample_small.pt")
+    ucfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in g["unet_cfg"].items()}
+    pipe = DiffusionPipeline(noise_scheduler=GaussianNoiseScheduler, noise_estimator=UNet,
+                             noise_scheduler_kwargs=dict(g["sched"]),
+                             noise_estimator_kwargs=dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder, **ucfg),
+                             clip_x0=False, use_ema=True)
+    assert any(k.startswith("ema_model.averaged_model.in_conv") for k in pipe.state_dict())
+    fill_(pipe.noise_estimator, seed=1)
+    fill_(pipe.ema_model.averaged_model, seed=0)      # the fixture's weights live in the EMA copy only
+    pipe = pipe.to(DEV)
+    gs = load_golden("unet_small.pt")
+    x, t, c = gs["x"].to(DEV), gs["t"].to(DEV), gs["cond"].to(DEV)
+    pred, _ = pipe._predict(x, t, c, 1.0, None)
+    assert_close(pred.cpu(), gs["y_cond"], what="EMA estimator output")
