@@ -228,11 +228,13 @@ def test_layernorm_and_geglu_match_oracle():
     out = torch.empty_like(xs)
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.mf_op_layernorm(xs.data_ptr(), xs[0].numel(), gamma.to(DEV).data_ptr(), beta.to(DEV).data_ptr(),
+    dg, db = gamma.to(DEV), beta.to(DEV)   # keep the device copies alive across the asynchronous launch
+    _lib.check(lib.mf_op_layernorm(xs.data_ptr(), xs[0].numel(), dg.data_ptr(), db.data_ptr(),
                                    out.data_ptr(), out[0].numel(), T, C, 1e-5, st), "layernorm")
     assert_close((out[0] + out[1]).reshape(T, C).cpu(), ref, what="layernorm")
     z = _rnd(g, T, 2 * C)
     refg = z[:, :C] * F.gelu(z[:, C:])
     zo = torch.empty((2, T, C), device=DEV)
-    _lib.check(lib.mf_op_geglu(z.to(DEV).data_ptr(), zo.data_ptr(), zo[0].numel(), T, C, st), "geglu")
+    dz = z.to(DEV)
+    _lib.check(lib.mf_op_geglu(dz.data_ptr(), zo.data_ptr(), zo[0].numel(), T, C, st), "geglu")
     assert_close((zo[0] + zo[1]).cpu(), refg, what="geglu")

@@ -112,11 +112,13 @@ def run_case(name):
             r32 = F.conv2d(x, w, b, padding=c["k"] // 2)
             res["torch_fp32_vs_fp64"] = float((r32.double() - ref).abs().max())
         from medfusion_b200 import _lib
-        combos = ([(1, 256, d) for d in (1, 2, 4, 8, 1000)] + [(2, 256, 1), (2, 128, 1)] if c["kind"] == "tc_sweep"
-                  else [(1, 256, 1), (2, 256, 1), (2, 128, 1), (2, 128, 1000), (2, 256, 2), (2, 256, 1000), (1, 128, 1)])
-        for cg, bn, di in combos:
+        combos = ([(1, 256, d, 1) for d in (1, 2, 4)] + [(2, 256, 1, 1), (2, 256, 2, 1), (2, 256, 2, 0)]
+                  if c["kind"] == "tc_sweep" else
+                  [(2, 256, 2, 0), (2, 256, 2, 1), (2, 256, 1, 1), (2, 256, 1000, 1), (1, 256, 2, 1), (2, 128, 2, 1)])
+        for cg, bn, di, sk in combos:
             _lib.load().mf_set_cta_group(cg)
             _lib.load().mf_set_block_n(bn)
+            _lib.load().mf_set_stream_k(sk)
             out, _ = ops.conv_tc(s0, wp, b, c["k"], src1=s1, drain_interval=di)
             torch.cuda.synchronize()
             ent = {}
@@ -139,7 +141,7 @@ def run_case(name):
                 ms = st.elapsed_time(en) / iters
                 ent["ms"] = round(ms, 4)
                 ent["tflops_alg"] = round(flops / ms / 1e9, 1)
-            res["sweep"][f"cg{cg}_n{bn}_drain{di}"] = ent
+            res["sweep"][f"cg{cg}_n{bn}_drain{di}_sk{sk}"] = ent
         res["viol"] = 0
     elif c["kind"] == "norm":
         N, Cc, H, W, G = 2, 64, 16, 16, 8
