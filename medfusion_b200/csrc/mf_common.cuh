@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,18 +40,39 @@ const char* get_error();
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// TF32 hi/lo split.  hi = x rounded to TF32 (low 13 mantissa bits zero), lo = x - hi (exact in
-// fp32).  The tensor core only looks at the top 19 bits of each operand, so x*y is recovered as
-// hi*hi' + hi*lo' + lo*hi' with fp32 accumulation (error ~2^-22 relative per product).
+// fp16 hi/lo split ("fp16x3").  hi = fp16(x) (11 significant bits, the same as TF32), lo = fp16(x - hi).
+// x*y is recovered as lo*hi' + hi*lo' + hi*hi' with fp32 accumulation: |x - hi - lo| <= 2^-22 |x| (or 3e-8 absolute
+// once lo is subnormal), the fp16 x fp16 products are exact in fp32.  Compared with the TF32 split the operands are
+// half as wide and kind::f16 MMAs cover K = 16 per instruction instead of 8: twice the math per tensor-core cycle and
+// per shared-memory byte, at identical accuracy.  Range: |x| <= 65504 (larger values saturate); weights are
+// pre-scaled by a power of two so that their lo parts stay in fp16's normal range.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+typedef __half sp_t;  // element type of the split (hi / lo) planes
+__device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+  lo = __float2half_rn(x - __half2float(hi));
 }
-__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
-  hi = tf32_hi(x);
-  lo = x - hi;
+__device__ __forceinline__ float join16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+// four consecutive channels: 8-byte vector accesses on both planes
+__device__ __forceinline__ float4 ld_join4(const __half* hi, const __half* lo) {
+  const uint2 uh = *reinterpret_cast<const uint2*>(hi);
+  const uint2 ul = *reinterpret_cast<const uint2*>(lo);
+  const __half2 h0 = *reinterpret_cast<const __half2*>(&uh.x), h1 = *reinterpret_cast<const __half2*>(&uh.y);
+  const __half2 l0 = *reinterpret_cast<const __half2*>(&ul.x), l1 = *reinterpret_cast<const __half2*>(&ul.y);
+  const float2 a = __half22float2(h0), b = __half22float2(h1), c = __half22float2(l0), d = __half22float2(l1);
+  return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
+}
+__device__ __forceinline__ void st_split4(__half* hi, __half* lo, float4 v) {
+  __half h[4], l[4];
+  split16(v.x, h[0], l[0]);
+  split16(v.y, h[1], l[1]);
+  split16(v.z, h[2], l[2]);
+  split16(v.w, h[3], l[3]);
+  uint2 uh, ul;
+  uh.x = *reinterpret_cast<uint32_t*>(&h[0]); uh.y = *reinterpret_cast<uint32_t*>(&h[2]);
+  ul.x = *reinterpret_cast<uint32_t*>(&l[0]); ul.y = *reinterpret_cast<uint32_t*>(&l[2]);
+  *reinterpret_cast<uint2*>(hi) = uh;
+  *reinterpret_cast<uint2*>(lo) = ul;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -138,13 +160,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, TF32 inputs, FP32 accumulate, single-CTA group.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 inputs (K = 16 per instruction), FP32 accumulate, single-CTA group.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -227,12 +249,12 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // 256-row MMA across the CTA pair (issued by the leader CTA only)
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -260,11 +282,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // layout type: SWIZZLE_128B
   return d;
 }
-// kind::tf32, A/B K-major, FP32 accumulator, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+// kind::f16 with fp16 operands, A/B K-major, FP32 accumulator, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4)                              // c_format = F32
-         | (2u << 7)                            // a_format = TF32
-         | (2u << 10)                           // b_format = TF32
+         | (0u << 7)                            // a_format = F16
+         | (0u << 10)                           // b_format = F16
          | (static_cast<uint32_t>(N >> 3) << 17)  // n_dim
          | (static_cast<uint32_t>(M >> 4) << 24); // m_dim
 }

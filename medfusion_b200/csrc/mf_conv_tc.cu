@@ -185,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kTcBlockM * CG, BLOCK_N);
+      constexpr uint32_t idesc = umma_idesc_f16(kTcBlockM * CG, BLOCK_N);
       int it = 0;  // running K-block count (smem ring)
       int jc = 0;  // running chunk count (TMEM ring)
       for (long long u = u_begin; u < u_end;) {
@@ -209,25 +209,25 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
             const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
             const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
             const uint64_t b_lo = umma_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
-            // K advance inside the 128-byte swizzled row: 8 tf32 = 32 bytes = +2 in 16-byte units.
+            // K advance inside the 128-byte swizzled row: 16 fp16 = 32 bytes = +2 in 16-byte units.
             // Cross terms first (tiny magnitudes, truncation negligible), dominant hi*hi products last.
 #pragma unroll
-            for (int k = 0; k < kTcBlockK / 8; ++k) {
+            for (int k = 0; k < kTcBlockK / 16; ++k) {
               const uint64_t koff = static_cast<uint64_t>(k * 2);
               if (CG == 2) {
-                umma_tf32_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
-                umma_tf32_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                umma_f16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+                umma_f16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
               } else {
-                umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
-                umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+                umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
               }
               first = false;
             }
 #pragma unroll
-            for (int k = 0; k < kTcBlockK / 8; ++k) {
+            for (int k = 0; k < kTcBlockK / 16; ++k) {
               const uint64_t koff = static_cast<uint64_t>(k * 2);
-              if (CG == 2) umma_tf32_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
-              else umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+              if (CG == 2) umma_f16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+              else umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
             }
             // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
             if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
@@ -251,6 +251,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
         (CG == 2) ? mapa_u32(smem_u32(&acc_empty_bar[0]), 0) : smem_u32(&acc_empty_bar[0]);
     const int osf = p.up2 ? 2 : 1;
     // stream-K scratch of THIS CTA: [128 rows][BLOCK_N] fp32 + one flag
+    // drained partials are de-biased and un-scaled (weights were pre-scaled by a power of two) in one FMA
+    const float pscale = p.partial_scale * __ldg(p.w_inv_scale);
     float* my_partial = p.sk_partials + static_cast<long long>(blockIdx.x) * (kTcBlockM * 256);
     int jc = 0;
 
@@ -273,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           float v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(v[i], p.partial_scale, acc[ch * 32 + i]);
+          for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(v[i], pscale, acc[ch * 32 + i]);
         }
         tc_fence_before();
         __syncwarp();
@@ -334,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
         const int n = tc.n0 + in, h = tc.h0 + ih, w = tc.w0 + iw;
         const bool valid = n < p.N;
         const long long pix = (static_cast<long long>(n) * (p.H * osf) + h * osf + oa) * (p.W * osf) + w * osf + ob;
-        float* orow = p.out + pix * p.Cout + nt * BLOCK_N + col0;
+        const long long ooff = pix * p.Cout + nt * BLOCK_N + col0;
 
 #pragma unroll
         for (int ch = 0; ch < CPW / 32; ++ch) {
@@ -372,13 +374,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           }
           if (valid && p.res_kind != 0) {
             // fused residual add: out = conv + bias + residual(same pixel, same channels)   (attention blocks)
-            const float* rrow = p.res + pix * p.Cout + nt * BLOCK_N + col0 + ch * 32;
+            const long long roff = ooff + ch * 32;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              float4 r = *reinterpret_cast<const float4*>(rrow + 4 * jj);
+              float4 r;
               if (p.res_kind == 1) {
-                const float4 rl = *reinterpret_cast<const float4*>(rrow + p.res_plane + 4 * jj);
-                r.x += rl.x; r.y += rl.y; r.z += rl.z; r.w += rl.w;
+                const __half* rh = reinterpret_cast<const __half*>(p.res) + roff + 4 * jj;
+                r = ld_join4(rh, rh + p.res_plane);
+              } else {
+                r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + roff + 4 * jj);
               }
               v[4 * jj + 0] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
             }
@@ -395,23 +399,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           }
           if (valid) {
             if (p.out_mode == kOutRaw) {
-              float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff + ch * 32);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj)
                 o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
             } else {
-              float4* o4h = reinterpret_cast<float4*>(orow + ch * 32);
-              float4* o4l = reinterpret_cast<float4*>(orow + p.out_plane + ch * 32);
+              __half* oh = reinterpret_cast<__half*>(p.out) + ooff + ch * 32;
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                float4 hi, lo;
-                tf32_split(v[4 * jj + 0], hi.x, lo.x);
-                tf32_split(v[4 * jj + 1], hi.y, lo.y);
-                tf32_split(v[4 * jj + 2], hi.z, lo.z);
-                tf32_split(v[4 * jj + 3], hi.w, lo.w);
-                o4h[jj] = hi;
-                o4l[jj] = lo;
-              }
+              for (int jj = 0; jj < 8; ++jj)
+                st_split4(oh + 4 * jj, oh + p.out_plane + 4 * jj,
+                          make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]));
             }
           }
         }
@@ -482,7 +479,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return 3;
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -555,12 +552,12 @@ int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, 
 
 // View of an NHWC split tensor sub-sampled by `sub` in H and W starting at (ph, pw): sub = 1 is the tensor itself,
 // sub = 2 selects one of the four input-parity grids a stride-2 convolution reads.
-static int encode_act_map(CUtensorMap* m, const float* base, long long plane, int N, int H, int W, int C, int bw,
+static int encode_act_map(CUtensorMap* m, const __half* base, long long plane, int N, int H, int W, int C, int bw,
                           int bh, int bn, int sub = 1, int ph = 0, int pw = 0) {
   base += (static_cast<long long>(ph) * W + pw) * C;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(W / sub), (cuuint64_t)(H / sub), (cuuint64_t)N, 2};
-  cuuint64_t strides[4] = {(cuuint64_t)sub * C * 4, (cuuint64_t)sub * W * C * 4, (cuuint64_t)H * W * C * 4,
-                           (cuuint64_t)plane * 4};
+  cuuint64_t strides[4] = {(cuuint64_t)sub * C * 2, (cuuint64_t)sub * W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)plane * 2};
   cuuint32_t box[5] = {(cuuint32_t)kTcBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return encode_map(m, base, 5, dims, strides, box, estr);
@@ -615,6 +612,8 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
   p.stats = d.stats;
   p.res = d.res; p.res_plane = d.res_plane; p.res_kind = d.res ? d.res_kind : 0;
+  MF_REQUIRE(d.w_inv_scale != nullptr, "conv_tc needs the weight scale produced by prep_weight_tc");
+  p.w_inv_scale = d.w_inv_scale;
   p.emb = d.emb; p.emb_stride = d.emb_stride;
   MF_REQUIRE(!(d.up2 && (d.res || d.emb)), "folded upsample conv has no fused residual");
   p.chunks_per_sample = conv_tc_stats_chunks(Ho, Wo);
@@ -673,7 +672,7 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
   const long long wrows = static_cast<long long>(d.Cout) * (d.up2 ? 4 : 1);  // up2: four phase matrices stacked
   cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)wrows, 2};
-  cuuint64_t ws[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * wrows * 4};
+  cuuint64_t ws[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * wrows * 2};
   cuuint32_t wb[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(plan->block_n / plan->cta_group), 1};
   cuuint32_t we[3] = {1, 1, 1};
   return encode_map(&plan->maps.w, d.w_planes, 3, wd, ws, wb, we);

@@ -1,4 +1,4 @@
-// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), error-compensated 3xTF32.
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), error-compensated fp16x3 (fp32-accurate).
 //
 // Replaces the reference's nn.Conv2d call sites on the hot path
 //   /root/reference/medical_diffusion/models/utils/conv_blocks.py:185   (BasicBlock.conv, 3x3 s1 p1)
@@ -7,8 +7,8 @@
 // and the torch.cat of unet2.py:259 (two-source K loop instead of a materialised concat).
 //
 // GEMM view:  D[M = N*H*W output pixels][Cout] = sum_{tap, c} A[pixel shifted by tap][c] * Wt[Cout][tap*Cin + c]
-// Activations live in HBM as NHWC fp32 in two planes (TF32 hi, fp32 residual lo); weights as
-// [plane][Cout][K] with K = 32-channel-slab major, tap minor.  One CTA computes a 128-pixel x BLOCK_N tile:
+// Activations live in HBM as NHWC fp16 in two planes (hi = fp16(x), lo = fp16(x - hi)); weights as
+// [plane][Cout][K] fp16 (pre-scaled by a power of two) with K = 64-channel-slab major, tap minor.  One CTA computes a 128-pixel x BLOCK_N tile:
 //   warp 0      : TMA producer  (5-D activation boxes with zero-filled halo, 3-D weight boxes)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per K-step: hi*hi, hi*lo, lo*hi)
 //   warps 4..11 : drain (tcgen05.ld of each finished TMEM partial sum -> round-to-nearest fp32 register
@@ -20,14 +20,14 @@
 namespace mf {
 
 constexpr int kTcBlockM = 128;  // output pixels per tile (UMMA M)
-constexpr int kTcBlockK = 32;   // fp32 elements per K block = 128 B = one swizzle row
+constexpr int kTcBlockK = 64;   // fp16 elements per K block = 128 B = one swizzle row
 constexpr int kTcDrainWarps = 8;
 constexpr int kTcThreads = 128 + 32 * kTcDrainWarps;  // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1-2: drain
 constexpr int kTcMaxTaps = 9;
 
 enum ConvOutMode : int {
   kOutRaw = 0,    // single fp32 plane (input of GroupNorm)
-  kOutSplit = 1,  // TF32 hi/lo planes (direct input of the next conv)
+  kOutSplit = 1,  // fp16 hi/lo planes (direct input of the next conv)
 };
 
 struct ConvTcParams {
@@ -47,11 +47,12 @@ struct ConvTcParams {
   int drain_interval;            // K blocks accumulated inside TMEM before the fp32 register add (1 = most exact)
   float partial_scale;           // (1 + eps): de-biases the truncating TMEM accumulation when a partial is drained
   const float* bias;             // [Cout] or nullptr
-  float* out;                    // NHWC [N,H,W,Cout]; split mode: hi plane
+  void* out;                     // NHWC [N,H,W,Cout]: float (raw mode) or __half hi plane (split mode)
   long long out_plane;           // elements between hi and lo plane (split mode)
+  const float* w_inv_scale;      // device scalar 2^-S undoing the power-of-two weight pre-scale
   int out_mode;
   float* stats;                  // [N][chunks][Cout/8][2] partial (sum, sumsq) or nullptr
-  const float* res;              // optional residual with the output's geometry; res_kind 1: split planes, 2: raw
+  const void* res;               // optional residual with the output's geometry; res_kind 1: split (__half) planes, 2: raw float
   long long res_plane;
   int res_kind;
   const float* emb;              // optional per-sample channel vector emb[n*emb_stride + c]
@@ -75,17 +76,18 @@ struct ConvTcPlan {
 
 // Host API -------------------------------------------------------------------------------------
 struct ConvTcDesc {
-  // sources: NHWC split tensors (hi plane pointer, lo = hi + plane elements)
-  const float* src0; long long src0_plane; int C0;
-  const float* src1; long long src1_plane; int C1;  // C1 == 0 -> none
+  // sources: NHWC split tensors (fp16 hi plane pointer, lo = hi + plane elements)
+  const __half* src0; long long src0_plane; int C0;
+  const __half* src1; long long src1_plane; int C1;  // C1 == 0 -> none
   int N, H, W;              // INPUT spatial size; output is H/stride x W/stride
   int stride;               // 1 (default when 0) or 2 (3x3, single source, even H and W)
-  const float* w_planes;    // [2][Cout][K] prepared by prep_weight_tc
+  const __half* w_planes;   // [2][Cout][K] fp16 prepared by prep_weight_tc (pre-scaled by 2^S)
+  const float* w_inv_scale; // device scalar 2^-S written by prep_weight_tc
   int Cout, ksize;          // ksize 1 or 3 (pad = ksize/2, stride 1)
   const float* bias;
-  float* out; long long out_plane; int out_mode;
+  void* out; long long out_plane; int out_mode;   // float* (raw) or __half* (split)
   float* stats;             // optional
-  const float* res; long long res_plane; int res_kind;  // optional fused residual add (1 split, 2 raw)
+  const void* res; long long res_plane; int res_kind;   // optional fused residual add (1 split fp16, 2 raw fp32)
   const float* emb; int emb_stride;                     // optional fused per-sample channel add
   int drain_interval;       // 0 -> default (1)
   int cta_group;            // 0 -> default (auto), 1 or 2
