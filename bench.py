@@ -307,7 +307,7 @@ def main():
         out = {
             "metric": "images/sec (256x256, 1000 DDPM steps)", "value": value, "unit": "images/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed_s / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 parity)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16x3 split, fp32 accumulate (fp32 parity)",
             "data": "synthetic",
             "config": {
                 "workload": (f"batch={B}/GPU 256x256, 8x32x32 latent, {args.timesteps} ancestral DDPM steps, "
@@ -315,7 +315,7 @@ def main():
                                 else "unconditional (BASELINE.json configs[1])")),
                 "global_batch": Bg, "parallelism": f"batch-shard x{n_gpus}, one all-gather of images",
                 "step": "one full sample(): x_T -> timesteps x (UNet + scheduler) -> VAE.decode",
-                "l2": "working set per timestep (2.3 GB split weights + ~2.9 GB activations) exceeds the 126 MB L2",
+                "l2": "working set per timestep (0.8 GB fp16 hi/lo weights + ~2 GB activations) exceeds the 126 MB L2",
                 "algorithmic_tflop_per_step": alg_flops_per_step / 1e12,
                 "job_algorithmic_tflops": alg_flops_per_step * n_gpus * args.steps / elapsed_s / 1e12,
             },
@@ -324,12 +324,12 @@ def main():
             "gpu_launches": launches_per_sample * args.steps,
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": "mf::conv_tc_kernel (tcgen05 kind::tf32, 3xTF32 split, 47 of 51 UNet convs)",
+                "kernel": "mf::conv_tc_kernel (tcgen05 kind::f16, fp16x3 split, 49 of 51 UNet convs)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); TF32 runs at 1/2 and the "
-                               "3-term split issues 3 MMAs per product, so frac <= 1/6 by construction",
-                "issued_tf32_tflops": 3.0 * achieved_tf,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); the fp32-accurate 3-term "
+                               "split issues 3 fp16 MMAs per product, so frac <= 1/3 by construction",
+                "issued_f16_tflops": 3.0 * achieved_tf,
                 "kernel_share_of_unet_step": tc_ms / step_ms if step_ms else None,
                 "avg_launch_ms": tc_ms / max(1, len(tc)), "launches_per_unet_step": len(tc),
             },

@@ -150,45 +150,53 @@ int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float
                   float* d_x_T, float* d_x_next, int B, int chw, mf_stream_t stream);
 
 /* -------------------------------------------------------------------------------------------------
- * Kernel-level ops (test / profiling surface; layouts: 0 = NCHW fp32, 1 = NHWC fp32, 2 = NHWC TF32 hi/lo planes)
+ * Kernel-level ops (test / profiling surface).  Layouts: 0 = NCHW fp32, 1 = NHWC fp32 ("raw"), 2 = NHWC "split":
+ * two fp16 planes [2][N,H,W,C], hi = fp16(x), lo = fp16(x - hi), `plane` = elements between the planes.  Split
+ * tensors are passed as void*.
  * ---------------------------------------------------------------------------------------------- */
-int mf_op_pack_split(const float* d_x_nchw, float* d_out, int64_t plane, int N, int C, int H, int W, mf_stream_t s);
-int mf_op_unpack_nchw(const float* d_in, int64_t plane, int layout, float* d_out_nchw, int N, int C, int H, int W,
+int mf_op_pack_split(const float* d_x_nchw, void* d_out, int64_t plane, int N, int C, int H, int W, mf_stream_t s);
+int mf_op_unpack_nchw(const void* d_in, int64_t plane, int layout, float* d_out_nchw, int N, int C, int H, int W,
                       mf_stream_t s);
-int mf_op_prep_weight_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
+/* OIHW fp32 -> fp16 [2][Cout][K] (K = 64-channel-slab major, tap minor), pre-scaled by 2^S; d_scales: device float[4]
+ * receiving {2^S, 2^-S, scratch}.  Cin % 64 == 0. */
+int mf_op_prep_weight_tc(const float* d_w_oihw, void* d_out, float* d_scales, int Cout, int Cin, int kh, int kw,
+                         mf_stream_t s);
 int mf_op_prep_weight_simt(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s);
 int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 /* 'same'-padded conv on the tcgen05 path (N,H,W = input size); stride 1 (1x1 / 3x3, optional second source
- * src1 concatenated along channels) or stride 2 (3x3, single source, even H/W).  src1 may be NULL (C1 = 0).  d_stats: [N][chunks][Cout/8][2] or NULL.
- * drain_interval: K blocks (of 32 channels) summed inside TMEM before the round-to-nearest fp32 register
+ * src1 concatenated along channels) or stride 2 (3x3, single source, even H/W).  src1 may be NULL (C1 = 0).
+ * d_out: float NHWC (out_layout 1) or fp16 split planes (out_layout 2).  d_stats: [N][chunks][Cout/8][2] or NULL.
+ * drain_interval: K blocks (of 64 channels) summed inside TMEM before the round-to-nearest fp32 register
  * accumulation; 0 = library default (2; 1 is the most exact, larger is faster). */
-int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
-                  int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
-                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, int stride, mf_stream_t s);
+int mf_op_conv_tc(const void* d_src0, int64_t src0_plane, int C0, const void* d_src1, int64_t src1_plane, int C1,
+                  int N, int H, int W, const void* d_w_planes, const float* d_scales, int Cout, int ksize,
+                  const float* d_bias, void* d_out, int64_t out_plane, int out_layout, float* d_stats,
+                  int drain_interval, int stride, mf_stream_t s);
 int mf_op_conv_tc_stats_chunks(int H, int W);
-/* conv3x3(nearest_x2(src)) + bias -> split [N,2H,2W,Cout]; weights from mf_op_prep_weight_up_tc ([2][4*Cout][4*C]) */
-int mf_op_prep_weight_up_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, mf_stream_t s);
-int mf_op_upconv_tc(const float* d_src, int64_t src_plane, int C, int N, int H, int W, const float* d_w_up_planes,
-                    int Cout, const float* d_bias, float* d_out, int64_t out_plane, mf_stream_t s);
-int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
-                    const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,
+/* conv3x3(nearest_x2(src)) + bias -> split [N,2H,2W,Cout]; weights from mf_op_prep_weight_up_tc (fp16 [2][4*Cout][4*C]) */
+int mf_op_prep_weight_up_tc(const float* d_w_oihw, void* d_out, float* d_scales, int Cout, int Cin, mf_stream_t s);
+int mf_op_upconv_tc(const void* d_src, int64_t src_plane, int C, int N, int H, int W, const void* d_w_up_planes,
+                    const float* d_scales, int Cout, const float* d_bias, void* d_out, int64_t out_plane,
+                    mf_stream_t s);
+int mf_op_conv_simt(const void* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
+                    const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, void* d_out,
                     int64_t out_plane, int out_layout, mf_stream_t s);
 int mf_op_gn_partial(const float* d_raw, float* d_partial, int N, int HW, int C, mf_stream_t s);
 int mf_op_gn_finalize(const float* d_partial, float* d_mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
                       mf_stream_t s);
 int mf_op_gn_apply(const float* d_raw, const float* d_mean_rstd, const float* d_gamma, const float* d_beta,
-                   const float* d_res, int64_t res_plane, int res_kind /* 0 none, 1 split, 2 raw */,
-                   const float* d_emb, int emb_stride, float* d_out, int64_t out_plane, int N, int HW, int C, int G,
+                   const void* d_res, int64_t res_plane, int res_kind /* 0 none, 1 split, 2 raw */,
+                   const float* d_emb, int emb_stride, void* d_out, int64_t out_plane, int N, int HW, int C, int G,
                    mf_stream_t s);
 /* attention-block kernels (attention_blocks.py): softmax((q s)^T (k s)) v per head with s = d^-0.25, q/k/v raw rows of
  * row_stride floats per token, out split [B*N][heads*d]; LayerNorm over channels (split -> split); GEGLU gate
  * (raw [tokens][2*Ch] -> split [tokens][Ch]) */
-int mf_op_attention(const float* d_q, const float* d_k, const float* d_v, int row_stride, float* d_out, int64_t out_plane,
+int mf_op_attention(const float* d_q, const float* d_k, const float* d_v, int row_stride, void* d_out, int64_t out_plane,
                     int B, int N, int heads, int d, mf_stream_t s);
-int mf_op_layernorm(const float* d_in, int64_t in_plane, const float* d_gamma, const float* d_beta, float* d_out,
+int mf_op_layernorm(const void* d_in, int64_t in_plane, const float* d_gamma, const float* d_beta, void* d_out,
                     int64_t out_plane, int64_t tokens, int C, float eps, mf_stream_t s);
-int mf_op_geglu(const float* d_in, float* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s);
-int mf_op_upsample2x(const float* d_in, int64_t in_plane, float* d_out, int64_t out_plane, int N, int H, int W, int C,
+int mf_op_geglu(const float* d_in, void* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s);
+int mf_op_upsample2x(const void* d_in, int64_t in_plane, void* d_out, int64_t out_plane, int N, int H, int W, int C,
                      mf_stream_t s);
 
 #ifdef __cplusplus

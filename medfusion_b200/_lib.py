@@ -79,14 +79,14 @@ SIGNATURES = {
                               _P, _P, _P, _P, c_int, c_int, _P]),
     "mf_op_pack_split": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "mf_op_unpack_nchw": (c_int, [_P, c_int64, c_int, _P, c_int, c_int, c_int, c_int, _P]),
-    "mf_op_prep_weight_tc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_prep_weight_tc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mf_op_prep_weight_simt": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "mf_op_conv_tc_supported": (c_int, [c_int] * 8),
     "mf_op_conv_tc_stats_chunks": (c_int, [c_int, c_int]),
-    "mf_op_conv_tc": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P,
+    "mf_op_conv_tc": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P,
                               _P, c_int64, c_int, _P, c_int, c_int, _P]),
-    "mf_op_prep_weight_up_tc": (c_int, [_P, _P, c_int, c_int, _P]),
-    "mf_op_upconv_tc": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int64, _P]),
+    "mf_op_prep_weight_up_tc": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "mf_op_upconv_tc": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int64, _P]),
     "mf_op_conv_simt": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P,
                                 c_int64, c_int, _P]),
     "mf_op_gn_partial": (c_int, [_P, _P, c_int, c_int, c_int, _P]),

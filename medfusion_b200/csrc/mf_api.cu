@@ -583,16 +583,19 @@ int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float
   return sched_step(d, static_cast<cudaStream_t>(stream));
 }
 
-// ---- kernel-level ops ---------------------------------------------------------------------------
-int mf_op_pack_split(const float* d_x_nchw, float* d_out, int64_t plane, int N, int C, int H, int W, mf_stream_t s) {
-  return pack_nchw_to_split(d_x_nchw, d_out, plane, N, C, H, W, static_cast<cudaStream_t>(s));
+// ---- kernel-level ops (split tensors are fp16 hi/lo planes, passed as void*) ---------------------------------------
+#define MF_H(p) reinterpret_cast<__half*>(p)
+#define MF_CH(p) reinterpret_cast<const __half*>(p)
+int mf_op_pack_split(const float* d_x_nchw, void* d_out, int64_t plane, int N, int C, int H, int W, mf_stream_t s) {
+  return pack_nchw_to_split(d_x_nchw, MF_H(d_out), plane, N, C, H, W, static_cast<cudaStream_t>(s));
 }
-int mf_op_unpack_nchw(const float* d_in, int64_t plane, int layout, float* d_out_nchw, int N, int C, int H, int W,
+int mf_op_unpack_nchw(const void* d_in, int64_t plane, int layout, float* d_out_nchw, int N, int C, int H, int W,
                       mf_stream_t s) {
   return unpack_to_nchw(d_in, plane, layout, d_out_nchw, N, C, H, W, static_cast<cudaStream_t>(s));
 }
-int mf_op_prep_weight_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s) {
-  return prep_weight_tc(d_w_oihw, d_out, Cout, Cin, kh, kw, static_cast<cudaStream_t>(s));
+int mf_op_prep_weight_tc(const float* d_w_oihw, void* d_out, float* d_scales, int Cout, int Cin, int kh, int kw,
+                         mf_stream_t s) {
+  return prep_weight_tc(d_w_oihw, MF_H(d_out), d_scales, Cout, Cin, kh, kw, static_cast<cudaStream_t>(s));
 }
 int mf_op_prep_weight_simt(const float* d_w_oihw, float* d_out, int Cout, int Cin, int kh, int kw, mf_stream_t s) {
   return prep_weight_simt(d_w_oihw, d_out, Cout, Cin, kh, kw, static_cast<cudaStream_t>(s));
@@ -601,15 +604,16 @@ int mf_op_conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int k
   return conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride);
 }
 int mf_op_conv_tc_stats_chunks(int H, int W) { return conv_tc_stats_chunks(H, W); }
-int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* d_src1, int64_t src1_plane, int C1,
-                  int N, int H, int W, const float* d_w_planes, int Cout, int ksize, const float* d_bias, float* d_out,
-                  int64_t out_plane, int out_layout, float* d_stats, int drain_interval, int stride, mf_stream_t s) {
+int mf_op_conv_tc(const void* d_src0, int64_t src0_plane, int C0, const void* d_src1, int64_t src1_plane, int C1,
+                  int N, int H, int W, const void* d_w_planes, const float* d_scales, int Cout, int ksize,
+                  const float* d_bias, void* d_out, int64_t out_plane, int out_layout, float* d_stats,
+                  int drain_interval, int stride, mf_stream_t s) {
   MF_REQUIRE(out_layout == kNHWCRaw || out_layout == kNHWCSplit, "conv_tc writes NHWC");
   ConvTcDesc d{};
-  d.src0 = d_src0; d.src0_plane = src0_plane; d.C0 = C0;
-  d.src1 = d_src1; d.src1_plane = src1_plane; d.C1 = C1;
+  d.src0 = MF_CH(d_src0); d.src0_plane = src0_plane; d.C0 = C0;
+  d.src1 = MF_CH(d_src1); d.src1_plane = src1_plane; d.C1 = C1;
   d.N = N; d.H = H; d.W = W; d.stride = stride;
-  d.w_planes = d_w_planes; d.Cout = Cout; d.ksize = ksize; d.bias = d_bias;
+  d.w_planes = MF_CH(d_w_planes); d.w_inv_scale = d_scales + 1; d.Cout = Cout; d.ksize = ksize; d.bias = d_bias;
   d.out = d_out; d.out_plane = out_plane; d.out_mode = out_layout == kNHWCSplit ? kOutSplit : kOutRaw;
   d.stats = d_stats;
   d.drain_interval = drain_interval;
@@ -618,23 +622,24 @@ int mf_op_conv_tc(const float* d_src0, int64_t src0_plane, int C0, const float* 
   if (rc) return rc;
   return conv_tc_launch(plan, static_cast<cudaStream_t>(s));
 }
-int mf_op_prep_weight_up_tc(const float* d_w_oihw, float* d_out, int Cout, int Cin, mf_stream_t s) {
-  return prep_weight_up_tc(d_w_oihw, d_out, Cout, Cin, static_cast<cudaStream_t>(s));
+int mf_op_prep_weight_up_tc(const float* d_w_oihw, void* d_out, float* d_scales, int Cout, int Cin, mf_stream_t s) {
+  return prep_weight_up_tc(d_w_oihw, MF_H(d_out), d_scales, Cout, Cin, static_cast<cudaStream_t>(s));
 }
-int mf_op_upconv_tc(const float* d_src, int64_t src_plane, int C, int N, int H, int W, const float* d_w_up_planes,
-                    int Cout, const float* d_bias, float* d_out, int64_t out_plane, mf_stream_t s) {
+int mf_op_upconv_tc(const void* d_src, int64_t src_plane, int C, int N, int H, int W, const void* d_w_up_planes,
+                    const float* d_scales, int Cout, const float* d_bias, void* d_out, int64_t out_plane,
+                    mf_stream_t s) {
   ConvTcDesc d{};
-  d.src0 = d_src; d.src0_plane = src_plane; d.C0 = C;
+  d.src0 = MF_CH(d_src); d.src0_plane = src_plane; d.C0 = C;
   d.N = N; d.H = H; d.W = W; d.stride = 1; d.up2 = 1;
-  d.w_planes = d_w_up_planes; d.Cout = Cout; d.ksize = 3; d.bias = d_bias;
+  d.w_planes = MF_CH(d_w_up_planes); d.w_inv_scale = d_scales + 1; d.Cout = Cout; d.ksize = 3; d.bias = d_bias;
   d.out = d_out; d.out_plane = out_plane; d.out_mode = kOutSplit;
   ConvTcPlan plan;
   int rc = conv_tc_build(d, &plan);
   if (rc) return rc;
   return conv_tc_launch(plan, static_cast<cudaStream_t>(s));
 }
-int mf_op_conv_simt(const float* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
-                    const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, float* d_out,
+int mf_op_conv_simt(const void* d_in, int64_t in_plane, int in_layout, int N, int Cin, int Hin, int Win,
+                    const float* d_w_kc, const float* d_bias, int Cout, int ksize, int stride, void* d_out,
                     int64_t out_plane, int out_layout, mf_stream_t s) {
   ConvSimtDesc d{};
   d.in = d_in; d.in_plane = in_plane; d.in_layout = in_layout;
@@ -651,30 +656,31 @@ int mf_op_gn_finalize(const float* d_partial, float* d_mean_rstd, int N, int chu
   return gn_finalize(d_partial, d_mean_rstd, N, chunks, C, G, HW, eps, static_cast<cudaStream_t>(s));
 }
 int mf_op_gn_apply(const float* d_raw, const float* d_mean_rstd, const float* d_gamma, const float* d_beta,
-                   const float* d_res, int64_t res_plane, int res_kind, const float* d_emb, int emb_stride,
-                   float* d_out, int64_t out_plane, int N, int HW, int C, int G, mf_stream_t s) {
+                   const void* d_res, int64_t res_plane, int res_kind, const float* d_emb, int emb_stride,
+                   void* d_out, int64_t out_plane, int N, int HW, int C, int G, mf_stream_t s) {
   GnApplyDesc d{};
   d.raw = d_raw; d.mean_rstd = d_mean_rstd; d.gamma = d_gamma; d.beta = d_beta;
   d.res = d_res; d.res_plane = res_plane; d.res_kind = res_kind;
   d.emb = d_emb; d.emb_stride = emb_stride;
-  d.out = d_out; d.out_plane = out_plane; d.N = N; d.HW = HW; d.C = C; d.G = G;
+  d.out = MF_H(d_out); d.out_plane = out_plane; d.N = N; d.HW = HW; d.C = C; d.G = G;
   d.raw_plane = 0; d.act = 1;
   return gn_apply(d, static_cast<cudaStream_t>(s));
 }
-int mf_op_attention(const float* d_q, const float* d_k, const float* d_v, int row_stride, float* d_out, int64_t out_plane,
+int mf_op_attention(const float* d_q, const float* d_k, const float* d_v, int row_stride, void* d_out, int64_t out_plane,
                     int B, int N, int heads, int d, mf_stream_t s) {
-  return attention_core(d_q, d_k, d_v, row_stride, d_out, out_plane, B, N, heads, d, static_cast<cudaStream_t>(s));
+  return attention_core(d_q, d_k, d_v, row_stride, MF_H(d_out), out_plane, B, N, heads, d, static_cast<cudaStream_t>(s));
 }
-int mf_op_layernorm(const float* d_in, int64_t in_plane, const float* d_gamma, const float* d_beta, float* d_out,
+int mf_op_layernorm(const void* d_in, int64_t in_plane, const float* d_gamma, const float* d_beta, void* d_out,
                     int64_t out_plane, int64_t tokens, int C, float eps, mf_stream_t s) {
-  return layernorm_split(d_in, in_plane, d_gamma, d_beta, d_out, out_plane, tokens, C, eps, static_cast<cudaStream_t>(s));
+  return layernorm_split(MF_CH(d_in), in_plane, d_gamma, d_beta, MF_H(d_out), out_plane, tokens, C, eps,
+                         static_cast<cudaStream_t>(s));
 }
-int mf_op_geglu(const float* d_in, float* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s) {
-  return geglu_split(d_in, d_out, out_plane, tokens, Ch, static_cast<cudaStream_t>(s));
+int mf_op_geglu(const float* d_in, void* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s) {
+  return geglu_split(d_in, MF_H(d_out), out_plane, tokens, Ch, static_cast<cudaStream_t>(s));
 }
-int mf_op_upsample2x(const float* d_in, int64_t in_plane, float* d_out, int64_t out_plane, int N, int H, int W, int C,
+int mf_op_upsample2x(const void* d_in, int64_t in_plane, void* d_out, int64_t out_plane, int N, int H, int W, int C,
                      mf_stream_t s) {
-  return upsample2x_split(d_in, in_plane, d_out, out_plane, N, H, W, C, static_cast<cudaStream_t>(s));
+  return upsample2x_split(MF_CH(d_in), in_plane, MF_H(d_out), out_plane, N, H, W, C, static_cast<cudaStream_t>(s));
 }
 
 }  // extern "C"

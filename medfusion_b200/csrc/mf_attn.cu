@@ -7,37 +7,34 @@ namespace mf {
 // =================================================================================================
 // LayerNorm: one warp per token, three passes over an L1-resident row (mean, centred variance, write)
 // =================================================================================================
-__global__ void layernorm_split_kernel(const float* __restrict__ in, long long in_plane, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float* __restrict__ out, long long out_plane,
+__global__ void layernorm_split_kernel(const __half* __restrict__ in, long long in_plane, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, __half* __restrict__ out, long long out_plane,
                                        long long tokens, int C, float eps) {
   const long long tok = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= tokens) return;
-  const float* hi = in + tok * C;
-  const float* lo = hi + in_plane;
+  const __half* hi = in + tok * C;
+  const __half* lo = hi + in_plane;
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += hi[c] + lo[c];
+  for (int c = lane; c < C; c += 32) s += join16(hi[c], lo[c]);
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   const float mean = s / static_cast<float>(C);
   float ss = 0.f;
   for (int c = lane; c < C; c += 32) {
-    const float d = (hi[c] + lo[c]) - mean;
+    const float d = join16(hi[c], lo[c]) - mean;
     ss = fmaf(d, d, ss);
   }
   for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
   const float rstd = rsqrtf(ss / static_cast<float>(C) + eps);
-  float* oh = out + tok * C;
-  float* ol = oh + out_plane;
+  __half* oh = out + tok * C;
+  __half* ol = oh + out_plane;
   for (int c = lane; c < C; c += 32) {
-    const float y = ((hi[c] + lo[c]) - mean) * rstd * gamma[c] + beta[c];
-    float h, l;
-    tf32_split(y, h, l);
-    oh[c] = h;
-    ol[c] = l;
+    const float y = (join16(hi[c], lo[c]) - mean) * rstd * gamma[c] + beta[c];
+    split16(y, oh[c], ol[c]);
   }
 }
 
-int layernorm_split(const float* in, long long in_plane, const float* gamma, const float* beta, float* out,
+int layernorm_split(const __half* in, long long in_plane, const float* gamma, const float* beta, __half* out,
                     long long out_plane, long long tokens, int C, float eps, cudaStream_t s) {
   if (tokens == 0) return 0;
   const long long threads = tokens * 32;
@@ -50,7 +47,7 @@ int layernorm_split(const float* in, long long in_plane, const float* gamma, con
 // =================================================================================================
 // GEGLU gate: x * gelu(gate), exact (erf) GELU like F.gelu's default
 // =================================================================================================
-__global__ void geglu_split_kernel(const float* __restrict__ in, float* __restrict__ out, long long out_plane,
+__global__ void geglu_split_kernel(const float* __restrict__ in, __half* __restrict__ out, long long out_plane,
                                    long long tokens, int Ch) {
   const int c4n = Ch / 4;
   const long long total = tokens * c4n;
@@ -61,18 +58,14 @@ __global__ void geglu_split_kernel(const float* __restrict__ in, float* __restri
     const float4 a = *reinterpret_cast<const float4*>(in + tok * 2 * Ch + c);
     const float4 g = *reinterpret_cast<const float4*>(in + tok * 2 * Ch + Ch + c);
     const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
-    float h[4], l[4];
+    float y[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float ge = 0.5f * gv[j] * (1.0f + erff(gv[j] * 0.70710678118654752440f));
-      tf32_split(av[j] * ge, h[j], l[j]);
-    }
-    *reinterpret_cast<float4*>(out + tok * Ch + c) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(out + out_plane + tok * Ch + c) = make_float4(l[0], l[1], l[2], l[3]);
+    for (int j = 0; j < 4; ++j) y[j] = av[j] * (0.5f * gv[j] * (1.0f + erff(gv[j] * 0.70710678118654752440f)));
+    st_split4(out + tok * Ch + c, out + out_plane + tok * Ch + c, make_float4(y[0], y[1], y[2], y[3]));
   }
 }
 
-int geglu_split(const float* in, float* out, long long out_plane, long long tokens, int Ch, cudaStream_t s) {
+int geglu_split(const float* in, __half* out, long long out_plane, long long tokens, int Ch, cudaStream_t s) {
   MF_REQUIRE(Ch % 4 == 0, "geglu: channel count must be a multiple of 4");
   const long long total = tokens * (Ch / 4);
   if (total == 0) return 0;
@@ -89,7 +82,7 @@ int geglu_split(const float* in, float* out, long long out_plane, long long toke
 template <int D>
 __global__ void __launch_bounds__(256) attention_core_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                               const float* __restrict__ v, int row_stride,
-                                                              float* __restrict__ out, long long out_plane, int N,
+                                                              __half* __restrict__ out, long long out_plane, int N,
                                                               int heads, float scale2) {
   constexpr int KT = 32;        // keys per tile
   constexpr int DP = D + 1;     // padded row: lane j walks row j without bank conflicts
@@ -152,18 +145,13 @@ __global__ void __launch_bounds__(256) attention_core_kernel(const float* __rest
   }
   if (qvalid) {
     const float inv = 1.0f / l;
-    float* oh = out + (tok0 + qi) * (static_cast<long long>(heads) * D) + h * D;
+    __half* oh = out + (tok0 + qi) * (static_cast<long long>(heads) * D) + h * D;
 #pragma unroll
-    for (int i = 0; i < DL; ++i) {
-      float hi, lo;
-      tf32_split(acc[i] * inv, hi, lo);
-      oh[lane + 32 * i] = hi;
-      oh[out_plane + lane + 32 * i] = lo;
-    }
+    for (int i = 0; i < DL; ++i) split16(acc[i] * inv, oh[lane + 32 * i], oh[out_plane + lane + 32 * i]);
   }
 }
 
-int attention_core(const float* q, const float* k, const float* v, int row_stride, float* out, long long out_plane,
+int attention_core(const float* q, const float* k, const float* v, int row_stride, __half* out, long long out_plane,
                    int B, int N, int heads, int d, cudaStream_t s) {
   if (B == 0 || N == 0) return 0;
   const float scale2 = 1.0f / sqrtf(static_cast<float>(d));  // (d^-0.25)^2
@@ -183,22 +171,19 @@ int attention_core(const float* q, const float* k, const float* v, int row_strid
 // =================================================================================================
 // out = in + bias[n][c]
 // =================================================================================================
-__global__ void add_channel_bias_split_kernel(const float* __restrict__ in, long long in_plane,
-                                              const float* __restrict__ bias, int bias_stride, float* __restrict__ out,
+__global__ void add_channel_bias_split_kernel(const __half* __restrict__ in, long long in_plane,
+                                              const float* __restrict__ bias, int bias_stride, __half* __restrict__ out,
                                               long long out_plane, int HW, int C, long long total) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
     const int n = static_cast<int>(i / (static_cast<long long>(HW) * C));
-    const float y = (in[i] + in[in_plane + i]) + bias[static_cast<long long>(n) * bias_stride + c];
-    float h, l;
-    tf32_split(y, h, l);
-    out[i] = h;
-    out[out_plane + i] = l;
+    const float y = join16(in[i], in[in_plane + i]) + bias[static_cast<long long>(n) * bias_stride + c];
+    split16(y, out[i], out[out_plane + i]);
   }
 }
 
-int add_channel_bias_split(const float* in, long long in_plane, const float* bias, int bias_stride, float* out,
+int add_channel_bias_split(const __half* in, long long in_plane, const float* bias, int bias_stride, __half* out,
                            long long out_plane, int N, int HW, int C, cudaStream_t s) {
   const long long total = static_cast<long long>(N) * HW * C;
   if (total == 0) return 0;

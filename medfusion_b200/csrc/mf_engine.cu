@@ -162,8 +162,9 @@ void init_resblock(EngineBase& e, ResBlockLayer& rb, const std::string& prefix, 
 Tens EngineBase::new_tensor(int N, int H, int W, int C, int layout) {
   Tens t;
   t.N = N; t.H = H; t.W = W; t.C = C; t.layout = layout;
-  const size_t plane_bytes = align_up(static_cast<size_t>(t.elems()) * 4, 1024);
-  t.plane = static_cast<long long>(plane_bytes / 4);
+  const size_t esize = layout == kNHWCSplit ? 2 : 4;  // split tensors are two fp16 planes
+  const size_t plane_bytes = align_up(static_cast<size_t>(t.elems()) * esize, 1024);
+  t.plane = static_cast<long long>(plane_bytes / esize);
   t.bytes = layout == kNHWCSplit ? 2 * plane_bytes : plane_bytes;
   t.off = arena.alloc(t.bytes);
   t.ptr = dry ? nullptr : reinterpret_cast<float*>(base + t.off);
@@ -182,8 +183,9 @@ void EngineBase::free_tensor(const Tens& t) { arena.release(t.off, t.bytes); }
 // ---- derived weight layouts ----------------------------------------------------------------------
 int EngineBase::ensure_w_tc(ConvLayer& L) {
   if (L.tc_version == version) return 0;
-  if (L.w_tc.alloc(2 * L.w->numel())) return 1;
-  int rc = prep_weight_tc(L.w->data.p, L.w_tc.p, L.Cout, L.Cin, L.k, L.k, prep_stream);
+  if (L.w_tc.alloc(L.w->numel()) || L.tc_scales.alloc(4)) return 1;  // 2 fp16 planes == numel floats
+  int rc = prep_weight_tc(L.w->data.p, reinterpret_cast<__half*>(L.w_tc.p), L.tc_scales.p, L.Cout, L.Cin, L.k, L.k,
+                          prep_stream);
   if (rc) return rc;
   L.tc_version = version;
   return 0;
@@ -213,10 +215,11 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
     int rc = ensure_w_tc(L);
     if (rc) return rc;
     ConvTcDesc d{};
-    d.src0 = in0.ptr; d.src0_plane = in0.plane; d.C0 = in0.C;
-    d.src1 = in1 ? in1->ptr : nullptr; d.src1_plane = in1 ? in1->plane : 0; d.C1 = C1;
+    d.src0 = in0.hptr(); d.src0_plane = in0.plane; d.C0 = in0.C;
+    d.src1 = in1 ? in1->hptr() : nullptr; d.src1_plane = in1 ? in1->plane : 0; d.C1 = C1;
     d.N = in0.N; d.H = in0.H; d.W = in0.W; d.stride = L.stride;
-    d.w_planes = L.w_tc.p; d.Cout = L.Cout; d.ksize = L.k;
+    d.w_planes = reinterpret_cast<const __half*>(L.w_tc.p); d.w_inv_scale = L.tc_scales.p + 1;
+    d.Cout = L.Cout; d.ksize = L.k;
     d.bias = L.b->data.p;
     d.out = out.ptr; d.out_plane = out.plane; d.out_mode = out.layout == kNHWCSplit ? kOutSplit : kOutRaw;
     d.stats = stats ? stats->ptr : nullptr;
@@ -269,15 +272,17 @@ int EngineBase::add_upconv2x(ConvLayer& L, const Tens& in, Tens* out) {
     ++n_tc;
     if (dry) return 0;
     if (L.up_version != version) {
-      if (L.w_up.alloc(2 * 16 * static_cast<size_t>(L.Cout) * L.Cin)) return 1;
-      int rc = prep_weight_up_tc(L.w->data.p, L.w_up.p, L.Cout, L.Cin, prep_stream);
+      if (L.w_up.alloc(16 * static_cast<size_t>(L.Cout) * L.Cin) || L.up_scales.alloc(4)) return 1;
+      int rc = prep_weight_up_tc(L.w->data.p, reinterpret_cast<__half*>(L.w_up.p), L.up_scales.p, L.Cout, L.Cin,
+                                 prep_stream);
       if (rc) return rc;
       L.up_version = version;
     }
     ConvTcDesc d{};
-    d.src0 = in.ptr; d.src0_plane = in.plane; d.C0 = in.C;
+    d.src0 = in.hptr(); d.src0_plane = in.plane; d.C0 = in.C;
     d.N = in.N; d.H = in.H; d.W = in.W; d.stride = 1; d.up2 = 1;
-    d.w_planes = L.w_up.p; d.Cout = L.Cout; d.ksize = 3;
+    d.w_planes = reinterpret_cast<const __half*>(L.w_up.p); d.w_inv_scale = L.up_scales.p + 1;
+    d.Cout = L.Cout; d.ksize = 3;
     d.bias = L.b->data.p;
     d.out = o.ptr; d.out_plane = o.plane; d.out_mode = kOutSplit;
     tc_plans.emplace_back(new ConvTcPlan());
@@ -292,7 +297,7 @@ int EngineBase::add_upconv2x(ConvLayer& L, const Tens& in, Tens* out) {
   Tens up = new_tensor(in.N, in.H * 2, in.W * 2, in.C, in.layout);
   if (!dry) {
     MF_REQUIRE(in.layout == kNHWCSplit, "explicit upsample expects a split tensor");
-    const float* ip = in.ptr; float* op = up.ptr;
+    const __half* ip = in.hptr(); __half* op = up.hptr();
     const long long ipl = in.plane, opl = up.plane;
     const int N = in.N, H = in.H, W = in.W, C = in.C;
     push_op([ip, ipl, op, opl, N, H, W, C](cudaStream_t st) { return upsample2x_split(ip, ipl, op, opl, N, H, W, C, st); },
@@ -372,7 +377,7 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
       d.res = nullptr; d.res_kind = kResNone;
     }
     d.emb = emb; d.emb_stride = emb_stride;
-    d.out = out.ptr; d.out_plane = out.plane;
+    d.out = out.hptr(); d.out_plane = out.plane;
     d.N = raw.N; d.HW = raw.H * raw.W; d.C = raw.C; d.G = groups;
     push_op([d](cudaStream_t s) { return gn_apply(d, s); }, kOpNorm);
   }
@@ -444,8 +449,8 @@ int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, co
     MF_REQUIRE(have_cb, "'linear' attention without an embedding (self-attention form) is not implemented");
     Tens o = new_tensor(B, H, W, C, kNHWCSplit);
     if (!dry) {
-      const float* ip = x.ptr; const long long ipl = x.plane; const float* bp = cb.ptr;
-      float* op = o.ptr; const long long opl = o.plane;
+      const __half* ip = x.hptr(); const long long ipl = x.plane; const float* bp = cb.ptr;
+      __half* op = o.hptr(); const long long opl = o.plane;
       push_op([ip, ipl, bp, C, op, opl, B, HW](cudaStream_t s) {
         return add_channel_bias_split(ip, ipl, bp, C, op, opl, B, HW, C, s);
       }, kOpOther);
@@ -477,7 +482,7 @@ int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, co
   free_tensor(xn);
   Tens ao = new_tensor(B, H, W, C, kNHWCSplit);
   if (!dry) {
-    const float* qp = qkv.ptr; float* op = ao.ptr; const long long opl = ao.plane;
+    const float* qp = qkv.ptr; __half* op = ao.hptr(); const long long opl = ao.plane;
     const int heads = A.heads, d = A.d;
     push_op([qp, C, op, opl, B, HW, heads, d](cudaStream_t s) {
       return attention_core(qp, qp + C, qp + 2 * C, 3 * C, op, opl, B, HW, heads, d, s);
@@ -494,7 +499,7 @@ int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, co
   // feed-forward: LayerNorm -> Linear C->8C -> x*gelu(gate) -> conv1x1 4C->C, + residual (attention_blocks.py:17-25,214-231)
   Tens ln = new_tensor(B, H, W, C, kNHWCSplit);
   if (!dry) {
-    const float* ip = h2.ptr; const long long ipl = h2.plane; float* op = ln.ptr; const long long opl = ln.plane;
+    const __half* ip = h2.hptr(); const long long ipl = h2.plane; __half* op = ln.hptr(); const long long opl = ln.plane;
     const float* g = A.ln.g->data.p; const float* bt = A.ln.b->data.p;
     const long long tokens = static_cast<long long>(B) * HW;
     push_op([ip, ipl, g, bt, op, opl, tokens, C](cudaStream_t s) {
@@ -507,7 +512,7 @@ int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, co
   free_tensor(ln);
   Tens ge = new_tensor(B, H, W, 4 * C, kNHWCSplit);
   if (!dry) {
-    const float* ip = gg.ptr; float* op = ge.ptr; const long long opl = ge.plane;
+    const float* ip = gg.ptr; __half* op = ge.hptr(); const long long opl = ge.plane;
     const long long tokens = static_cast<long long>(B) * HW;
     const int Ch = 4 * C;
     push_op([ip, op, opl, tokens, Ch](cudaStream_t s) { return geglu_split(ip, op, opl, tokens, Ch, s); }, kOpOther);

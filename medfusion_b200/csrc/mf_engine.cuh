@@ -54,7 +54,8 @@ struct ConvLayer {
   Param* w = nullptr;
   Param* b = nullptr;
   int Cout = 0, Cin = 0, k = 1, stride = 1;
-  DevBuf w_tc, w_simt, w_up;  // derived layouts, built lazily by the plan builder
+  DevBuf w_tc, w_simt, w_up;  // derived layouts, built lazily by the plan builder (w_tc / w_up hold fp16 planes)
+  DevBuf tc_scales, up_scales;  // device float[4] each: {2^S, 2^-S, scratch} of the power-of-two weight pre-scale
   int tc_version = -1, simt_version = -1, up_version = -1;
 };
 struct NormLayer {
@@ -107,7 +108,8 @@ struct Tens {
   int N = 0, H = 0, W = 0, C = 0;
   int layout = kNHWCSplit;
   long long plane = 0;  // elements between hi and lo plane
-  float* ptr = nullptr;
+  float* ptr = nullptr; // raw tensors: float data; split tensors: fp16 planes (use hptr())
+  __half* hptr() const { return reinterpret_cast<__half*>(ptr); }
   long long elems() const { return static_cast<long long>(N) * H * W * C; }
 };
 

@@ -9,7 +9,7 @@ __device__ __forceinline__ float swish(float x) { return x / (1.0f + expf(-x)); 
 // =================================================================================================
 // Layout packing
 // =================================================================================================
-__global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, float* __restrict__ out, long long plane, int N,
+__global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, __half* __restrict__ out, long long plane, int N,
                                           int C, int H, int W) {
   const long long total = static_cast<long long>(N) * H * W * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -20,14 +20,11 @@ __global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, float* __
     const int h = static_cast<int>((pix / W) % H);
     const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
     const float v = x[((static_cast<long long>(n) * C + c) * H + h) * W + w];
-    float hi, lo;
-    tf32_split(v, hi, lo);
-    out[i] = hi;
-    out[plane + i] = lo;
+    split16(v, out[i], out[plane + i]);
   }
 }
 
-int pack_nchw_to_split(const float* x, float* out, long long plane, int N, int C, int H, int W, cudaStream_t s) {
+int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s) {
   const long long total = static_cast<long long>(N) * H * W * C;
   if (total == 0) return 0;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
@@ -36,8 +33,10 @@ int pack_nchw_to_split(const float* x, float* out, long long plane, int N, int C
   return 0;
 }
 
-__global__ void unpack_to_nchw_kernel(const float* __restrict__ in, long long plane, int layout, float* __restrict__ out,
+__global__ void unpack_to_nchw_kernel(const void* __restrict__ in_v, long long plane, int layout, float* __restrict__ out,
                                       int N, int C, int H, int W) {
+  const float* in = reinterpret_cast<const float*>(in_v);
+  const __half* inh = reinterpret_cast<const __half*>(in_v);
   const long long total = static_cast<long long>(N) * H * W * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -46,13 +45,12 @@ __global__ void unpack_to_nchw_kernel(const float* __restrict__ in, long long pl
     const int w = static_cast<int>(pix % W);
     const int h = static_cast<int>((pix / W) % H);
     const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    float v = in[i];
-    if (layout == kNHWCSplit) v += in[plane + i];
+    const float v = (layout == kNHWCSplit) ? join16(inh[i], inh[plane + i]) : in[i];
     out[((static_cast<long long>(n) * C + c) * H + h) * W + w] = v;
   }
 }
 
-int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
+int unpack_to_nchw(const void* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
                    cudaStream_t s) {
   MF_REQUIRE(in_layout == kNHWCRaw || in_layout == kNHWCSplit, "unpack_to_nchw expects an NHWC source");
   const long long total = static_cast<long long>(N) * H * W * C;
@@ -66,32 +64,66 @@ int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, 
 // =================================================================================================
 // Weight re-layout (once, at load time)
 // =================================================================================================
-__global__ void prep_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
-                                      int kw) {
+// max |w| of a tensor -> *out (device float), used to choose the power-of-two weight pre-scale
+__global__ void absmax_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0: int order == float order
+}
+// scale = 2^S with max|w| * 2^S in [2^12, 2^13): the lo parts (~2^-11 of the hi parts) stay in fp16's normal range and
+// the largest scaled weight is far below 65504.  scales[0] = 2^S, scales[1] = 2^-S (read by conv_tc's drain FMA).
+__global__ void weight_scale_kernel(const float* __restrict__ absmax, float* __restrict__ scales) {
+  const float m = *absmax;
+  int e = 0;
+  if (m > 0.f && isfinite(m)) {
+    frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+    e = 13 - e;
+  }
+  e = max(-24, min(24, e));
+  scales[0] = ldexpf(1.0f, e);
+  scales[1] = ldexpf(1.0f, -e);
+}
+
+__global__ void prep_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ out,
+                                      const float* __restrict__ scales, int Cout, int Cin, int kh, int kw) {
   const long long K = static_cast<long long>(kh) * kw * Cin;
   const long long total = K * Cout;
+  const float sc = scales[0];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long k = i % K;
     const int o = static_cast<int>(i / K);
-    // K = ((c / 32) * taps + tap) * 32 + c % 32 : channel-block major, tap minor (matches conv_tc's K loop)
+    // K = ((c / 64) * taps + tap) * 64 + c % 64 : 64-channel slab major, tap minor (matches conv_tc's K loop)
     const int taps = kh * kw;
-    const int cb = static_cast<int>(k / (taps * 32));
-    const int rem = static_cast<int>(k % (taps * 32));
-    const int tap = rem / 32;
-    const int c = cb * 32 + rem % 32;
-    const float v = w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap];
-    float hi, lo;
-    tf32_split(v, hi, lo);
-    out[i] = hi;
-    out[total + i] = lo;
+    const int cb = static_cast<int>(k / (taps * 64));
+    const int rem = static_cast<int>(k % (taps * 64));
+    const int tap = rem / 64;
+    const int c = cb * 64 + rem % 64;
+    const float v = w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap] * sc;
+    split16(v, out[i], out[total + i]);
   }
 }
 
-int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
+static int weight_scales(const float* w, long long n, float* scales, cudaStream_t s) {
+  // scales: device float[4]: [0] = 2^S, [1] = 2^-S, [2] = scratch for the max
+  MF_CUDA_OK(cudaMemsetAsync(scales + 2, 0, sizeof(float), s));
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8));
+  absmax_kernel<<<blocks, 256, 0, s>>>(w, n, scales + 2);
+  weight_scale_kernel<<<1, 1, 0, s>>>(scales + 2, scales);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int prep_weight_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
+  MF_REQUIRE(Cin % 64 == 0, "prep_weight_tc needs Cin % 64 == 0");
   const long long total = static_cast<long long>(Cout) * Cin * kh * kw;
+  int rc = weight_scales(w_oihw, total, scales, s);
+  if (rc) return rc;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  prep_weight_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, Cout, Cin, kh, kw);
+  prep_weight_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, scales, Cout, Cin, kh, kw);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -99,9 +131,11 @@ int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, i
 // BasicUp fold: conv3x3(nearest_x2(x)) == four 2x2 convolutions on x, one per output parity (a, b):
 //   rows: a=0 -> {h-1: w[r=0], h: w[1]+w[2]}   a=1 -> {h: w[0]+w[1], h+1: w[2]}   (same for columns)
 // out[2][4*Cout][4*Cin] in conv_tc's K order (32-channel slab major, tap (u,v) minor).
-__global__ void prep_weight_up_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
+__global__ void prep_weight_up_tc_kernel(const float* __restrict__ w, __half* __restrict__ out,
+                                         const float* __restrict__ scales, int Cout, int Cin) {
   const long long K = 4LL * Cin;
   const long long total = K * Cout * 4;
+  const float sc = scales[0];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long k = i % K;
@@ -109,9 +143,9 @@ __global__ void prep_weight_up_tc_kernel(const float* __restrict__ w, float* __r
     const int o = static_cast<int>(row % Cout);
     const int phase = static_cast<int>(row / Cout);
     const int a = phase >> 1, b = phase & 1;
-    const int cb = static_cast<int>(k / 128);
-    const int rem = static_cast<int>(k % 128);
-    const int tap = rem / 32, c = cb * 32 + rem % 32;
+    const int cb = static_cast<int>(k / 256);
+    const int rem = static_cast<int>(k % 256);
+    const int tap = rem / 64, c = cb * 64 + rem % 64;
     const int u = tap >> 1, v = tap & 1;
     const float* wk = w + (static_cast<long long>(o) * Cin + c) * 9;
     // rows/cols of the 3x3 kernel that land on low-res offset u (resp. v) for output parity a (resp. b)
@@ -122,18 +156,18 @@ __global__ void prep_weight_up_tc_kernel(const float* __restrict__ w, float* __r
     float acc = 0.f;
     for (int r = r_lo; r <= r_hi; ++r)
       for (int sx = s_lo; sx <= s_hi; ++sx) acc += wk[r * 3 + sx];
-    float hi, lo;
-    tf32_split(acc, hi, lo);
-    out[i] = hi;
-    out[total + i] = lo;
+    split16(acc * sc, out[i], out[total + i]);
   }
 }
 
-int prep_weight_up_tc(const float* w_oihw, float* out, int Cout, int Cin, cudaStream_t s) {
-  MF_REQUIRE(Cin % 32 == 0, "prep_weight_up_tc needs Cin % 32 == 0");
+int prep_weight_up_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, cudaStream_t s) {
+  MF_REQUIRE(Cin % 64 == 0, "prep_weight_up_tc needs Cin % 64 == 0");
   const long long total = 16LL * Cout * Cin;
+  // the pre-summed phase taps are at most 4x the largest 3x3 weight: the scale chosen from max|w| leaves 2^13 * 4 < 65504
+  int rc = weight_scales(w_oihw, 9LL * Cout * Cin, scales, s);
+  if (rc) return rc;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  prep_weight_up_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, Cout, Cin);
+  prep_weight_up_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, scales, Cout, Cin);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -207,11 +241,15 @@ conv_simt_kernel(const ConvSimtDesc d, int Hout, int Wout) {
         const int wi = wo * d.stride + sx - pad;
         if (hi >= 0 && hi < d.Hin && wi >= 0 && wi < d.Win) {
           if (d.in_layout == kNCHW) {
-            v = d.in[((static_cast<long long>(n) * d.Cin + c) * d.Hin + hi) * d.Win + wi];
+            v = reinterpret_cast<const float*>(d.in)[((static_cast<long long>(n) * d.Cin + c) * d.Hin + hi) * d.Win + wi];
           } else {
             const long long off = ((static_cast<long long>(n) * d.Hin + hi) * d.Win + wi) * d.Cin + c;
-            v = d.in[off];
-            if (d.in_layout == kNHWCSplit) v += d.in[d.in_plane + off];
+            if (d.in_layout == kNHWCSplit) {
+              const __half* ih = reinterpret_cast<const __half*>(d.in);
+              v = join16(ih[off], ih[d.in_plane + off]);
+            } else {
+              v = reinterpret_cast<const float*>(d.in)[off];
+            }
           }
         }
       }
@@ -253,16 +291,14 @@ conv_simt_kernel(const ConvSimtDesc d, int Hout, int Wout) {
       if (o >= d.Cout) continue;
       float v = acc[i][j] + (d.bias ? d.bias[o] : 0.f);
       if (d.out_layout == kNCHW) {
-        d.out[((static_cast<long long>(n) * d.Cout + o) * Hout + ho) * Wout + wo] = v;
+        reinterpret_cast<float*>(d.out)[((static_cast<long long>(n) * d.Cout + o) * Hout + ho) * Wout + wo] = v;
       } else {
         const long long off = m * d.Cout + o;
         if (d.out_layout == kNHWCSplit) {
-          float hi, lo;
-          tf32_split(v, hi, lo);
-          d.out[off] = hi;
-          d.out[d.out_plane + off] = lo;
+          __half* oh = reinterpret_cast<__half*>(d.out);
+          split16(v, oh[off], oh[d.out_plane + off]);
         } else {
-          d.out[off] = v;
+          reinterpret_cast<float*>(d.out)[off] = v;
         }
       }
     }
@@ -295,19 +331,21 @@ int conv_simt(const ConvSimtDesc& d, cudaStream_t s) {
 // GroupNorm (reference: conv_blocks.py:177,187 -> nn.GroupNorm(eps=1e-5, affine), biased variance)
 // =================================================================================================
 // One block per (n, 8-channel slab): sum / sumsq over all pixels.  Only used after SIMT convs.
-__global__ void gn_partial_from_raw_kernel(const float* __restrict__ raw, long long plane, float* __restrict__ partial,
+__global__ void gn_partial_from_raw_kernel(const void* __restrict__ raw_v, long long plane, float* __restrict__ partial,
                                            int HW, int C) {
   const int n = blockIdx.y, g8 = blockIdx.x;
-  const float* base = raw + static_cast<long long>(n) * HW * C + g8 * 8;
+  const long long boff = static_cast<long long>(n) * HW * C + g8 * 8;
   float s = 0.f, ss = 0.f;
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-    float4 a = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C);
-    float4 b = *reinterpret_cast<const float4*>(base + static_cast<long long>(p) * C + 4);
-    if (plane != 0) {  // split tensor: x = hi + lo
-      const float4 al = *reinterpret_cast<const float4*>(base + plane + static_cast<long long>(p) * C);
-      const float4 bl = *reinterpret_cast<const float4*>(base + plane + static_cast<long long>(p) * C + 4);
-      a.x += al.x; a.y += al.y; a.z += al.z; a.w += al.w;
-      b.x += bl.x; b.y += bl.y; b.z += bl.z; b.w += bl.w;
+    float4 a, b;
+    if (plane != 0) {  // split tensor: x = hi + lo (fp16 planes)
+      const __half* h = reinterpret_cast<const __half*>(raw_v) + boff + static_cast<long long>(p) * C;
+      a = ld_join4(h, h + plane);
+      b = ld_join4(h + 4, h + plane + 4);
+    } else {
+      const float* base = reinterpret_cast<const float*>(raw_v) + boff + static_cast<long long>(p) * C;
+      a = *reinterpret_cast<const float4*>(base);
+      b = *reinterpret_cast<const float4*>(base + 4);
     }
     s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
     ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
@@ -336,7 +374,7 @@ __global__ void gn_partial_from_raw_kernel(const float* __restrict__ raw, long l
   }
 }
 
-int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s, long long plane) {
+int gn_partial_from_raw(const void* raw, float* partial, int N, int HW, int C, cudaStream_t s, long long plane) {
   MF_REQUIRE(C % 8 == 0, "GroupNorm partial sums need C % 8 == 0");
   dim3 grid(C / 8, N);
   gn_partial_from_raw_kernel<<<grid, 256, 0, s>>>(raw, plane, partial, HW, C);
@@ -395,10 +433,12 @@ __global__ void gn_apply_kernel(const GnApplyDesc d) {
     const long long pix = i / c4n;
     const int n = static_cast<int>(pix / d.HW);
     const long long off = pix * d.C + c;
-    float4 x = *reinterpret_cast<const float4*>(d.raw + off);
+    float4 x;
     if (d.raw_plane != 0) {
-      const float4 xl = *reinterpret_cast<const float4*>(d.raw + d.raw_plane + off);
-      x.x += xl.x; x.y += xl.y; x.z += xl.z; x.w += xl.w;
+      const __half* xh = reinterpret_cast<const __half*>(d.raw) + off;
+      x = ld_join4(xh, xh + d.raw_plane);
+    } else {
+      x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.raw) + off);
     }
     const float2 mr = *reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + c / cpg) * 2);
     const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
@@ -410,24 +450,18 @@ __global__ void gn_apply_kernel(const GnApplyDesc d) {
       for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
     }
     if (d.res_kind == kResSplit) {
-      const float4 rh = *reinterpret_cast<const float4*>(d.res + off);
-      const float4 rl = *reinterpret_cast<const float4*>(d.res + d.res_plane + off);
-      y[0] += rh.x + rl.x; y[1] += rh.y + rl.y; y[2] += rh.z + rl.z; y[3] += rh.w + rl.w;
+      const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
+      const float4 r = ld_join4(rh, rh + d.res_plane);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
     } else if (d.res_kind == kResRaw) {
-      const float4 r = *reinterpret_cast<const float4*>(d.res + off);
+      const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
       y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
     }
     if (d.emb != nullptr) {
       const float4 e = *reinterpret_cast<const float4*>(d.emb + static_cast<long long>(n) * d.emb_stride + c);
       y[0] += e.x; y[1] += e.y; y[2] += e.z; y[3] += e.w;
     }
-    float4 hi, lo;
-    tf32_split(y[0], hi.x, lo.x);
-    tf32_split(y[1], hi.y, lo.y);
-    tf32_split(y[2], hi.z, lo.z);
-    tf32_split(y[3], hi.w, lo.w);
-    *reinterpret_cast<float4*>(d.out + off) = hi;
-    *reinterpret_cast<float4*>(d.out + d.out_plane + off) = lo;
+    st_split4(d.out + off, d.out + d.out_plane + off, make_float4(y[0], y[1], y[2], y[3]));
   }
 }
 
@@ -445,7 +479,7 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
 // =================================================================================================
 // nearest x2 upsample (split -> split)
 // =================================================================================================
-__global__ void upsample2x_split_kernel(const float* __restrict__ in, long long in_plane, float* __restrict__ out,
+__global__ void upsample2x_split_kernel(const __half* __restrict__ in, long long in_plane, __half* __restrict__ out,
                                         long long out_plane, int N, int H, int W, int C) {
   const int c4n = C / 4;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -459,12 +493,12 @@ __global__ void upsample2x_split_kernel(const float* __restrict__ in, long long 
     const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
     const long long src = ((static_cast<long long>(n) * H + (ho >> 1)) * W + (wo >> 1)) * C + c;
     const long long dst = pix * C + c;
-    *reinterpret_cast<float4*>(out + dst) = *reinterpret_cast<const float4*>(in + src);
-    *reinterpret_cast<float4*>(out + out_plane + dst) = *reinterpret_cast<const float4*>(in + in_plane + src);
+    *reinterpret_cast<uint2*>(out + dst) = *reinterpret_cast<const uint2*>(in + src);
+    *reinterpret_cast<uint2*>(out + out_plane + dst) = *reinterpret_cast<const uint2*>(in + in_plane + src);
   }
 }
 
-int upsample2x_split(const float* in, long long in_plane, float* out, long long out_plane, int N, int H, int W, int C,
+int upsample2x_split(const __half* in, long long in_plane, __half* out, long long out_plane, int N, int H, int W, int C,
                      cudaStream_t s) {
   MF_REQUIRE(C % 4 == 0, "upsample2x_split needs C % 4 == 0");
   const long long total = static_cast<long long>(N) * 4 * H * W * (C / 4);

@@ -11,54 +11,55 @@ namespace mf {
 enum ActLayout : int {
   kNCHW = 0,       // contiguous fp32 [N,C,H,W]        (reference tensor layout at the API boundary)
   kNHWCRaw = 1,    // fp32 [N,H,W,C], one plane
-  kNHWCSplit = 2,  // fp32 [2][N,H,W,C], TF32-hi plane + residual-lo plane
+  kNHWCSplit = 2,  // fp16 [2][N,H,W,C]: hi = fp16(x) plane + lo = fp16(x - hi) plane
 };
 
 // ---- layout / weight preparation -----------------------------------------------------------------
-int pack_nchw_to_split(const float* x, float* out, long long plane, int N, int C, int H, int W, cudaStream_t s);
-int unpack_to_nchw(const float* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
+int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s);
+int unpack_to_nchw(const void* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
                    cudaStream_t s);
-// OIHW -> [2][Cout][K], K = ((c/32)*kh*kw + r*kw+s)*32 + c%32  (tensor-core path; Cin % 32 == 0)
-int prep_weight_tc(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+// OIHW -> fp16 [2][Cout][K], K = ((c/64)*kh*kw + r*kw+s)*64 + c%64, pre-scaled by 2^S  (tensor-core path; Cin % 64 == 0)
+// scales: device float[4], receives {2^S, 2^-S, scratch}
+int prep_weight_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, int kh, int kw, cudaStream_t s);
 // OIHW 3x3 -> [2][4*Cout][4*Cin]: the four 2x2 phase kernels of conv3x3(nearest_x2(.)) with pre-summed taps
-int prep_weight_up_tc(const float* w_oihw, float* out, int Cout, int Cin, cudaStream_t s);
+int prep_weight_up_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, cudaStream_t s);
 // OIHW -> [K][Cout] fp32 (SIMT path)
 int prep_weight_simt(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t s);
 
 // ---- exact fp32 convolution on CUDA cores ---------------------------------------------------------
 struct ConvSimtDesc {
-  const float* in; long long in_plane; int in_layout;
+  const void* in; long long in_plane; int in_layout;   // float (NCHW / raw) or __half planes (split)
   int N, Cin, Hin, Win;
   const float* w_kc;      // [K][Cout]
   const float* bias;      // [Cout] or nullptr
   int Cout, ksize, stride;  // pad = ksize/2
-  float* out; long long out_plane; int out_layout;
+  void* out; long long out_plane; int out_layout;
 };
 int conv_simt(const ConvSimtDesc& d, cudaStream_t s);
 
 // ---- GroupNorm ------------------------------------------------------------------------------------
 // partial stats layout (shared with conv_tc epilogue): [N][chunks][C/8][2] = (sum, sumsq) over 8 channels
 // plane != 0: `raw` is a split tensor (x = hi + lo)
-int gn_partial_from_raw(const float* raw, float* partial, int N, int HW, int C, cudaStream_t s, long long plane = 0);
+int gn_partial_from_raw(const void* raw, float* partial, int N, int HW, int C, cudaStream_t s, long long plane = 0);
 // partial -> (mean, rstd) per (n, group): out [N][G][2]
 int gn_finalize(const float* partial, float* mean_rstd, int N, int chunks, int C, int G, int HW, float eps,
                 cudaStream_t s);
 enum ResKind : int { kResNone = 0, kResSplit = 1, kResRaw = 2 };
 struct GnApplyDesc {
-  const float* raw;         // [N,HW,C] conv output (+bias)
+  const void* raw;          // [N,HW,C] conv output (+bias), float; or a split tensor (__half planes) when raw_plane != 0
   long long raw_plane;      // != 0: input is a split tensor (hi + lo)
   int act;                  // 1: Swish after the affine (conv blocks), 0: none (attention-block norms)
   const float* mean_rstd;   // [N][G][2]
   const float* gamma; const float* beta;  // [C]
-  const float* res; long long res_plane; int res_kind;
+  const void* res; long long res_plane; int res_kind;   // split: __half planes, raw: float
   const float* emb; int emb_stride;       // emb[n*emb_stride + c] or nullptr
-  float* out; long long out_plane;        // split planes
+  __half* out; long long out_plane;       // split planes
   int N, HW, C, G;
 };
 int gn_apply(const GnApplyDesc& d, cudaStream_t s);
 
 // nearest x2 upsample of a split tensor (reference: conv_blocks.py:123-125, F.interpolate nearest-exact)
-int upsample2x_split(const float* in, long long in_plane, float* out, long long out_plane, int N, int H, int W, int C,
+int upsample2x_split(const __half* in, long long in_plane, __half* out, long long out_plane, int N, int H, int W, int C,
                      cudaStream_t s);
 
 // ---- embedding MLP --------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 """Kernel-level wrappers over the C ABI for tests/profiling (torch tensors in, torch tensors out).
 
-Layouts: activations are NHWC fp32, either one plane ("raw") or two planes [2, N, H, W, C]
-("split": TF32-rounded hi + fp32 residual lo).  torch only provides memory and streams here.
+Layouts: activations are NHWC, either one fp32 plane ("raw") or two fp16 planes [2, N, H, W, C]
+("split": hi = fp16(x), lo = fp16(x - hi)).  torch only provides memory and streams here.
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ def _p(t):
 def pack_split(x_nchw: torch.Tensor) -> torch.Tensor:
     x = x_nchw.contiguous().float()
     N, C, H, W = x.shape
-    out = torch.empty((2, N, H, W, C), device=x.device, dtype=torch.float32)
+    out = torch.empty((2, N, H, W, C), device=x.device, dtype=torch.float16)
     _lib.check(_lib.load().mf_op_pack_split(_p(x), _p(out), out[0].numel(), N, C, H, W, _stream()), "pack_split")
     return out
 
@@ -38,12 +38,15 @@ def unpack_nchw(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def prep_weight_tc(w: torch.Tensor) -> torch.Tensor:
+def prep_weight_tc(w: torch.Tensor):
+    """-> (fp16 planes [2, Cout, K] pre-scaled by 2^S, scales float32[4] = {2^S, 2^-S, scratch})"""
     w = w.contiguous().float()
     Cout, Cin, kh, kw = w.shape
-    out = torch.empty((2, Cout, kh * kw * Cin), device=w.device, dtype=torch.float32)
-    _lib.check(_lib.load().mf_op_prep_weight_tc(_p(w), _p(out), Cout, Cin, kh, kw, _stream()), "prep_weight_tc")
-    return out
+    out = torch.empty((2, Cout, kh * kw * Cin), device=w.device, dtype=torch.float16)
+    scales = torch.zeros(4, device=w.device, dtype=torch.float32)
+    _lib.check(_lib.load().mf_op_prep_weight_tc(_p(w), _p(out), _p(scales), Cout, Cin, kh, kw, _stream()),
+               "prep_weight_tc")
+    return out, scales
 
 
 def prep_weight_simt(w: torch.Tensor) -> torch.Tensor:
@@ -59,20 +62,22 @@ def conv_tc_supported(N, H, W, C0, C1, Cout, ksize, stride=1) -> bool:
 
 
 def conv_tc(src0, w_planes, bias, ksize, src1=None, split_out=False, want_stats=False, drain_interval=0, stride=1):
-    """src*: split tensors [2,N,H,W,C]; returns (out, stats or None)."""
+    """src*: split tensors [2,N,H,W,C]; w_planes: the (planes, scales) pair of prep_weight_tc; returns (out, stats)."""
+    w_planes, scales = w_planes
     _, N, H, W, C0 = src0.shape
     C1 = 0 if src1 is None else src1.shape[-1]
     Cout = w_planes.shape[1]
     dev = src0.device
     Ho, Wo = H // stride, W // stride
-    out = torch.empty(((2, N, Ho, Wo, Cout) if split_out else (N, Ho, Wo, Cout)), device=dev, dtype=torch.float32)
+    out = torch.empty(((2, N, Ho, Wo, Cout) if split_out else (N, Ho, Wo, Cout)), device=dev,
+                      dtype=torch.float16 if split_out else torch.float32)
     stats = None
     if want_stats:
         chunks = _lib.load().mf_op_conv_tc_stats_chunks(Ho, Wo)
         stats = torch.zeros((N, chunks, Cout // 8, 2), device=dev, dtype=torch.float32)
     _lib.check(_lib.load().mf_op_conv_tc(
         _p(src0), src0[0].numel(), C0, _p(src1), 0 if src1 is None else src1[0].numel(), C1, N, H, W,
-        _p(w_planes), Cout, ksize, _p(bias), _p(out), out[0].numel() if split_out else 0,
+        _p(w_planes), _p(scales), Cout, ksize, _p(bias), _p(out), out[0].numel() if split_out else 0,
         NHWC_SPLIT if split_out else NHWC_RAW, _p(stats), drain_interval, stride, _stream()), "conv_tc")
     return out, stats
 
@@ -93,7 +98,7 @@ def conv_simt(x, in_layout, w_kc, bias, Cin, ksize, stride, out_layout):
     Ho = (H + 2 * pad - ksize) // stride + 1
     Wo = (W + 2 * pad - ksize) // stride + 1
     shape = {NCHW: (N, Cout, Ho, Wo), NHWC_RAW: (N, Ho, Wo, Cout), NHWC_SPLIT: (2, N, Ho, Wo, Cout)}[out_layout]
-    out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    out = torch.empty(shape, device=x.device, dtype=torch.float16 if out_layout == NHWC_SPLIT else torch.float32)
     _lib.check(_lib.load().mf_op_conv_simt(_p(x), plane, in_layout, N, Cin, H, W, _p(w_kc), _p(bias), Cout, ksize,
                                            stride, _p(out), out[0].numel() if out_layout == NHWC_SPLIT else 0,
                                            out_layout, _stream()), "conv_simt")
@@ -116,7 +121,7 @@ def gn_finalize(partial, C, G, HW, eps=1e-5):
 
 def gn_apply(raw, mean_rstd, gamma, beta, G, res=None, emb=None):
     N, H, W, C = raw.shape
-    out = torch.empty((2, N, H, W, C), device=raw.device, dtype=torch.float32)
+    out = torch.empty((2, N, H, W, C), device=raw.device, dtype=torch.float16)
     if res is None:
         kind, rplane = 0, 0
     elif res.dim() == 5:
@@ -131,7 +136,7 @@ def gn_apply(raw, mean_rstd, gamma, beta, G, res=None, emb=None):
 
 def upsample2x(x_split):
     _, N, H, W, C = x_split.shape
-    out = torch.empty((2, N, 2 * H, 2 * W, C), device=x_split.device, dtype=torch.float32)
+    out = torch.empty((2, N, 2 * H, 2 * W, C), device=x_split.device, dtype=torch.float16)
     _lib.check(_lib.load().mf_op_upsample2x(_p(x_split), x_split[0].numel(), _p(out), out[0].numel(), N, H, W, C,
                                             _stream()), "upsample2x")
     return out
@@ -142,9 +147,10 @@ def upconv_tc(src_split, w_oihw, bias):
     _, N, H, W, C = src_split.shape
     Cout = w_oihw.shape[0]
     w = w_oihw.contiguous().float()
-    wup = torch.empty((2, 4 * Cout, 4 * C), device=w.device, dtype=torch.float32)
-    _lib.check(_lib.load().mf_op_prep_weight_up_tc(_p(w), _p(wup), Cout, C, _stream()), "prep_weight_up_tc")
-    out = torch.empty((2, N, 2 * H, 2 * W, Cout), device=w.device, dtype=torch.float32)
-    _lib.check(_lib.load().mf_op_upconv_tc(_p(src_split), src_split[0].numel(), C, N, H, W, _p(wup), Cout, _p(bias),
-                                           _p(out), out[0].numel(), _stream()), "upconv_tc")
+    wup = torch.empty((2, 4 * Cout, 4 * C), device=w.device, dtype=torch.float16)
+    scales = torch.zeros(4, device=w.device, dtype=torch.float32)
+    _lib.check(_lib.load().mf_op_prep_weight_up_tc(_p(w), _p(wup), _p(scales), Cout, C, _stream()), "prep_weight_up_tc")
+    out = torch.empty((2, N, 2 * H, 2 * W, Cout), device=w.device, dtype=torch.float16)
+    _lib.check(_lib.load().mf_op_upconv_tc(_p(src_split), src_split[0].numel(), C, N, H, W, _p(wup), _p(scales), Cout,
+                                           _p(bias), _p(out), out[0].numel(), _stream()), "upconv_tc")
     return out

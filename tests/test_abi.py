@@ -83,6 +83,7 @@ def test_plan_census_and_workspace():
     assert lib.mf_op_conv_tc_supported(64, 32, 32, 256, 0, 256, 3, 1) == 1
     assert lib.mf_op_conv_tc_supported(64, 8, 8, 1024, 1024, 1024, 3, 1) == 1
     assert lib.mf_op_conv_tc_supported(64, 32, 32, 8, 0, 256, 3, 1) == 0      # Cin = 8 stem
+    assert lib.mf_op_conv_tc_supported(64, 32, 32, 96, 0, 256, 3, 1) == 0     # channels must be multiples of 64
     assert lib.mf_op_conv_tc_supported(64, 16, 16, 256, 0, 256, 3, 2) == 1     # stride 2 (output 16x16)
     assert lib.mf_op_conv_tc_supported(64, 16, 16, 256, 256, 256, 3, 2) == 0   # stride 2 has no concat source
     assert lib.mf_op_conv_tc_supported(1, 4, 4, 256, 0, 256, 3, 1) == 0        # fewer than 32 pixels

@@ -148,12 +148,16 @@ def test_upsample_nearest_exact():
     assert torch.equal(ops.unpack_nchw(ops.upsample2x(ops.pack_split(x.to(DEV)))).cpu(), ref)
 
 
-def test_split_planes_are_exact():
+def test_split_planes_carry_22_bits():
+    """x = hi + lo with fp16 planes: relative error <= 2^-21 (11 + 11 significant bits), saturation instead of inf."""
     from medfusion_b200 import ops
     x = _rnd(torch.Generator().manual_seed(9), 1, 32, 4, 8) * 1e3
     p = ops.pack_split(x.to(DEV))
-    assert torch.equal(ops.unpack_nchw(p).cpu(), x)                   # hi + lo == x bit for bit
-    assert int((p[0].view(torch.int32) & 0x1FFF).abs().sum()) == 0   # hi plane is TF32-representable
+    assert p.dtype == torch.float16
+    back = ops.unpack_nchw(p).cpu()
+    assert float(((back - x).abs() / x.abs().clamp_min(1e-3)).max()) <= 2.0 ** -21
+    big = torch.full((1, 8, 2, 2), 1e6)
+    assert float(ops.unpack_nchw(ops.pack_split(big.to(DEV))).max()) <= 65504.0 * (1 + 2.0 ** -10)
 
 
 def test_scheduler_step_matches_reference_fixture():
@@ -209,11 +213,11 @@ def test_attention_core_matches_oracle(B, N, heads, d):
     q, k, v = (qkv[..., i * C:(i + 1) * C].transpose(1, 2).contiguous() for i in range(3))   # [B, C, N]
     ref = O.compute_attention(q, k, v, heads, d ** -0.25).transpose(1, 2)                      # [B, N, C]
     dq = qkv.to(DEV).contiguous()
-    out = torch.empty((2, B, N, 1, C), device=DEV)
+    out = torch.empty((2, B, N, 1, C), device=DEV, dtype=torch.float16)
     _lib.check(_lib.load().mf_op_attention(dq.data_ptr(), dq.data_ptr() + 4 * C, dq.data_ptr() + 8 * C, 3 * C,
                                            out.data_ptr(), out[0].numel(), B, N, heads, d,
                                            torch.cuda.current_stream().cuda_stream), "attention")
-    got = (out[0] + out[1]).reshape(B, N, C).cpu()
+    got = (out[0].float() + out[1].float()).reshape(B, N, C).cpu()
     assert_close(got, ref, what="attention core")
 
 
@@ -231,10 +235,10 @@ def test_layernorm_and_geglu_match_oracle():
     dg, db = gamma.to(DEV), beta.to(DEV)   # keep the device copies alive across the asynchronous launch
     _lib.check(lib.mf_op_layernorm(xs.data_ptr(), xs[0].numel(), dg.data_ptr(), db.data_ptr(),
                                    out.data_ptr(), out[0].numel(), T, C, 1e-5, st), "layernorm")
-    assert_close((out[0] + out[1]).reshape(T, C).cpu(), ref, what="layernorm")
+    assert_close((out[0].float() + out[1].float()).reshape(T, C).cpu(), ref, what="layernorm")
     z = _rnd(g, T, 2 * C)
     refg = z[:, :C] * F.gelu(z[:, C:])
-    zo = torch.empty((2, T, C), device=DEV)
+    zo = torch.empty((2, T, C), device=DEV, dtype=torch.float16)
     dz = z.to(DEV)
     _lib.check(lib.mf_op_geglu(dz.data_ptr(), zo.data_ptr(), zo[0].numel(), T, C, st), "geglu")
-    assert_close((zo[0] + zo[1]).cpu(), refg, what="geglu")
+    assert_close((zo[0].float() + zo[1].float()).cpu(), refg, what="geglu")
