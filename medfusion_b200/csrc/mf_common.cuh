@@ -50,7 +50,7 @@ const char* get_error();
 typedef __half sp_t;  // element type of the split (hi / lo) planes
 __device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-  lo = __float2half_rn(x - __half2float(hi));
+  lo = __float2half_rn(fminf(fmaxf(x - __half2float(hi), -65504.f), 65504.f));  // only clamps when hi saturated
 }
 __device__ __forceinline__ float join16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 // four consecutive channels: 8-byte vector accesses on both planes
