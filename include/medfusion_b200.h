@@ -52,6 +52,9 @@ int mf_set_debias_eps(float eps_per_kblock);
 /* BasicUp (nearest x2 + conv3x3, conv_blocks.py:121-131): 1 = four 2x2 phase convolutions on the low-resolution
  * input with pre-summed weights (default), 0 = explicit upsample kernel followed by the 3x3 convolution. */
 int mf_set_fold_upsample(int enable);
+/* Cin < 64 stem convolutions (UNet in_conv, VAE inc_dec): 1 = tcgen05 path through a zero-padded 64-channel copy of the
+ * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
+int mf_set_stem_on_tc(int enable);
 
 /* -------------------------------------------------------------------------------------------------
  * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block

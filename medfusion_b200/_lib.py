@@ -51,6 +51,7 @@ SIGNATURES = {
     "mf_set_block_n": (c_int, [c_int]),
     "mf_set_stream_k": (c_int, [c_int]),
     "mf_set_fold_upsample": (c_int, [c_int]),
+    "mf_set_stem_on_tc": (c_int, [c_int]),
     "mf_set_debias_eps": (c_int, [c_float]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),

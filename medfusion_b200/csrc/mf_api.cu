@@ -402,6 +402,10 @@ int mf_set_debias_eps(float eps_per_kblock) {
   mf::g_debias_eps_per_kblock = eps_per_kblock;
   return 0;
 }
+int mf_set_stem_on_tc(int enable) {
+  mf::g_stem_on_tc = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_fold_upsample(int enable) {
   mf::g_fold_upsample = enable ? 1 : 0;
   return 0;

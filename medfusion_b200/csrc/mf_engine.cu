@@ -4,7 +4,8 @@
 
 namespace mf {
 
-int g_fold_upsample = 1;  // BasicUp as four phase convolutions (0: explicit nearest-x2 kernel + conv3x3)
+int g_fold_upsample = 1;
+int g_stem_on_tc = 1;      // Cin < 64 stem convolutions on the tensor core through a zero-padded 64-channel input  // BasicUp as four phase convolutions (0: explicit nearest-x2 kernel + conv3x3)
 
 // ---- error string --------------------------------------------------------------------------------
 static thread_local std::string g_error;
@@ -181,11 +182,13 @@ Tens EngineBase::new_floats(size_t n) {
 void EngineBase::free_tensor(const Tens& t) { arena.release(t.off, t.bytes); }
 
 // ---- derived weight layouts ----------------------------------------------------------------------
-int EngineBase::ensure_w_tc(ConvLayer& L) {
+int EngineBase::ensure_w_tc(ConvLayer& L, int cin_pad) {
   if (L.tc_version == version) return 0;
-  if (L.w_tc.alloc(L.w->numel()) || L.tc_scales.alloc(4)) return 1;  // 2 fp16 planes == numel floats
+  const int cp = cin_pad > 0 ? cin_pad : L.Cin;
+  // 2 fp16 planes of Cout x k x k x cp elements == that many floats
+  if (L.w_tc.alloc(static_cast<size_t>(L.Cout) * cp * L.k * L.k) || L.tc_scales.alloc(4)) return 1;
   int rc = prep_weight_tc(L.w->data.p, reinterpret_cast<__half*>(L.w_tc.p), L.tc_scales.p, L.Cout, L.Cin, L.k, L.k,
-                          prep_stream);
+                          prep_stream, cp);
   if (rc) return rc;
   L.tc_version = version;
   return 0;
@@ -311,6 +314,39 @@ int EngineBase::add_upconv2x(ConvLayer& L, const Tens& in, Tens* out) {
 int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, int Cin, int H, int W, const Tens& out,
                                  const Tens* stats, int* chunks) {
   MF_REQUIRE(Cin == L.Cin && out.C == L.Cout, "stem conv channel mismatch (" + L.w->name + ")");
+  // Narrow stems (Cin = 8) still go to the tensor core: the NCHW input is packed into a zero-padded 64-channel split
+  // tensor and the weights get zero columns.  7/8 of the issued MMAs multiply zeros, yet at ~400 TFLOP/s that is 5x
+  // faster than the exact-fp32 CUDA-core kernel (0.05 ms instead of 0.25 ms per UNet step at B = 64).
+  if (g_stem_on_tc && L.stride == 1 && Cin < 64 && out.layout != kNCHW && out.H == H && out.W == W &&
+      conv_tc_supported(N, H, W, 64, 0, L.Cout, L.k, 1)) {
+    ++n_tc;
+    if (chunks) *chunks = conv_tc_stats_chunks(H, W);
+    Tens xp = new_tensor(N, H, W, 64, kNHWCSplit);
+    if (!dry) {
+      __half* xpp = xp.hptr();
+      const long long xpl = xp.plane;
+      push_op([src, xpp, xpl, N, Cin, H, W](cudaStream_t s) { return pack_nchw_to_split(*src, xpp, xpl, N, Cin, H, W, s, 64); },
+              kOpOther);
+      int rc = ensure_w_tc(L, 64);
+      if (rc) return rc;
+      ConvTcDesc d{};
+      d.src0 = xp.hptr(); d.src0_plane = xp.plane; d.C0 = 64;
+      d.N = N; d.H = H; d.W = W; d.stride = 1;
+      d.w_planes = reinterpret_cast<const __half*>(L.w_tc.p); d.w_inv_scale = L.tc_scales.p + 1;
+      d.Cout = L.Cout; d.ksize = L.k;
+      d.bias = L.b->data.p;
+      d.out = out.ptr; d.out_plane = out.plane; d.out_mode = out.layout == kNHWCSplit ? kOutSplit : kOutRaw;
+      d.stats = stats ? stats->ptr : nullptr;
+      tc_plans.emplace_back(new ConvTcPlan());
+      ConvTcPlan* plan = tc_plans.back().get();
+      rc = conv_tc_build(d, plan);
+      if (rc) return rc;
+      push_op([plan](cudaStream_t s) { return conv_tc_launch(*plan, s); }, kOpConvTc,
+              2.0 * N * H * W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
+    }
+    free_tensor(xp);
+    return 0;
+  }
   ++n_simt;
   if (chunks) *chunks = 1;
   if (dry) return 0;

@@ -114,6 +114,7 @@ struct Tens {
 };
 
 extern int g_fold_upsample;
+extern int g_stem_on_tc;
 using Launch = std::function<int(cudaStream_t)>;
 enum OpKind : int { kOpConvTc = 0, kOpConvSimt = 1, kOpNorm = 2, kOpOther = 3 };
 struct OpMeta { int kind; double flops; };
@@ -172,7 +173,7 @@ class EngineBase {
   // full res block: in0 (+in1 concat) -> returns output tensor (split)
   int add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, const Tens* in1, const Tens* embT, int emb_stride,
                    Tens* out);
-  int ensure_w_tc(ConvLayer& L);
+  int ensure_w_tc(ConvLayer& L, int cin_pad = 0);
   int ensure_w_simt(ConvLayer& L);
   int run(cudaStream_t s);
   // run with a CUDA event pair around every op; synchronises. ms[i] receives the device time of op i.

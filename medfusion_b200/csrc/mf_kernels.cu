@@ -10,25 +10,27 @@ __device__ __forceinline__ float swish(float x) { return x / (1.0f + expf(-x)); 
 // Layout packing
 // =================================================================================================
 __global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, __half* __restrict__ out, long long plane, int N,
-                                          int C, int H, int W) {
-  const long long total = static_cast<long long>(N) * H * W * C;
+                                          int C, int H, int W, int Cpad) {
+  const long long total = static_cast<long long>(N) * H * W * Cpad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const long long pix = i / C;
+    const int c = static_cast<int>(i % Cpad);
+    const long long pix = i / Cpad;
     const int w = static_cast<int>(pix % W);
     const int h = static_cast<int>((pix / W) % H);
     const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    const float v = x[((static_cast<long long>(n) * C + c) * H + h) * W + w];
+    const float v = c < C ? x[((static_cast<long long>(n) * C + c) * H + h) * W + w] : 0.f;  // zero-padded channels
     split16(v, out[i], out[plane + i]);
   }
 }
 
-int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s) {
-  const long long total = static_cast<long long>(N) * H * W * C;
+int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s,
+                       int Cpad) {
+  if (Cpad < C) Cpad = C;
+  const long long total = static_cast<long long>(N) * H * W * Cpad;
   if (total == 0) return 0;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W);
+  pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W, Cpad);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -88,8 +90,8 @@ __global__ void weight_scale_kernel(const float* __restrict__ absmax, float* __r
 }
 
 __global__ void prep_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ out,
-                                      const float* __restrict__ scales, int Cout, int Cin, int kh, int kw) {
-  const long long K = static_cast<long long>(kh) * kw * Cin;
+                                      const float* __restrict__ scales, int Cout, int Cin, int kh, int kw, int CinPad) {
+  const long long K = static_cast<long long>(kh) * kw * CinPad;
   const long long total = K * Cout;
   const float sc = scales[0];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -102,7 +104,7 @@ __global__ void prep_weight_tc_kernel(const float* __restrict__ w, __half* __res
     const int rem = static_cast<int>(k % (taps * 64));
     const int tap = rem / 64;
     const int c = cb * 64 + rem % 64;
-    const float v = w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap] * sc;
+    const float v = c < Cin ? w[(static_cast<long long>(o) * Cin + c) * kh * kw + tap] * sc : 0.f;
     split16(v, out[i], out[total + i]);
   }
 }
@@ -117,13 +119,15 @@ static int weight_scales(const float* w, long long n, float* scales, cudaStream_
   return 0;
 }
 
-int prep_weight_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, int kh, int kw, cudaStream_t s) {
-  MF_REQUIRE(Cin % 64 == 0, "prep_weight_tc needs Cin % 64 == 0");
-  const long long total = static_cast<long long>(Cout) * Cin * kh * kw;
-  int rc = weight_scales(w_oihw, total, scales, s);
+int prep_weight_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, int kh, int kw, cudaStream_t s,
+                   int cin_pad) {
+  if (cin_pad <= 0) cin_pad = Cin;
+  MF_REQUIRE(cin_pad % 64 == 0 && cin_pad >= Cin, "prep_weight_tc needs the (padded) channel count to be a multiple of 64");
+  int rc = weight_scales(w_oihw, static_cast<long long>(Cout) * Cin * kh * kw, scales, s);
   if (rc) return rc;
+  const long long total = static_cast<long long>(Cout) * cin_pad * kh * kw;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  prep_weight_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, scales, Cout, Cin, kh, kw);
+  prep_weight_tc_kernel<<<blocks, 256, 0, s>>>(w_oihw, out, scales, Cout, Cin, kh, kw, cin_pad);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -15,12 +15,15 @@ enum ActLayout : int {
 };
 
 // ---- layout / weight preparation -----------------------------------------------------------------
-int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s);
+// Cpad > C: channels C..Cpad-1 of the NHWC output are zero (stem convolutions on the tensor-core path)
+int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s,
+                       int Cpad = 0);
 int unpack_to_nchw(const void* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
                    cudaStream_t s);
 // OIHW -> fp16 [2][Cout][K], K = ((c/64)*kh*kw + r*kw+s)*64 + c%64, pre-scaled by 2^S  (tensor-core path; Cin % 64 == 0)
 // scales: device float[4], receives {2^S, 2^-S, scratch}
-int prep_weight_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, int kh, int kw, cudaStream_t s);
+int prep_weight_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, int kh, int kw, cudaStream_t s,
+                   int cin_pad = 0);
 // OIHW 3x3 -> [2][4*Cout][4*Cin]: the four 2x2 phase kernels of conv3x3(nearest_x2(.)) with pre-summed taps
 int prep_weight_up_tc(const float* w_oihw, __half* out, float* scales, int Cout, int Cin, cudaStream_t s);
 // OIHW -> [K][Cout] fp32 (SIMT path)

@@ -78,8 +78,8 @@ def test_plan_census_and_workspace():
     nbytes = lib.mf_unet_workspace_bytes(m._h, 64, 32, 32)
     assert 100e6 < nbytes < 8e9
     info = m.plan_info()
-    # canonical UNet: 51 convs; only the Cin=8 stem and the Cout=8 head are SIMT
-    assert info["tc_convs"] == 49 and info["simt_convs"] == 2
+    # canonical UNet: 51 convs; only the Cout=8 head is not on the tensor-core path
+    assert info["tc_convs"] == 50 and info["simt_convs"] == 1
     assert lib.mf_op_conv_tc_supported(64, 32, 32, 256, 0, 256, 3, 1) == 1
     assert lib.mf_op_conv_tc_supported(64, 8, 8, 1024, 1024, 1024, 3, 1) == 1
     assert lib.mf_op_conv_tc_supported(64, 32, 32, 8, 0, 256, 3, 1) == 0      # Cin = 8 stem

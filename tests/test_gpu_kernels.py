@@ -53,7 +53,7 @@ def test_conv_tc_matches_oracle(shape):
     # split-plane (fp16 hi/lo) output variant carries the same values to 22 bits
     out2, _ = ops.conv_tc(s0, ops.prep_weight_tc(wd), bd, k, src1=s1, split_out=True)
     a, b2 = ops.unpack_nchw(out2), ops.unpack_nchw(out)
-    assert float(((a - b2).abs() / b2.abs().clamp_min(1e-2)).max()) <= 2.0 ** -20
+    assert bool(((a - b2).abs() <= 2.0 ** -21 * b2.abs() + 1.2e-7).all())   # 22 bits, or fp16-subnormal lo (6e-8 steps)
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 256, 256), (3, 16, 16, 512, 512), (1, 64, 64, 64, 128)],
