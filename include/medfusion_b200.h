@@ -56,6 +56,17 @@ int mf_set_fold_upsample(int enable);
  * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
 int mf_set_stem_on_tc(int enable);
 
+/* scheduler tables: fp32[T] device arrays as registered by gaussian_scheduler.py:44-58 */
+typedef struct {
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_variance;
+  const float* betas;
+  const float* alphas_cumprod;
+} mf_sched_tables;
+
 /* -------------------------------------------------------------------------------------------------
  * UNet noise estimator (unet2.py:15-219 constructor arguments, restricted to the 2-D res-block
  * configuration the hot path uses)
@@ -93,6 +104,23 @@ size_t mf_unet_workspace_bytes(mf_unet* h, int B, int H, int W);
 /* y[B,out_ch,H,W] = UNet(x_t[B,in_ch,H,W], t[B] (int64), cond[B] (int64) or NULL).  NCHW fp32. */
 int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
                     int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream);
+/* UNet.forward with the scheduler update fused into the epilogue of the output head (unet2.py:267 +
+ * gaussian_scheduler.py:80-124 + diffusion_pipeline.py:244,297-304): the estimator output never round-trips through a
+ * separate elementwise kernel.  d_y may be NULL when only the step outputs are wanted.  Requires out_ch <= 8. */
+typedef struct {
+  const mf_sched_tables* tables;
+  const float* d_pred_uncond;   /* NULL: no classifier-free guidance */
+  float guidance_scale;
+  const float* d_noise;         /* scheduler draw, NULL = 0 */
+  const int64_t* d_t_next;      /* NULL: no DDIM-form re-noise */
+  const float* d_noise_ddim;
+  int objective_is_x0;
+  int clip_x0;
+  float* d_x_prior; float* d_x_0; float* d_x_T; float* d_x_next;   /* any may be NULL */
+} mf_step_args;
+int mf_unet_forward_step(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
+                         int H, int W, void* d_workspace, size_t workspace_bytes, const mf_step_args* step,
+                         mf_stream_t stream);
 /* Same as mf_unet_forward but with a CUDA-event pair around every kernel launch of the plan (synchronises).
  * ms[i]: device time of launch i; kinds[i]: 0 conv_tc, 1 conv_simt, 2 GroupNorm family, 3 other;
  * flops[i]: algorithmic FLOPs of launch i (2*MACs of the reference formulation; 0 for non-GEMM work). */
@@ -136,15 +164,7 @@ int mf_vae_plan_info(const mf_vae* h, int* n_tc_convs, int* n_simt_convs, int* n
  * Scheduler step (all tensors [B, chw] fp32 contiguous; tables fp32[T] as registered by
  * gaussian_scheduler.py:44-58; t int64[B]; t_next int64 scalar or NULL)
  * ---------------------------------------------------------------------------------------------- */
-typedef struct {
-  const float* sqrt_recip_alphas_cumprod;
-  const float* sqrt_recipm1_alphas_cumprod;
-  const float* posterior_mean_coef1;
-  const float* posterior_mean_coef2;
-  const float* posterior_variance;
-  const float* betas;
-  const float* alphas_cumprod;
-} mf_sched_tables;
+/* mf_sched_tables is declared above (before the UNet section). */
 
 int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred,
                   const float* d_pred_uncond /* NULL: no guidance */, float guidance_scale, const int64_t* d_t,

@@ -41,6 +41,15 @@ class SchedTables(ctypes.Structure):
         "posterior_mean_coef2", "posterior_variance", "betas", "alphas_cumprod")]
 
 
+class StepArgs(ctypes.Structure):
+    _fields_ = [
+        ("tables", POINTER(SchedTables)), ("d_pred_uncond", c_void_p), ("guidance_scale", c_float),
+        ("d_noise", c_void_p), ("d_t_next", c_void_p), ("d_noise_ddim", c_void_p),
+        ("objective_is_x0", c_int), ("clip_x0", c_int),
+        ("d_x_prior", c_void_p), ("d_x_0", c_void_p), ("d_x_T", c_void_p), ("d_x_next", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/medfusion_b200.h
 _P = c_void_p
 SIGNATURES = {
@@ -62,6 +71,7 @@ SIGNATURES = {
     "mf_unet_set_time_freqs": (c_int, [_P, _P, c_int, _P]),
     "mf_unet_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_unet_forward_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, POINTER(StepArgs), _P]),
     "mf_unet_profile": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float),
                                 POINTER(c_int), POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "mf_unet_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

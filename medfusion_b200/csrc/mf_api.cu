@@ -485,6 +485,44 @@ int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const in
   h->io_y = d_y;
   return h->run(s);
 }
+static void fill_step_desc(SchedStepDesc& d, const mf_step_args* a, const float* x_t, const int64_t* t, int B, int chw) {
+  d = SchedStepDesc{};
+  d.x_t = x_t; d.pred = nullptr; d.pred_uncond = a->d_pred_uncond; d.guidance = a->guidance_scale;
+  d.t = reinterpret_cast<const long long*>(t);
+  d.noise = a->d_noise;
+  d.t_next = reinterpret_cast<const long long*>(a->d_t_next);
+  d.noise2 = a->d_noise_ddim;
+  d.objective_x0 = a->objective_is_x0; d.clip_x0 = a->clip_x0;
+  d.x_prior = a->d_x_prior; d.x_0 = a->d_x_0; d.x_T = a->d_x_T; d.x_next = a->d_x_next;
+  d.B = B; d.CHW = chw;
+  d.tab.sqrt_recip_ac = a->tables->sqrt_recip_alphas_cumprod;
+  d.tab.sqrt_recipm1_ac = a->tables->sqrt_recipm1_alphas_cumprod;
+  d.tab.coef1 = a->tables->posterior_mean_coef1;
+  d.tab.coef2 = a->tables->posterior_mean_coef2;
+  d.tab.post_var = a->tables->posterior_variance;
+  d.tab.betas = a->tables->betas;
+  d.tab.alphas_cumprod = a->tables->alphas_cumprod;
+}
+int mf_unet_forward_step(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
+                         int H, int W, void* d_workspace, size_t workspace_bytes, const mf_step_args* step,
+                         mf_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MF_REQUIRE(d_x_t && d_t && step && step->tables && B > 0 && H > 0 && W > 0, "bad arguments");
+  MF_REQUIRE(h->cfg.out_ch <= 8 && h->cfg.hid_chs[0] % 64 == 0 && h->cfg.kernel_sizes[0] / 2 * 2 + 1 == h->cfg.kernel_sizes[0] &&
+                 h->cfg.strides[0] == 1,
+             "the fused head needs out_ch <= 8, hid_chs[0] % 64 == 0 and a stride-1 stem (use mf_unet_forward + mf_sched_step)");
+  int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_x = d_x_t;
+  h->io_t = reinterpret_cast<const long long*>(d_t);
+  h->io_cond = reinterpret_cast<const long long*>(d_cond);
+  h->io_y = d_y;
+  fill_step_desc(h->io_step, step, d_x_t, d_t, B, h->cfg.out_ch * H * W);
+  h->io_step_on = true;
+  rc = h->run(s);
+  h->io_step_on = false;
+  return rc;
+}
 int mf_unet_profile(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B, int H,
                     int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds,
                     double* flops, int max_ops, int* n_ops) {

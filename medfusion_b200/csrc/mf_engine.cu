@@ -374,6 +374,21 @@ int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, i
 
 int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst) {
   MF_REQUIRE(in0.C == L.Cin, "head conv channel mismatch (" + L.w->name + ")");
+  if (L.k == 1 && L.stride == 1 && L.Cout <= 8 && in0.layout == kNHWCSplit && in0.C % 64 == 0) {
+    // narrow 1x1 head straight from the reference-layout weights; the scheduler update can ride in its epilogue
+    ++n_simt;
+    if (dry) return 0;
+    HeadDesc hd{};
+    hd.in = in0.hptr(); hd.in_plane = in0.plane;
+    hd.w = L.w->data.p; hd.bias = L.b->data.p;
+    hd.N = in0.N; hd.HW = in0.H * in0.W; hd.C = in0.C; hd.Cout = L.Cout;
+    push_op([this, hd, dst](cudaStream_t s) {
+      HeadDesc h2 = hd;
+      h2.out = *dst;
+      return head1x1(h2, io_step_on ? &io_step : nullptr, s);
+    }, kOpConvSimt, 2.0 * in0.N * in0.H * in0.W * L.Cout * static_cast<double>(L.Cin));
+    return 0;
+  }
   ++n_simt;
   if (dry) return 0;
   int rc = ensure_w_simt(L);

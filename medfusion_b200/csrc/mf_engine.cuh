@@ -141,6 +141,10 @@ class EngineBase {
   std::vector<std::unique_ptr<ConvTcPlan>> tc_plans;
   int n_tc = 0, n_simt = 0;
 
+  // optional scheduler update fused into the narrow output head (set per call by the C ABI)
+  SchedStepDesc io_step{};
+  bool io_step_on = false;
+
   // ---- builder state (valid during build())
   bool dry = false;
   char* base = nullptr;

@@ -573,53 +573,119 @@ int linear_small(const LinearDesc& d, cudaStream_t s) {
 // =================================================================================================
 // Scheduler step (reference: gaussian_scheduler.py:80-124, diffusion_pipeline.py:240-244, :297-304)
 // =================================================================================================
+// one element of the reverse step; `pred` is the estimator output for this element (before guidance)
+__device__ __forceinline__ void sched_element(const SchedStepDesc& d, long long i, int b, float pred) {
+  const long long t = d.t[b];
+  if (d.pred_uncond != nullptr) {
+    const float pu = d.pred_uncond[i];
+    pred = pu + d.guidance * (pred - pu);  // classifier-free guidance combine
+  }
+  const float xt = d.x_t[i];
+  const float A = d.tab.sqrt_recip_ac[t], Bm = d.tab.sqrt_recipm1_ac[t];
+  float x0, xT;
+  if (d.objective_x0) {
+    x0 = pred;
+    if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    xT = __fdiv_rn(__fsub_rn(__fmul_rn(A, xt), x0), Bm);
+  } else {
+    xT = pred;
+    x0 = __fsub_rn(__fmul_rn(A, xt), __fmul_rn(Bm, pred));
+    if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  }
+  const float mean = __fadd_rn(__fmul_rn(d.tab.coef1[t], x0), __fmul_rn(d.tab.coef2[t], xt));
+  float stdv = 0.f;
+  if (t != 0) stdv = expf(0.5f * logf(fmaxf(d.tab.post_var[t], 1e-20f)));
+  const float nz = d.noise ? d.noise[i] : 0.f;
+  const float prior = __fadd_rn(mean, __fmul_rn(stdv, nz));
+  if (d.x_prior) d.x_prior[i] = prior;
+  if (d.x_0) d.x_0[i] = x0;
+  if (d.x_T) d.x_T[i] = xT;
+  if (d.x_next) {
+    float xn = prior;
+    if (d.t_next != nullptr) {
+      // DDIM-form re-noise with eta == 1 (diffusion_pipeline.py:297-304)
+      const float a = d.tab.alphas_cumprod[t];
+      const float an = d.tab.alphas_cumprod[*d.t_next];
+      const float sig2arg =
+          __fdiv_rn(__fmul_rn(__fsub_rn(1.f, __fdiv_rn(a, an)), __fsub_rn(1.f, an)), __fsub_rn(1.f, a));
+      const float sigma = __fsqrt_rn(sig2arg);
+      const float cc = __fsqrt_rn(__fsub_rn(__fsub_rn(1.f, an), __fmul_rn(sigma, sigma)));
+      const float n2 = d.noise2 ? d.noise2[i] : 0.f;
+      xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, __fsqrt_rn(an)), __fmul_rn(cc, xT)), __fmul_rn(sigma, n2));
+    }
+    d.x_next[i] = xn;
+  }
+}
+
 __global__ void sched_step_kernel(const SchedStepDesc d) {
   const long long total = static_cast<long long>(d.B) * d.CHW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(i / d.CHW);
-    const long long t = d.t[b];
-    float pred = d.pred[i];
-    if (d.pred_uncond != nullptr) {
-      const float pu = d.pred_uncond[i];
-      pred = pu + d.guidance * (pred - pu);  // classifier-free guidance combine
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    sched_element(d, i, static_cast<int>(i / d.CHW), d.pred[i]);
+}
+
+// =================================================================================================
+// Narrow 1x1 head (Cout <= 8) on a split NHWC tensor -> NCHW fp32, optionally fused with the scheduler update:
+//   reference: unet2.py:213,267 (UnetOutBlock 256 -> 8) + gaussian_scheduler.py:80-124;  latent_embedders.py:743 (64 -> 3)
+// One warp per pixel: lanes stride the channels, 8 butterfly reductions, lane o owns output channel o.
+// =================================================================================================
+__global__ void __launch_bounds__(256) head1x1_kernel(const HeadDesc h, const SchedStepDesc sd) {
+  extern __shared__ float wsm[];  // [Cout][C] weights + [Cout] bias
+  for (int e = threadIdx.x; e < h.Cout * h.C; e += blockDim.x) wsm[e] = h.w[e];
+  for (int e = threadIdx.x; e < h.Cout; e += blockDim.x) wsm[h.Cout * h.C + e] = h.bias ? h.bias[e] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long npix = static_cast<long long>(h.N) * h.HW;
+  for (long long pix = warp0; pix < npix; pix += nwarps) {
+    const __half* xh = h.in + pix * h.C;
+    const __half* xl = xh + h.in_plane;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int c = lane * 2; c < h.C; c += 64) {  // two channels per lane per pass (4-byte loads on both planes)
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xh + c));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(xl + c));
+      const float x0 = a.x + b.x, x1 = a.y + b.y;
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < h.Cout) acc[o] = fmaf(x1, wsm[o * h.C + c + 1], fmaf(x0, wsm[o * h.C + c], acc[o]));
     }
-    const float xt = d.x_t[i];
-    const float A = d.tab.sqrt_recip_ac[t], Bm = d.tab.sqrt_recipm1_ac[t];
-    float x0, xT;
-    if (d.objective_x0) {
-      x0 = pred;
-      if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-      xT = __fdiv_rn(__fsub_rn(__fmul_rn(A, xt), x0), Bm);
-    } else {
-      xT = pred;
-      x0 = __fsub_rn(__fmul_rn(A, xt), __fmul_rn(Bm, pred));
-      if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-    }
-    const float mean = __fadd_rn(__fmul_rn(d.tab.coef1[t], x0), __fmul_rn(d.tab.coef2[t], xt));
-    float stdv = 0.f;
-    if (t != 0) stdv = expf(0.5f * logf(fmaxf(d.tab.post_var[t], 1e-20f)));
-    const float nz = d.noise ? d.noise[i] : 0.f;
-    const float prior = __fadd_rn(mean, __fmul_rn(stdv, nz));
-    if (d.x_prior) d.x_prior[i] = prior;
-    if (d.x_0) d.x_0[i] = x0;
-    if (d.x_T) d.x_T[i] = xT;
-    if (d.x_next) {
-      float xn = prior;
-      if (d.t_next != nullptr) {
-        // DDIM-form re-noise with eta == 1 (diffusion_pipeline.py:297-304)
-        const float a = d.tab.alphas_cumprod[t];
-        const float an = d.tab.alphas_cumprod[*d.t_next];
-        const float sig2arg =
-            __fdiv_rn(__fmul_rn(__fsub_rn(1.f, __fdiv_rn(a, an)), __fsub_rn(1.f, an)), __fsub_rn(1.f, a));
-        const float sigma = __fsqrt_rn(sig2arg);
-        const float cc = __fsqrt_rn(__fsub_rn(__fsub_rn(1.f, an), __fmul_rn(sigma, sigma)));
-        const float n2 = d.noise2 ? d.noise2[i] : 0.f;
-        xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, __fsqrt_rn(an)), __fmul_rn(cc, xT)), __fmul_rn(sigma, n2));
-      }
-      d.x_next[i] = xn;
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if (lane < h.Cout) {
+      float y = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o == lane) y = acc[o];
+      y += wsm[h.Cout * h.C + lane];
+      const int n = static_cast<int>(pix / h.HW);
+      const long long i = (static_cast<long long>(n) * h.Cout + lane) * h.HW + (pix - static_cast<long long>(n) * h.HW);
+      if (h.out != nullptr) h.out[i] = y;
+      if (h.fuse_step) sched_element(sd, i, n, y);
     }
   }
+}
+
+int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s) {
+  MF_REQUIRE(h.Cout >= 1 && h.Cout <= 8 && h.C % 64 == 0, "head1x1: Cout <= 8 and C % 64 == 0");
+  const long long npix = static_cast<long long>(h.N) * h.HW;
+  if (npix == 0) return 0;
+  HeadDesc hh = h;
+  SchedStepDesc sd{};
+  hh.fuse_step = 0;
+  if (step != nullptr) {
+    sd = *step;
+    hh.fuse_step = 1;
+    MF_REQUIRE(sd.B == h.N && sd.CHW == h.Cout * h.HW, "fused scheduler step geometry must match the head output");
+  }
+  const size_t smem = (static_cast<size_t>(h.Cout) * h.C + h.Cout) * sizeof(float);
+  const int blocks = static_cast<int>(std::min<long long>((npix + 7) / 8, 148 * 8));
+  head1x1_kernel<<<blocks, 256, smem, s>>>(hh, sd);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int sched_step(const SchedStepDesc& d, cudaStream_t s) {

@@ -97,4 +97,15 @@ struct SchedStepDesc {
 };
 int sched_step(const SchedStepDesc& d, cudaStream_t s);
 
+// ---- narrow 1x1 head (Cout <= 8): split NHWC -> NCHW fp32, optional fused scheduler step ------------------------
+struct HeadDesc {
+  const __half* in; long long in_plane;  // split [N][HW][C]
+  const float* w; const float* bias;     // [Cout][C] (reference OIHW layout of a 1x1 conv), [Cout]
+  float* out;                            // NCHW [N][Cout][HW] or nullptr (only the fused step outputs are wanted)
+  int N, HW, C, Cout;
+  int fuse_step;
+};
+// step != nullptr: every output element is fed to the scheduler update as `pred` (step->pred is ignored)
+int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s);
+
 }  // namespace mf

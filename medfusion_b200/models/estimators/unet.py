@@ -138,6 +138,40 @@ class UNet(EngineModule):
                                                None if cond is None else cond.data_ptr(), y.data_ptr(), B, H, W, ws,
                                                ws_bytes, cuda_stream_ptr()), "mf_unet_forward")
 
+    def forward_step(self, x_t, t, condition, scheduler, *, pred_uncond=None, guidance_scale=1.0, noise=None,
+                     t_next=None, noise_ddim=None, objective="x_T", clip_x0=True, want=("x_next",), want_pred=False):
+        """UNet.forward with `scheduler`'s reverse step fused into the output head's epilogue (mf_unet_forward_step).
+
+        Returns a dict with the requested tensors among x_prior, x_0, x_T, x_next (+ 'pred' if want_pred)."""
+        require_cuda(x_t, "UNet.forward_step(x_t)")
+        self.sync_params()
+        B, _, H, W = x_t.shape
+        x = x_t.contiguous().float()
+        tt = t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
+        cc = None
+        if condition is not None and self.cond_spec is not None:
+            cc = condition.to(device=x.device, dtype=torch.int64).contiguous()
+        outs = {k: torch.empty_like(x) for k in want}
+        pred = torch.empty_like(x) if want_pred else None
+        if t_next is not None:
+            t_next = t_next.to(device=x.device, dtype=torch.int64).reshape(1).contiguous()
+        tab = scheduler._tables()
+        keep = [v.contiguous() if v is not None else None for v in (pred_uncond, noise, noise_ddim)]
+
+        def ptr(v):
+            return None if v is None else v.data_ptr()
+
+        args = _lib.StepArgs(ctypes.pointer(tab), ptr(keep[0]), float(guidance_scale), ptr(keep[1]), ptr(t_next),
+                             ptr(keep[2]), 1 if objective == "x_0" else 0, 1 if clip_x0 else 0,
+                             ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")))
+        ws, ws_bytes = self._workspace(B, H, W)
+        _lib.check(_lib.load().mf_unet_forward_step(self._h, x.data_ptr(), tt.data_ptr(), ptr(cc), ptr(pred), B, H, W, ws,
+                                                    ws_bytes, ctypes.byref(args), cuda_stream_ptr()),
+                   "mf_unet_forward_step")
+        if want_pred:
+            outs["pred"] = pred
+        return outs
+
     def profile(self, x_t, t, condition=None):
         """Per-launch device times of one forward: list of (ms, kind, algorithmic_flops); kind 0 = tcgen05 conv."""
         self.sync_params()

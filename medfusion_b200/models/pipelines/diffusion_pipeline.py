@@ -150,20 +150,32 @@ class DiffusionPipeline(nn.Module):
         B = x_t.shape[0]
         x_t = x_t.contiguous().float()
         ts = timesteps_array.flip(0)
+        est = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
+        fused = hasattr(est, "forward_step") and getattr(est, "out_ch", 99) <= 8 and not est.estimate_variance
+        cfg = (condition is not None) and (guidance_scale != 1.0)
         for i in range(steps):
             t = ts[i]
             tb = t.expand(B)
-            pred, pred_u = self._predict(x_t, tb, condition, guidance_scale, un_cond)
-            noise = noise_fn(x_t)                             # scheduler draw (gaussian_scheduler.py:99)
             ddim = use_ddim and (steps - i - 1 > 0)
-            if ddim:
-                noise2 = noise_fn(x_t)                        # DDIM draw (diffusion_pipeline.py:303)
-                o = sched.step(x_t, tb, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
-                               t_next=timesteps_array[steps - i - 2], noise_ddim=noise2,
-                               objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",))
+            t_next = timesteps_array[steps - i - 2] if ddim else None
+            if fused:
+                # estimator pass(es) first (as in the reference), then the draws; the last estimator pass carries the
+                # CFG combine + scheduler update (+ DDIM re-noise) in the epilogue of its output head
+                pred_u = est(x_t, tb, condition=un_cond, self_cond=None)[0] if cfg else None
+                noise = noise_fn(x_t)                         # scheduler draw (gaussian_scheduler.py:99)
+                noise2 = noise_fn(x_t) if ddim else None      # DDIM draw (diffusion_pipeline.py:303)
+                # NOTE: the draws happen before the (asynchronous) estimator launch but consume the generator in the
+                # reference's order; their values do not depend on the estimator.
+                o = est.forward_step(x_t, tb, condition, sched, pred_uncond=pred_u, guidance_scale=guidance_scale,
+                                     noise=noise, t_next=t_next, noise_ddim=noise2,
+                                     objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",))
             else:
+                pred, pred_u = self._predict(x_t, tb, condition, guidance_scale, un_cond)
+                noise = noise_fn(x_t)
+                noise2 = noise_fn(x_t) if ddim else None
                 o = sched.step(x_t, tb, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
-                               objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",))
+                               t_next=t_next, noise_ddim=noise2, objective=self.estimator_objective,
+                               clip_x0=self.clip_x0, want=("x_next",))
             x_t = o["x_next"]
         if self.latent_embedder is not None:
             x_t = self.latent_embedder.decode(x_t)

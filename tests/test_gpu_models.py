@@ -165,3 +165,27 @@ def test_use_ema_selects_the_averaged_weights():
     x, t, c = gs["x"].to(DEV), gs["t"].to(DEV), gs["cond"].to(DEV)
     pred, _ = pipe._predict(x, t, c, 1.0, None)
     assert_close(pred.cpu(), gs["y_cond"], what="EMA estimator output")
+
+
+def test_fused_head_step_equals_separate_calls():
+    """mf_unet_forward_step (scheduler update in the epilogue of the 1x1 head) == UNet.forward + scheduler.step."""
+    from medfusion_b200.models import GaussianNoiseScheduler
+    g = load_golden("unet_small.pt")
+    gs = load_golden("sched.pt")
+    m = make_unet(g["cfg"], DEV)
+    s = GaussianNoiseScheduler(**gs["sched"]).to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    x = g["x"].to(DEV)
+    t = torch.tensor([700, 700], device=DEV)
+    c = g["cond"].to(DEV)
+    n1, n2 = (torch.randn(2, 8, 32, 32, generator=gen).to(DEV) for _ in range(2))
+    pu, _ = m(x, t, None)
+    pc, _ = m(x, t, c)
+    ref = s.step(x, t, pc, pred_uncond=pu, guidance_scale=2.5, noise=n1, t_next=torch.tensor(350), noise_ddim=n2,
+                 objective="x_T", clip_x0=False, want=("x_prior", "x_0", "x_T", "x_next"))
+    got = m.forward_step(x, t, c, s, pred_uncond=pu, guidance_scale=2.5, noise=n1, t_next=torch.tensor(350),
+                         noise_ddim=n2, objective="x_T", clip_x0=False, want=("x_prior", "x_0", "x_T", "x_next"),
+                         want_pred=True)
+    assert torch.equal(got["pred"], pc)
+    for k in ("x_prior", "x_0", "x_T", "x_next"):
+        assert torch.equal(got[k], ref[k]), k
