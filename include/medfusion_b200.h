@@ -117,6 +117,8 @@ typedef struct {
   int objective_is_x0;
   int clip_x0;
   float* d_x_prior; float* d_x_0; float* d_x_T; float* d_x_next;   /* any may be NULL */
+  int uniform_t;                /* 1: all entries of d_t are equal (the sampling loop) -> the embedding MLP is evaluated
+                                   once per class instead of once per sample */
 } mf_step_args;
 int mf_unet_forward_step(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
                          int H, int W, void* d_workspace, size_t workspace_bytes, const mf_step_args* step,

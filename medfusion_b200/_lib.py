@@ -47,6 +47,7 @@ class StepArgs(ctypes.Structure):
         ("d_noise", c_void_p), ("d_t_next", c_void_p), ("d_noise_ddim", c_void_p),
         ("objective_is_x0", c_int), ("clip_x0", c_int),
         ("d_x_prior", c_void_p), ("d_x_0", c_void_p), ("d_x_T", c_void_p), ("d_x_next", c_void_p),
+        ("uniform_t", c_int),
     ]
 
 

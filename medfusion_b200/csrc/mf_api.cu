@@ -36,6 +36,8 @@ struct mf_unet : public EngineBase {
   const long long* io_cond = nullptr;
   float* io_y = nullptr;
   int n_launches = 0;
+  int emb_rows = 0;       // rows of the embedding tables actually computed this call (dedup mode)
+  bool has_attention = false;
 
   int init(const mf_unet_config& c);
   int build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s);
@@ -46,8 +48,10 @@ int mf_unet::init(const mf_unet_config& c) {
   cfg = c;
   MF_REQUIRE(c.depth >= 2 && c.depth <= MF_MAX_LEVELS, "depth must be in [2, 8]");
   MF_REQUIRE(c.num_res_blocks >= 1, "num_res_blocks >= 1");
-  for (int i = 0; i < c.depth; ++i)
+  for (int i = 0; i < c.depth; ++i) {
     MF_REQUIRE(c.attention[i] >= 0 && c.attention[i] <= 2, "attention must be 0 ('none'), 1 ('linear') or 2 ('spatial')");
+    has_attention = has_attention || c.attention[i] != 0;
+  }
   const int E = c.emb_dim;
   if (E > 0) {
     MF_REQUIRE(c.pos_emb_dim > 0 && c.pos_emb_dim % 64 == 0, "pos_emb_dim must be a multiple of 64");
@@ -163,6 +167,8 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
       push_op([this, l1](cudaStream_t st) {
         LinearDesc d = l1;
         d.t = io_t;
+        d.t_stride = 1;
+        if (io_emb_dedup) { d.B = emb_rows; d.t_stride = 0; }
         return linear_small(d, st);
       }, kOpOther, 2.0 * B * E * cfg.pos_emb_dim);
       LinearDesc l2{};
@@ -175,12 +181,20 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
           d.add_table = table;
           d.add_idx = io_cond;
         }
+        if (io_emb_dedup) {            // row r is class r (identity index); a single row when there is no condition
+          d.B = emb_rows;
+          d.add_idx = nullptr;
+        }
         return linear_small(d, st);
       }, kOpOther, 2.0 * B * E * E);
       LinearDesc l3{};
       l3.in_mode = 0; l3.in = semb.ptr; l3.W = loc_w.p; l3.bias = loc_b.p;
       l3.out = embT.ptr; l3.post = 0; l3.B = B; l3.J = emb_total; l3.K = E;
-      push_op([l3](cudaStream_t st) { return linear_small(l3, st); }, kOpOther, 2.0 * B * emb_total * E);
+      push_op([this, l3](cudaStream_t st) {
+        LinearDesc d = l3;
+        if (io_emb_dedup) d.B = emb_rows;
+        return linear_small(d, st);
+      }, kOpOther, 2.0 * B * emb_total * E);
     }
     free_tensor(h1);
     free_tensor(semb);
@@ -485,6 +499,19 @@ int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const in
   h->io_y = d_y;
   return h->run(s);
 }
+// All samples share the timestep (the sampling loop calls the estimator with t.expand(B)): the embedding MLP then
+// depends only on the class, so it is evaluated once per class (or once) instead of once per sample.
+static void set_emb_dedup(mf_unet* h, int uniform_t, const int64_t* d_cond, int B) {
+  h->io_emb_dedup = false;
+  h->io_emb_index = nullptr;
+  if (!uniform_t || h->cfg.emb_dim <= 0 || h->has_attention) return;
+  const bool cond = d_cond != nullptr && h->cfg.num_classes > 0;
+  const int rows = cond ? h->cfg.num_classes : 1;
+  if (rows > B) return;   // the plan's embedding buffers hold B rows
+  h->io_emb_dedup = true;
+  h->emb_rows = rows;
+  h->io_emb_index = cond ? reinterpret_cast<const long long*>(d_cond) : nullptr;
+}
 static void fill_step_desc(SchedStepDesc& d, const mf_step_args* a, const float* x_t, const int64_t* t, int B, int chw) {
   d = SchedStepDesc{};
   d.x_t = x_t; d.pred = nullptr; d.pred_uncond = a->d_pred_uncond; d.guidance = a->guidance_scale;
@@ -517,10 +544,12 @@ int mf_unet_forward_step(mf_unet* h, const float* d_x_t, const int64_t* d_t, con
   h->io_t = reinterpret_cast<const long long*>(d_t);
   h->io_cond = reinterpret_cast<const long long*>(d_cond);
   h->io_y = d_y;
+  set_emb_dedup(h, step->uniform_t, d_cond, B);
   fill_step_desc(h->io_step, step, d_x_t, d_t, B, h->cfg.out_ch * H * W);
   h->io_step_on = true;
   rc = h->run(s);
   h->io_step_on = false;
+  h->io_emb_dedup = false;
   return rc;
 }
 int mf_unet_profile(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B, int H,

@@ -430,7 +430,14 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     d.emb = emb; d.emb_stride = emb_stride;
     d.out = out.hptr(); d.out_plane = out.plane;
     d.N = raw.N; d.HW = raw.H * raw.W; d.C = raw.C; d.G = groups;
-    push_op([d](cudaStream_t s) { return gn_apply(d, s); }, kOpNorm);
+    push_op([this, d](cudaStream_t s) {
+      GnApplyDesc dd = d;
+      if (dd.emb != nullptr && io_emb_dedup) {   // deduplicated embedding rows: one per class (or a single row)
+        dd.emb_index = io_emb_index;
+        if (io_emb_index == nullptr) dd.emb_stride = 0;
+      }
+      return gn_apply(dd, s);
+    }, kOpNorm);
   }
   free_tensor(mr);
   return 0;

@@ -144,6 +144,9 @@ class EngineBase {
   // optional scheduler update fused into the narrow output head (set per call by the C ABI)
   SchedStepDesc io_step{};
   bool io_step_on = false;
+  // embedding rows deduplicated for this call (all samples share t): row index = class id, or one shared row
+  bool io_emb_dedup = false;
+  const long long* io_emb_index = nullptr;
 
   // ---- builder state (valid during build())
   bool dry = false;

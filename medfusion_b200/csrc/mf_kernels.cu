@@ -427,54 +427,65 @@ int gn_finalize(const float* partial, float* mean_rstd, int N, int chunks, int C
 
 // y = swish(gn(raw)) + residual (+ emb)   -> split planes
 //   reference: conv_blocks.py:184-192 (conv -> norm -> drop(p=0) -> act), :236-240 (+ residual), :362-363 (+= emb)
-__global__ void gn_apply_kernel(const GnApplyDesc d) {
+// Thread layout: a thread owns ONE channel quad for its whole life (gamma / beta / group index stay in registers) and
+// walks the pixels; 256 / (C/4) pixels per block iteration.  Pure streaming: 4 B raw + 4 B residual in, 4 B out per element.
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDesc d) {
   const int c4n = d.C / 4;
-  const long long total = static_cast<long long>(d.N) * d.HW * c4n;
+  const int tpp = c4n < 256 ? c4n : 256;          // threads per pixel
+  const int ppb = 256 / tpp;                      // pixels per block iteration
+  const int cq = threadIdx.x % tpp;
+  const int psub = threadIdx.x / tpp;
+  if (psub >= ppb) return;                        // C/4 does not divide 256: the remainder threads idle
   const int cpg = d.C / d.G;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c4n) * 4;
-    const long long pix = i / c4n;
-    const int n = static_cast<int>(pix / d.HW);
-    const long long off = pix * d.C + c;
-    float4 x;
-    if (d.raw_plane != 0) {
-      const __half* xh = reinterpret_cast<const __half*>(d.raw) + off;
-      x = ld_join4(xh, xh + d.raw_plane);
-    } else {
-      x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.raw) + off);
-    }
-    const float2 mr = *reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + c / cpg) * 2);
+  const long long npix = static_cast<long long>(d.N) * d.HW;
+  for (int c = cq * 4; c < d.C; c += tpp * 4) {   // one pass unless C > 1024
     const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
     const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + c));
-    float y[4] = {(x.x - mr.x) * mr.y * ga.x + be.x, (x.y - mr.x) * mr.y * ga.y + be.y,
-                  (x.z - mr.x) * mr.y * ga.z + be.z, (x.w - mr.x) * mr.y * ga.w + be.w};
-    if (d.act != 0) {
+    const int g = c / cpg;
+    for (long long pix = static_cast<long long>(blockIdx.x) * ppb + psub; pix < npix;
+         pix += static_cast<long long>(gridDim.x) * ppb) {
+      const int n = static_cast<int>(pix / d.HW);
+      const long long off = pix * d.C + c;
+      float4 x;
+      if (d.raw_plane != 0) {
+        const __half* xh = reinterpret_cast<const __half*>(d.raw) + off;
+        x = ld_join4(xh, xh + d.raw_plane);
+      } else {
+        x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.raw) + off);
+      }
+      const float2 mr = __ldg(reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + g) * 2));
+      float y[4] = {(x.x - mr.x) * mr.y * ga.x + be.x, (x.y - mr.x) * mr.y * ga.y + be.y,
+                    (x.z - mr.x) * mr.y * ga.z + be.z, (x.w - mr.x) * mr.y * ga.w + be.w};
+      if (d.act != 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
+        for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
+      }
+      if (d.res_kind == kResSplit) {
+        const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
+        const float4 r = ld_join4(rh, rh + d.res_plane);
+        y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+      } else if (d.res_kind == kResRaw) {
+        const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
+        y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+      }
+      if (d.emb != nullptr) {
+        const long long er = d.emb_index ? d.emb_index[n] : static_cast<long long>(n);
+        const float4 e = __ldg(reinterpret_cast<const float4*>(d.emb + er * d.emb_stride + c));
+        y[0] += e.x; y[1] += e.y; y[2] += e.z; y[3] += e.w;
+      }
+      st_split4(d.out + off, d.out + d.out_plane + off, make_float4(y[0], y[1], y[2], y[3]));
     }
-    if (d.res_kind == kResSplit) {
-      const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
-      const float4 r = ld_join4(rh, rh + d.res_plane);
-      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-    } else if (d.res_kind == kResRaw) {
-      const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
-      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-    }
-    if (d.emb != nullptr) {
-      const float4 e = *reinterpret_cast<const float4*>(d.emb + static_cast<long long>(n) * d.emb_stride + c);
-      y[0] += e.x; y[1] += e.y; y[2] += e.z; y[3] += e.w;
-    }
-    st_split4(d.out + off, d.out + d.out_plane + off, make_float4(y[0], y[1], y[2], y[3]));
   }
 }
 
 int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   MF_REQUIRE(d.C % 4 == 0 && d.C % d.G == 0 && (d.C / d.G) % 4 == 0, "gn_apply channel constraints");
   MF_REQUIRE(d.emb == nullptr || d.emb_stride % 4 == 0, "emb rows must be float4 aligned");
-  const long long total = static_cast<long long>(d.N) * d.HW * (d.C / 4);
-  if (total == 0) return 0;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+  const long long npix = static_cast<long long>(d.N) * d.HW;
+  if (npix == 0) return 0;
+  const int c4n = d.C / 4;
+  const int ppb = c4n < 256 ? 256 / c4n : 1;
+  const int blocks = static_cast<int>(std::min<long long>((npix + ppb - 1) / ppb, 148 * 16));
   gn_apply_kernel<<<blocks, 256, 0, s>>>(d);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
@@ -534,7 +545,7 @@ __global__ void linear_small_kernel(const LinearDesc d) {
       for (int i = 0; i < KPL; ++i) acc = fmaf(w[i], x[i * 32 + lane], acc);
     } else {
       // sinusoidal position embedding: cat(sin(t*f), cos(t*f)), f given by the host table
-      const float tf = static_cast<float>(d.t[b]);
+      const float tf = static_cast<float>(d.t[static_cast<long long>(b) * d.t_stride]);
       const int half = d.K / 2;
 #pragma unroll
       for (int i = 0; i < KPL; ++i) {
@@ -546,7 +557,7 @@ __global__ void linear_small_kernel(const LinearDesc d) {
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) {
       float v = acc + bj;
-      if (d.add_table != nullptr) v += d.add_table[d.add_idx[b] * d.J + j];
+      if (d.add_table != nullptr) v += d.add_table[(d.add_idx ? d.add_idx[b] : static_cast<long long>(b)) * d.J + j];
       if (d.post == 1) v = swish(v);
       d.out[static_cast<long long>(b) * d.J + j] = v;
       if (d.out2 != nullptr) d.out2[static_cast<long long>(b) * d.J + j] = swish(v);

@@ -55,7 +55,8 @@ struct GnApplyDesc {
   const float* mean_rstd;   // [N][G][2]
   const float* gamma; const float* beta;  // [C]
   const void* res; long long res_plane; int res_kind;   // split: __half planes, raw: float
-  const float* emb; int emb_stride;       // emb[n*emb_stride + c] or nullptr
+  const float* emb; int emb_stride;       // emb[row*emb_stride + c] or nullptr; row = emb_index ? emb_index[n] : n
+  const long long* emb_index;             // optional row indirection (deduplicated embeddings: one row per class)
   __half* out; long long out_plane;       // split planes
   int N, HW, C, G;
 };
@@ -70,9 +71,9 @@ int upsample2x_split(const __half* in, long long in_plane, __half* out, long lon
 //   in_mode 0: in is a float [B][K] matrix;  in_mode 1: in is built on the fly as sinusoidal(t[b]) with freqs[K/2]
 //   post 0: identity, 1: swish;  out2 (optional) receives swish(out)
 struct LinearDesc {
-  const float* in; const long long* t; const float* freqs; int in_mode;
+  const float* in; const long long* t; int t_stride; const float* freqs; int in_mode;  // t[b * t_stride]
   const float* W; const float* bias;
-  const float* add_table; const long long* add_idx;  // optional embedding-table add: add_table[add_idx[b]][j]
+  const float* add_table; const long long* add_idx;  // optional embedding-table add: add_table[add_idx ? add_idx[b] : b][j]
   float* out; float* out2; int post;
   int B, J, K;
 };

@@ -139,10 +139,13 @@ class UNet(EngineModule):
                                                ws_bytes, cuda_stream_ptr()), "mf_unet_forward")
 
     def forward_step(self, x_t, t, condition, scheduler, *, pred_uncond=None, guidance_scale=1.0, noise=None,
-                     t_next=None, noise_ddim=None, objective="x_T", clip_x0=True, want=("x_next",), want_pred=False):
+                     t_next=None, noise_ddim=None, objective="x_T", clip_x0=True, want=("x_next",), want_pred=False,
+                     uniform_t=False):
         """UNet.forward with `scheduler`'s reverse step fused into the output head's epilogue (mf_unet_forward_step).
 
-        Returns a dict with the requested tensors among x_prior, x_0, x_T, x_next (+ 'pred' if want_pred)."""
+        Returns a dict with the requested tensors among x_prior, x_0, x_T, x_next (+ 'pred' if want_pred).
+        uniform_t=True promises that all entries of t are equal (true in the sampling loop): the time/label embedding
+        MLP is then evaluated once per class instead of once per sample."""
         require_cuda(x_t, "UNet.forward_step(x_t)")
         self.sync_params()
         B, _, H, W = x_t.shape
@@ -163,7 +166,8 @@ class UNet(EngineModule):
 
         args = _lib.StepArgs(ctypes.pointer(tab), ptr(keep[0]), float(guidance_scale), ptr(keep[1]), ptr(t_next),
                              ptr(keep[2]), 1 if objective == "x_0" else 0, 1 if clip_x0 else 0,
-                             ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")))
+                             ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")),
+                             1 if uniform_t else 0)
         ws, ws_bytes = self._workspace(B, H, W)
         _lib.check(_lib.load().mf_unet_forward_step(self._h, x.data_ptr(), tt.data_ptr(), ptr(cc), ptr(pred), B, H, W, ws,
                                                     ws_bytes, ctypes.byref(args), cuda_stream_ptr()),

@@ -20,6 +20,51 @@ import torch.nn as nn
 from ..._engine import require_cuda
 
 
+class _StepGraph:
+    """One reverse-diffusion timestep captured as a CUDA graph (estimator pass(es) + noise draws + fused update).
+
+    Static buffers: x (updated in place by every replay), t [B], t_next [1], condition / un_cond.  The launch plan
+    of the estimator is built by the warm-up call, so the capture contains kernel launches only; the torch RNG draws
+    inside use the graph-safe generator offsets, so the noise stream continues exactly as in eager mode.
+    """
+
+    def __init__(self, pipe, est, x, condition, un_cond, guidance_scale, ddim, noise_fn):
+        self.x = x.clone()
+        B = x.shape[0]
+        self.t = torch.zeros(B, dtype=torch.int64, device=x.device)
+        self.t_next = torch.zeros(1, dtype=torch.int64, device=x.device)
+        self.cond = None if condition is None else condition.clone()
+        self.un_cond = None if un_cond is None else un_cond.clone()
+        cfg = (condition is not None) and (guidance_scale != 1.0)
+        sched = pipe.noise_scheduler
+
+        def body():
+            pred_u = est(self.x, self.t, condition=self.un_cond, self_cond=None)[0] if cfg else None
+            noise = noise_fn(self.x)
+            noise2 = noise_fn(self.x) if ddim else None
+            o = est.forward_step(self.x, self.t, self.cond, sched, pred_uncond=pred_u, guidance_scale=guidance_scale,
+                                 noise=noise, t_next=self.t_next if ddim else None, noise_ddim=noise2,
+                                 objective=pipe.estimator_objective, clip_x0=pipe.clip_x0, want=("x_next",),
+                                 uniform_t=True)
+            self.x.copy_(o["x_next"])
+
+        # warm-up on a side stream (builds the launch plan, primes allocations) without disturbing the noise stream
+        rng = torch.cuda.get_rng_state(x.device)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        torch.cuda.set_rng_state(rng, x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        torch.cuda.set_rng_state(rng, x.device)   # capture does not draw, but keep the contract explicit
+
+    def replay(self):
+        self.graph.replay()
+
+
 class _EMAWeights(nn.Module):
     """Holder with the reference's attribute name (`EMAModel.averaged_model`, utils/train_utils.py:33)."""
 
@@ -82,6 +127,8 @@ class DiffusionPipeline(nn.Module):
         self.estimate_variance = estimate_variance
         self.clip_x0 = clip_x0
         self.use_ema = use_ema
+        self.use_cuda_graph = True    # capture one timestep as a CUDA graph inside denoise() (medfusion_b200 extension)
+        self._step_graphs = {}
         if use_ema:
             # weight selection only (diffusion_pipeline.py:234-237): a second estimator holding the averaged weights under
             # the reference's key prefix `ema_model.averaged_model.*`; the EMA *update* is training-side (train_utils.py).
@@ -131,7 +178,9 @@ class DiffusionPipeline(nn.Module):
     @torch.no_grad()
     def denoise(self, x_t, steps=None, condition=None, use_ddim=True, **kwargs):
         """Reverse loop + latent decode (diffusion_pipeline.py:278-310)."""
-        noise_fn = kwargs.pop("_noise_fn", None) or self.noise_scheduler.x_final
+        custom_noise = kwargs.pop("_noise_fn", None)
+        graph_ok = kwargs.pop("_cuda_graph", self.use_cuda_graph)
+        noise_fn = custom_noise or self.noise_scheduler.x_final
         unknown = set(kwargs) - {"guidance_scale", "un_cond", "cold_diffusion"}
         if unknown:  # the reference forwards **kwargs to forward(), which raises TypeError on anything else
             raise TypeError(f"forward() got an unexpected keyword argument '{sorted(unknown)[0]}'")
@@ -153,6 +202,43 @@ class DiffusionPipeline(nn.Module):
         est = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
         fused = hasattr(est, "forward_step") and getattr(est, "out_ch", 99) <= 8 and not est.estimate_variance
         cfg = (condition is not None) and (guidance_scale != 1.0)
+        # CUDA-graph path: one captured timestep replayed `steps` times (a second capture without the DDIM re-noise
+        # for the last step).  Host-side noise injection (tests) cannot be captured -> eager loop below.
+        if fused and graph_ok and (custom_noise is None or getattr(custom_noise, "graph_safe", False)) and steps > 2:
+            def get_graph(ddim):
+                key = (id(est), tuple(x_t.shape), condition is not None, un_cond is not None, float(guidance_scale),
+                       ddim, self.estimator_objective, self.clip_x0, id(custom_noise))
+                g = self._step_graphs.get(key)
+                if g is None:
+                    if len(self._step_graphs) >= 4:
+                        self._step_graphs.clear()
+                    g = _StepGraph(self, est, x_t, condition, un_cond, guidance_scale, ddim, noise_fn)
+                    self._step_graphs[key] = g
+                if condition is not None:
+                    g.cond.copy_(condition)
+                if un_cond is not None:
+                    g.un_cond.copy_(un_cond)
+                return g
+
+            n_main = steps - 1 if use_ddim else steps        # the last DDIM step has no re-noise
+            g = get_graph(use_ddim)
+            g.x.copy_(x_t)
+            for i in range(n_main):
+                g.t.copy_(ts[i].expand(B))
+                if use_ddim:
+                    g.t_next.copy_(timesteps_array[steps - i - 2].reshape(1))
+                g.replay()
+            x_t = g.x
+            if use_ddim:
+                g2 = get_graph(False)
+                g2.x.copy_(x_t)
+                g2.t.copy_(ts[steps - 1].expand(B))
+                g2.replay()
+                x_t = g2.x
+            x_t = x_t.clone()
+            if self.latent_embedder is not None:
+                x_t = self.latent_embedder.decode(x_t)
+            return x_t
         for i in range(steps):
             t = ts[i]
             tb = t.expand(B)
@@ -168,7 +254,8 @@ class DiffusionPipeline(nn.Module):
                 # reference's order; their values do not depend on the estimator.
                 o = est.forward_step(x_t, tb, condition, sched, pred_uncond=pred_u, guidance_scale=guidance_scale,
                                      noise=noise, t_next=t_next, noise_ddim=noise2,
-                                     objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",))
+                                     objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",),
+                                     uniform_t=True)
             else:
                 pred, pred_u = self._predict(x_t, tb, condition, guidance_scale, un_cond)
                 noise = noise_fn(x_t)

@@ -25,6 +25,7 @@ def make_sharded_noise_fn(template: torch.Tensor, lo: int, hi: int):
     def noise_fn(_x_local):
         return torch.randn_like(template)[lo:hi].contiguous()
 
+    noise_fn.graph_safe = True   # pure device-side torch ops: may be captured into the per-timestep CUDA graph
     return noise_fn
 
 

@@ -189,3 +189,27 @@ def test_fused_head_step_equals_separate_calls():
     assert torch.equal(got["pred"], pc)
     for k in ("x_prior", "x_0", "x_T", "x_next"):
         assert torch.equal(got[k], ref[k]), k
+    # uniform_t: the embedding MLP is evaluated once per class instead of once per sample — same arithmetic, same bits
+    for cond in (c, None):
+        a = m.forward_step(x, t, cond, s, noise=n1, objective="x_T", clip_x0=False, want=("x_next",), want_pred=True)
+        b = m.forward_step(x, t, cond, s, noise=n1, objective="x_T", clip_x0=False, want=("x_next",), want_pred=True,
+                           uniform_t=True)
+        assert torch.equal(a["pred"], b["pred"]) and torch.equal(a["x_next"], b["x_next"])
+
+
+@pytest.mark.parametrize("use_ddim,cfg", [(True, False), (False, False), (True, True)])
+def test_cuda_graph_sampling_equals_eager(use_ddim, cfg):
+    """denoise() replays one captured timestep per step; with the same seed it must reproduce the eager loop bit for bit
+    (same kernels, same launch plan, same torch noise stream)."""
+    g = load_golden("sample_small.pt")
+    pipe = _make_pipe(g)
+    cond = torch.tensor([0, 1, 1], device=DEV) if cfg else None
+    kw = dict(steps=5, use_ddim=use_ddim)
+    if cfg:
+        kw["guidance_scale"] = 2.0
+    outs = []
+    for graph in (False, True, True):        # second graphed run reuses the cached capture
+        pipe.use_cuda_graph = graph
+        torch.manual_seed(99)
+        outs.append(pipe.sample(3, (8, 32, 32), condition=cond, **kw))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
