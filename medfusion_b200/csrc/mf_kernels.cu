@@ -665,7 +665,8 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const HeadDesc h, const Sc
     }
 #pragma unroll
     for (int o = 0; o < 8; ++o)
-      for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+      if (o < h.Cout)   // warp-uniform
+        for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
     if (lane < h.Cout) {
       float y = 0.f;
 #pragma unroll
