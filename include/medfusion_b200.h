@@ -55,6 +55,9 @@ int mf_set_fold_upsample(int enable);
 /* Cin < 64 stem convolutions (UNet in_conv, VAE inc_dec): 1 = tcgen05 path through a zero-padded 64-channel copy of the
  * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
 int mf_set_stem_on_tc(int enable);
+/* thread mapping of the GroupNorm-apply kernel (tuning knob): 0 flat grid-stride, 1 fixed channel quad per thread,
+ * 2 flat with one channel quad per thread */
+int mf_set_gn_variant(int v);
 
 /* scheduler tables: fp32[T] device arrays as registered by gaussian_scheduler.py:44-58 */
 typedef struct {
@@ -157,6 +160,10 @@ size_t mf_vae_workspace_bytes(mf_vae* h, int B, int H, int W);
 /* x[B,out_channels,H*2^(depth-1),W*2^(depth-1)] = decode(z[B,emb_channels,H,W]) */
 int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
                   size_t workspace_bytes, mf_stream_t stream);
+/* decode + the image post-processing of scripts/helpers/sample_dataset.py:47-50 fused into the output head:
+ * d_x_u8[B][H'][W'][out_channels] = uint8((clip(x,-1,1)+1)/2*255); d_x (fp32 NCHW) may be NULL. */
+int mf_vae_decode_u8(mf_vae* h, const float* d_z, float* d_x, uint8_t* d_x_u8, int B, int H, int W, void* d_workspace,
+                     size_t workspace_bytes, mf_stream_t stream);
 int mf_vae_profile(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
                    size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds, double* flops, int max_ops,
                    int* n_ops);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mf_set_stream_k": (c_int, [c_int]),
     "mf_set_fold_upsample": (c_int, [c_int]),
     "mf_set_stem_on_tc": (c_int, [c_int]),
+    "mf_set_gn_variant": (c_int, [c_int]),
     "mf_set_debias_eps": (c_int, [c_float]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),
@@ -84,6 +85,7 @@ SIGNATURES = {
     "mf_vae_set_param": (c_int, [_P, c_char_p, _P, POINTER(c_int64), c_int, _P]),
     "mf_vae_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_vae_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_vae_decode_u8": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "mf_vae_profile": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float), POINTER(c_int),
                                POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "mf_vae_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
@@ -140,6 +142,8 @@ def load():
         lib.mf_set_debias_eps(float(os.environ["MF_DEBIAS_EPS"]))
     if os.environ.get("MF_STREAM_K"):
         lib.mf_set_stream_k(int(os.environ["MF_STREAM_K"]))
+    if os.environ.get("MF_GN_VARIANT"):
+        lib.mf_set_gn_variant(int(os.environ["MF_GN_VARIANT"]))
     if os.environ.get("MF_BLOCK_N"):
         lib.mf_set_block_n(int(os.environ["MF_BLOCK_N"]))
     if os.environ.get("MF_DRAIN_INTERVAL"):

@@ -416,6 +416,10 @@ int mf_set_debias_eps(float eps_per_kblock) {
   mf::g_debias_eps_per_kblock = eps_per_kblock;
   return 0;
 }
+int mf_set_gn_variant(int v) {
+  mf::g_gn_variant = v;
+  return 0;
+}
 int mf_set_stem_on_tc(int enable) {
   mf::g_stem_on_tc = enable ? 1 : 0;
   return 0;
@@ -611,6 +615,20 @@ int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, 
   h->io_z = d_z;
   h->io_x = d_x;
   return h->run(s);
+}
+int mf_vae_decode_u8(mf_vae* h, const float* d_z, float* d_x, uint8_t* d_x_u8, int B, int H, int W, void* d_workspace,
+                     size_t workspace_bytes, mf_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MF_REQUIRE(d_z && d_x_u8 && B > 0 && H > 0 && W > 0, "bad arguments");
+  MF_REQUIRE(h->cfg.out_channels <= 8 && h->cfg.hid_chs[0] % 64 == 0, "uint8 output needs the narrow 1x1 head");
+  int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_z = d_z;
+  h->io_x = d_x;            // may be NULL: only the uint8 image is written
+  h->io_out_u8 = d_x_u8;
+  rc = h->run(s);
+  h->io_out_u8 = nullptr;
+  return rc;
 }
 int mf_vae_profile(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
                    size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds, double* flops, int max_ops,

@@ -385,6 +385,7 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
     push_op([this, hd, dst](cudaStream_t s) {
       HeadDesc h2 = hd;
       h2.out = *dst;
+      h2.out_u8 = io_out_u8;
       return head1x1(h2, io_step_on ? &io_step : nullptr, s);
     }, kOpConvSimt, 2.0 * in0.N * in0.H * in0.W * L.Cout * static_cast<double>(L.Cin));
     return 0;

@@ -145,6 +145,7 @@ class EngineBase {
   SchedStepDesc io_step{};
   bool io_step_on = false;
   // embedding rows deduplicated for this call (all samples share t): row index = class id, or one shared row
+  unsigned char* io_out_u8 = nullptr;   // optional uint8 HWC copy of the narrow head's output (VAE images)
   bool io_emb_dedup = false;
   const long long* io_emb_index = nullptr;
 

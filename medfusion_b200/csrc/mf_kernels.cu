@@ -478,6 +478,50 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDesc d) {
   }
 }
 
+// flat variant: every thread-iteration handles one channel quad of one pixel (index math per element, maximal parallelism)
+__global__ void __launch_bounds__(256) gn_apply_flat_kernel(const GnApplyDesc d) {
+  const int c4n = d.C / 4;
+  const unsigned total = static_cast<unsigned>(static_cast<long long>(d.N) * d.HW * c4n);
+  const int cpg = d.C / d.G;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / c4n;
+    const int c = static_cast<int>(i - pix * c4n) * 4;
+    const int n = static_cast<int>(pix / d.HW);
+    const long long off = static_cast<long long>(pix) * d.C + c;
+    float4 x;
+    if (d.raw_plane != 0) {
+      const __half* xh = reinterpret_cast<const __half*>(d.raw) + off;
+      x = ld_join4(xh, xh + d.raw_plane);
+    } else {
+      x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.raw) + off);
+    }
+    const float2 mr = __ldg(reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + c / cpg) * 2));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(d.beta + c));
+    float y[4] = {(x.x - mr.x) * mr.y * ga.x + be.x, (x.y - mr.x) * mr.y * ga.y + be.y,
+                  (x.z - mr.x) * mr.y * ga.z + be.z, (x.w - mr.x) * mr.y * ga.w + be.w};
+    if (d.act != 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = swish(y[j]);
+    }
+    if (d.res_kind == kResSplit) {
+      const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
+      const float4 r = ld_join4(rh, rh + d.res_plane);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+    } else if (d.res_kind == kResRaw) {
+      const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+    }
+    if (d.emb != nullptr) {
+      const long long er = d.emb_index ? d.emb_index[n] : static_cast<long long>(n);
+      const float4 e = __ldg(reinterpret_cast<const float4*>(d.emb + er * d.emb_stride + c));
+      y[0] += e.x; y[1] += e.y; y[2] += e.z; y[3] += e.w;
+    }
+    st_split4(d.out + off, d.out + d.out_plane + off, make_float4(y[0], y[1], y[2], y[3]));
+  }
+}
+
+int g_gn_variant = 0;
 int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   MF_REQUIRE(d.C % 4 == 0 && d.C % d.G == 0 && (d.C / d.G) % 4 == 0, "gn_apply channel constraints");
   MF_REQUIRE(d.emb == nullptr || d.emb_stride % 4 == 0, "emb rows must be float4 aligned");
@@ -485,8 +529,16 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   if (npix == 0) return 0;
   const int c4n = d.C / 4;
   const int ppb = c4n < 256 ? 256 / c4n : 1;
-  const int blocks = static_cast<int>(std::min<long long>((npix + ppb - 1) / ppb, 148 * 16));
-  gn_apply_kernel<<<blocks, 256, 0, s>>>(d);
+  const long long total = npix * c4n;
+  if (g_gn_variant == 1 || total >= (1LL << 32)) {
+    const int blocks = static_cast<int>(std::min<long long>((npix + ppb - 1) / ppb, 148 * 16));
+    gn_apply_kernel<<<blocks, 256, 0, s>>>(d);
+  } else if (g_gn_variant == 2) {
+    gn_apply_flat_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(d);   // one quad per thread
+  } else {
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+    gn_apply_flat_kernel<<<blocks, 256, 0, s>>>(d);
+  }
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -676,6 +728,12 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const HeadDesc h, const Sc
       const int n = static_cast<int>(pix / h.HW);
       const long long i = (static_cast<long long>(n) * h.Cout + lane) * h.HW + (pix - static_cast<long long>(n) * h.HW);
       if (h.out != nullptr) h.out[i] = y;
+      if (h.out_u8 != nullptr) {
+        // scripts/helpers/sample_dataset.py:47-50: clip(-1,1) -> (x+1)/2*255 -> HWC -> astype(uint8) (truncation)
+        const float c01 = fminf(fmaxf(y, -1.f), 1.f);
+        const float v255 = __fmul_rn(__fmul_rn(__fadd_rn(c01, 1.f), 0.5f), 255.f);
+        h.out_u8[pix * h.Cout + lane] = static_cast<unsigned char>(v255);
+      }
       if (h.fuse_step) sched_element(sd, i, n, y);
     }
   }

@@ -61,6 +61,7 @@ struct GnApplyDesc {
   int N, HW, C, G;
 };
 int gn_apply(const GnApplyDesc& d, cudaStream_t s);
+extern int g_gn_variant;  // 0: flat grid-stride (default), 1: fixed channel quad per thread, 2: flat, one quad per thread
 
 // nearest x2 upsample of a split tensor (reference: conv_blocks.py:123-125, F.interpolate nearest-exact)
 int upsample2x_split(const __half* in, long long in_plane, __half* out, long long out_plane, int N, int H, int W, int C,
@@ -103,6 +104,7 @@ struct HeadDesc {
   const __half* in; long long in_plane;  // split [N][HW][C]
   const float* w; const float* bias;     // [Cout][C] (reference OIHW layout of a 1x1 conv), [Cout]
   float* out;                            // NCHW [N][Cout][HW] or nullptr (only the fused step outputs are wanted)
+  unsigned char* out_u8;                 // optional NHWC uint8 image [N][HW][Cout]: clip(-1,1) -> (x+1)/2*255 -> truncate
   int N, HW, C, Cout;
   int fuse_step;
 };

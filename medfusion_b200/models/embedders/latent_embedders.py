@@ -106,6 +106,22 @@ class VAE(EngineModule):
                                              cuda_stream_ptr()), "mf_vae_decode")
         return x
 
+    def decode_uint8(self, z, also_float=False):
+        """decode + `clip(-1,1) -> (x+1)/2*255 -> HWC -> uint8` (scripts/helpers/sample_dataset.py:47-50) fused into the
+        output head: returns uint8 [B, H, W, C] (and the fp32 NCHW images too if also_float)."""
+        require_cuda(z, "VAE.decode_uint8(z)")
+        self.sync_params()
+        B, _, H, W = z.shape
+        zc = z.contiguous().float()
+        Ho, Wo = H * self.up_factor, W * self.up_factor
+        img = torch.empty((B, Ho, Wo, self.out_channels), device=z.device, dtype=torch.uint8)
+        x = torch.empty((B, self.out_channels, Ho, Wo), device=z.device, dtype=torch.float32) if also_float else None
+        ws, ws_bytes = self._workspace(B, H, W)
+        _lib.check(_lib.load().mf_vae_decode_u8(self._h, zc.data_ptr(), None if x is None else x.data_ptr(),
+                                                img.data_ptr(), B, H, W, ws, ws_bytes, cuda_stream_ptr()),
+                   "mf_vae_decode_u8")
+        return (img, x) if also_float else img
+
     def profile(self, z):
         """Per-launch device times of one decode: list of (ms, kind, algorithmic_flops)."""
         self.sync_params()

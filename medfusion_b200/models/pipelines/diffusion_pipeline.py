@@ -221,7 +221,15 @@ class DiffusionPipeline(nn.Module):
                 return g
 
             n_main = steps - 1 if use_ddim else steps        # the last DDIM step has no re-noise
-            g = get_graph(use_ddim)
+            try:
+                g = get_graph(use_ddim)
+                g2 = get_graph(False) if use_ddim else None
+            except RuntimeError as exc:                      # capture refused (e.g. an outer capture is active):
+                import warnings                              # same kernels, just launched one by one
+                warnings.warn(f"medfusion_b200: CUDA-graph capture of the timestep failed ({exc}); running eagerly")
+                self.use_cuda_graph = False
+                return self.denoise(x_t, steps=steps if use_ddim else steps, condition=condition, use_ddim=use_ddim,
+                                    _noise_fn=custom_noise, _cuda_graph=False, **kwargs)
             g.x.copy_(x_t)
             for i in range(n_main):
                 g.t.copy_(ts[i].expand(B))
@@ -230,7 +238,6 @@ class DiffusionPipeline(nn.Module):
                 g.replay()
             x_t = g.x
             if use_ddim:
-                g2 = get_graph(False)
                 g2.x.copy_(x_t)
                 g2.t.copy_(ts[steps - 1].expand(B))
                 g2.replay()

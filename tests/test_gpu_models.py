@@ -213,3 +213,48 @@ def test_cuda_graph_sampling_equals_eager(use_ddim, cfg):
         torch.manual_seed(99)
         outs.append(pipe.sample(3, (8, 32, 32), condition=cond, **kw))
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+def test_config4_shapes_attention_at_64x64_latent_vs_oracle():
+    """BASELINE.json configs[3]: 8x64x64 latent, canonical widths, use_attention=['none','none','none','spatial']
+    (6 SpatialTransformer sites, 256 tokens, d = 128 / 64) — one forward at B=1 against the CPU oracle."""
+    cfg = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
+               strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
+               cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False, use_res_block=True,
+               use_attention=["none", "none", "none", "spatial"])
+    m = make_unet(cfg, DEV)
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 8, 64, 64, generator=gen)
+    t = torch.tensor([321])
+    c = torch.tensor([1])
+    y, _ = m(x.to(DEV), t.to(DEV), c.to(DEV))
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.unet_forward(sd, unet_oracle_cfg(cfg), x, t, c)
+    assert_close(y.cpu(), ref, what="config-4 UNet (attention, 64x64 latent)")
+
+
+def test_vae_decode_512_vs_oracle():
+    """configs[3] decode side: 8x64x64 latent -> 3x512x512."""
+    g = load_golden("vae_canonical.pt")
+    m = make_vae(_vae_cfg(g["cfg"]), DEV)
+    z = torch.randn(1, 8, 64, 64, generator=torch.Generator().manual_seed(6))
+    x = m.decode(z.to(DEV))
+    assert x.shape == (1, 3, 512, 512)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.vae_decode(sd, vae_oracle_cfg(g["cfg"]), z)
+    assert_close(x.cpu(), ref, what="VAE.decode 512x512")
+
+
+def test_decode_uint8_matches_the_dataset_script_conversion():
+    """scripts/helpers/sample_dataset.py:47-50: clip(-1,1), (x+1)/2*255, moveaxis -> HWC, astype(uint8)."""
+    import numpy as np
+    g = load_golden("vae_canonical.pt")
+    m = make_vae(_vae_cfg(g["cfg"]), DEV)
+    z = (torch.randn(2, 8, 16, 16, generator=torch.Generator().manual_seed(2)) * 0.3).to(DEV)
+    img, x = m.decode_uint8(z, also_float=True)
+    assert torch.equal(x, m.decode(z))
+    ref = x.cpu().numpy()
+    ref = np.moveaxis(((ref.clip(-1, 1) + 1) / 2 * 255), 1, -1).astype(np.uint8)
+    assert img.shape == (2, 128, 128, 3) and np.array_equal(img.cpu().numpy(), ref)
