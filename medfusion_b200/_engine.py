@@ -83,16 +83,26 @@ class EngineModule(nn.Module):
     def _after_param_sync(self, stream):
         pass
 
-    def _workspace(self, B, H, W):
+    _WS_KEEP = 3   # workspaces kept per module (alternating batch sizes, e.g. the ragged tail of a chunked job)
+
+    def _workspace_tensor(self, B, H, W):
+        """Caller-owned scratch for one (B,H,W) plan.  A few recent shapes are kept so that alternating batch sizes
+        return to the SAME address (the engine then rebuilds an identical plan, and CUDA graphs captured against it
+        stay valid); graph holders additionally keep their tensor alive themselves."""
         key = (B, H, W, torch.cuda.current_device())
-        ws = self._ws.get(key)
+        ws = self._ws.pop(key, None)
         if ws is None:
             nbytes = getattr(_lib.load(), f"{self._prefix}_workspace_bytes")(self._h, B, H, W)
             if nbytes == 0:
                 _lib.check(2, "workspace_bytes")
-            self._ws.clear()  # one live plan per module: the engine caches a single (B,H,W,workspace) plan
+            while len(self._ws) >= self._WS_KEEP:
+                self._ws.pop(next(iter(self._ws)))
             ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
-            self._ws[key] = ws
+        self._ws[key] = ws   # most recently used last
+        return ws
+
+    def _workspace(self, B, H, W):
+        ws = self._workspace_tensor(B, H, W)
         off = (-ws.data_ptr()) % 1024
         return ws.data_ptr() + off, ws.numel() - off
 

@@ -7,7 +7,7 @@
 
 namespace mf {
 
-int g_default_drain_interval = 2;
+int g_default_drain_interval = 3;
 int g_default_cta_group = 0;
 int g_default_block_n = 0;    // 0 = auto
 int g_stream_k = 1;           // persistent stream-K schedule (0: one tile per CTA group)

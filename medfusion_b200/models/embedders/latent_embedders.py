@@ -12,11 +12,12 @@ import torch
 
 from ... import _lib
 from ..._engine import EngineModule, cuda_stream_ptr, require_cuda
+from ...checkpoint import CheckpointMixin
 
 _ENCODER_SIDE_PREFIXES = ("inc.", "encoders.", "out_enc.", "outc_ver.", "perceiver.", "loss_fct.", "quantizer.")
 
 
-class VAE(EngineModule):
+class VAE(CheckpointMixin, EngineModule):
     _prefix = "mf_vae"
 
     def __init__(
@@ -78,17 +79,6 @@ class VAE(EngineModule):
     def load_state_dict(self, state_dict, strict=True, **kw):
         own = {k: v for k, v in state_dict.items() if not k.startswith(_ENCODER_SIDE_PREFIXES)}
         return super().load_state_dict(own, strict=strict, **kw)
-
-    @classmethod
-    def load_from_checkpoint(cls, path, map_location=None, **overrides):
-        """Lightning-style checkpoint: {'state_dict': ..., 'hyper_parameters': {...}} (model_base.py:68-85)."""
-        ckpt = torch.load(path, map_location=map_location or "cpu", weights_only=False)
-        hp = dict(ckpt.get("hyper_parameters", {}))
-        hp.update(overrides)
-        accepted = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
-        model = cls(**{k: v for k, v in hp.items() if k in accepted})
-        model.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
-        return model
 
     # --- hot path -------------------------------------------------------------------------------
     def decode(self, z):

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from ..._engine import require_cuda
+from ...checkpoint import CheckpointMixin
 
 
 class _StepGraph:
@@ -59,6 +60,10 @@ class _StepGraph:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
+        # the captured launches point into the estimator's workspace for this shape and at its prepared weights:
+        # keep the former alive with the graph, remember the version of the latter
+        self._workspace = est._workspace_tensor(B, x.shape[2], x.shape[3])
+        self.param_sig = est._synced_sig
         torch.cuda.set_rng_state(rng, x.device)   # capture does not draw, but keep the contract explicit
 
     def replay(self):
@@ -75,7 +80,7 @@ class _EMAWeights(nn.Module):
             p.requires_grad = False
 
 
-class DiffusionPipeline(nn.Module):
+class DiffusionPipeline(CheckpointMixin, nn.Module):
     def __init__(
         self,
         noise_scheduler,
@@ -138,18 +143,17 @@ class DiffusionPipeline(nn.Module):
     def device(self):
         return self.noise_scheduler.betas.device
 
-    @classmethod
-    def load_from_checkpoint(cls, path, map_location=None, **overrides):
-        ckpt = torch.load(path, map_location=map_location or "cpu", weights_only=False)
-        hp = dict(ckpt.get("hyper_parameters", {}))
-        hp.update(overrides)
-        accepted = cls.__init__.__code__.co_varnames[1:cls.__init__.__code__.co_argcount]
-        model = cls(**{k: v for k, v in hp.items() if k in accepted})
-        sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
-        drop = ("loss_fct.",) if model.use_ema else ("ema_model.", "loss_fct.")
-        sd = {k: v for k, v in sd.items() if not k.startswith(drop)}
-        model.load_state_dict(sd)
-        return model
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts the reference pipeline's full state_dict (model_base.py:77-83 / Lightning): training-side entries
+        (`loss_fct.*`, the VAE's encoder / discriminator / LPIPS tensors, `ema_model.*` when use_ema is off) are not
+        part of the sampling path and are skipped; everything on the path must match exactly when strict."""
+        from ..embedders.latent_embedders import _ENCODER_SIDE_PREFIXES
+        drop = ("loss_fct.",) + (() if self.use_ema else ("ema_model.",))
+        drop += tuple("latent_embedder." + p for p in _ENCODER_SIDE_PREFIXES)
+        if self.latent_embedder is None:
+            drop += ("latent_embedder.",)
+        own = {k: v for k, v in state_dict.items() if not k.startswith(drop)}
+        return super().load_state_dict(own, strict=strict, **kw)
 
     # ---------------------------------------------------------------------------------------------
     def _predict(self, x_t, t, condition, guidance_scale, un_cond):
@@ -180,6 +184,7 @@ class DiffusionPipeline(nn.Module):
         """Reverse loop + latent decode (diffusion_pipeline.py:278-310)."""
         custom_noise = kwargs.pop("_noise_fn", None)
         graph_ok = kwargs.pop("_cuda_graph", self.use_cuda_graph)
+        as_uint8 = kwargs.pop("_uint8", False)
         noise_fn = custom_noise or self.noise_scheduler.x_final
         unknown = set(kwargs) - {"guidance_scale", "un_cond", "cold_diffusion"}
         if unknown:  # the reference forwards **kwargs to forward(), which raises TypeError on anything else
@@ -209,6 +214,9 @@ class DiffusionPipeline(nn.Module):
                 key = (id(est), tuple(x_t.shape), condition is not None, un_cond is not None, float(guidance_scale),
                        ddim, self.estimator_objective, self.clip_x0, id(custom_noise))
                 g = self._step_graphs.get(key)
+                est.sync_params()
+                if g is not None and g.param_sig != est._synced_sig:   # weights changed since the capture
+                    g = None
                 if g is None:
                     if len(self._step_graphs) >= 4:
                         self._step_graphs.clear()
@@ -229,7 +237,7 @@ class DiffusionPipeline(nn.Module):
                 warnings.warn(f"medfusion_b200: CUDA-graph capture of the timestep failed ({exc}); running eagerly")
                 self.use_cuda_graph = False
                 return self.denoise(x_t, steps=steps if use_ddim else steps, condition=condition, use_ddim=use_ddim,
-                                    _noise_fn=custom_noise, _cuda_graph=False, **kwargs)
+                                    _noise_fn=custom_noise, _cuda_graph=False, _uint8=as_uint8, **kwargs)
             g.x.copy_(x_t)
             for i in range(n_main):
                 g.t.copy_(ts[i].expand(B))
@@ -242,10 +250,7 @@ class DiffusionPipeline(nn.Module):
                 g2.t.copy_(ts[steps - 1].expand(B))
                 g2.replay()
                 x_t = g2.x
-            x_t = x_t.clone()
-            if self.latent_embedder is not None:
-                x_t = self.latent_embedder.decode(x_t)
-            return x_t
+            return self._decode(x_t.clone(), as_uint8)
         for i in range(steps):
             t = ts[i]
             tb = t.expand(B)
@@ -271,6 +276,13 @@ class DiffusionPipeline(nn.Module):
                                t_next=t_next, noise_ddim=noise2, objective=self.estimator_objective,
                                clip_x0=self.clip_x0, want=("x_next",))
             x_t = o["x_next"]
+        return self._decode(x_t, as_uint8)
+
+    def _decode(self, x_t, as_uint8=False):
+        if as_uint8:
+            if self.latent_embedder is None or not hasattr(self.latent_embedder, "decode_uint8"):
+                raise RuntimeError("sample_uint8 needs a latent embedder with decode_uint8 (medfusion_b200 VAE)")
+            return self.latent_embedder.decode_uint8(x_t)
         if self.latent_embedder is not None:
             x_t = self.latent_embedder.decode(x_t)
         return x_t
@@ -289,6 +301,15 @@ class DiffusionPipeline(nn.Module):
             return sharded_sample(self, template, condition, **kwargs)
         x_T = self.noise_scheduler.x_final(template)
         return self.denoise(x_T, condition=condition, **kwargs)
+
+    @torch.no_grad()
+    def sample_uint8(self, num_samples, img_size, condition=None, **kwargs):
+        """sample() with the `clip(-1,1) -> (x+1)/2*255 -> HWC -> uint8` conversion of the bulk generator
+        (scripts/helpers/sample_dataset.py:47-50) fused into the decoder's output head: uint8 [B, H, W, C] on device.
+        Same noise stream as sample() (medfusion_b200 extension; used by medfusion_b200.sample_dataset)."""
+        template = torch.zeros((num_samples, *img_size), device=self.device)
+        x_T = self.noise_scheduler.x_final(template)
+        return self.denoise(x_T, condition=condition, _uint8=True, **kwargs)
 
     def interpolate(self, *a, **k):
         raise NotImplementedError("interpolate() needs the forward diffusion (training side); out of scope")

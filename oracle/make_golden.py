@@ -155,6 +155,48 @@ def sample_fixture():
                os.path.join(OUT, "sample_small.pt"))
 
 
+def ckpt_fixture():
+    """Skeleton of the two Lightning checkpoints the reference's training scripts write (model_base.py:11-14 →
+    `save_hyperparameters()`; scripts/train_diffusion.py:117-132, scripts/train_latent_embedder_2d.py:68-90):
+    the *pickled* `hyper_parameters` (class objects by qualified reference name, incl. training-side classes that do
+    not exist at sampling time) and the state_dict key/shape lists.  Weights are not stored (tests rebuild them from
+    medfusion_b200.synthetic per key); scheduler buffers are (they are tiny and computed, not learned)."""
+    import lpips
+    vae_hp = dict(in_channels=3, out_channels=3, spatial_dims=2, emb_channels=8, hid_chs=[64, 128], kernel_sizes=[3, 3],
+                  strides=[1, 2], norm_name=("GROUP", {"num_groups": 8, "affine": True}), act_name=("Swish", {}),
+                  dropout=None, use_res_block=True, deep_supervision=False, learnable_interpolation=True,
+                  use_attention="none", embedding_loss_weight=1e-6, perceiver=lpips.LPIPS, perceiver_kwargs={},
+                  perceptual_loss_weight=1.0, optimizer=torch.optim.Adam, optimizer_kwargs={"lr": 1e-4},
+                  lr_scheduler=None, lr_scheduler_kwargs={}, loss=torch.nn.L1Loss, loss_kwargs={"reduction": "none"},
+                  sample_every_n_steps=1000)
+    vae = VAE(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in vae_hp.items()})
+    pipe_hp = dict(noise_scheduler=GaussianNoiseScheduler, noise_estimator=UNet, latent_embedder=VAE,
+                   noise_scheduler_kwargs=dict(SCHED),
+                   noise_estimator_kwargs=dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder,
+                                               **fresh(UNET_SMALL)),
+                   latent_embedder_checkpoint="runs/2022_12_12_133315_chest_vaegan/last_vae.ckpt",
+                   estimator_objective="x_T", estimate_variance=False, use_self_conditioning=False,
+                   classifier_free_guidance_dropout=0.5, num_samples=4, do_input_centering=False, clip_x0=False,
+                   use_ema=False, ema_kwargs={}, optimizer=torch.optim.AdamW, optimizer_kwargs={"lr": 1e-4},
+                   lr_scheduler=None, lr_scheduler_kwargs={}, loss=torch.nn.L1Loss, loss_kwargs={},
+                   sample_every_n_steps=1000)
+    kw = {k: v for k, v in pipe_hp.items() if k not in ("latent_embedder", "latent_embedder_checkpoint")}
+    kw["noise_estimator_kwargs"] = dict(kw["noise_estimator_kwargs"])
+    pipe = DiffusionPipeline(latent_embedder=None, **kw)
+    pipe.latent_embedder = vae
+
+    def keys(m):
+        return [(k, tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()]
+
+    lightning_extras = {"epoch": 3, "global_step": 1234, "pytorch-lightning_version": "1.8.6", "callbacks": {},
+                        "optimizer_states": [], "lr_schedulers": []}
+    torch.save(dict(vae=dict(hyper_parameters=vae_hp, keys=keys(vae), **lightning_extras),
+                    pipeline=dict(hyper_parameters=pipe_hp, keys=keys(pipe), **lightning_extras),
+                    sched_buffers={k: v.clone() for k, v in pipe.noise_scheduler.state_dict().items()}),
+               os.path.join(OUT, "ckpt_skeleton.pt"))
+    print("ckpt skeleton:", len(keys(vae)), "vae keys,", len(keys(pipe)), "pipeline keys")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     unet_fixture("unet_small.pt", UNET_SMALL, 1)
@@ -163,5 +205,6 @@ if __name__ == "__main__":
     vae_fixture()
     sched_fixture()
     sample_fixture()
+    ckpt_fixture()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
