@@ -55,9 +55,13 @@ int mf_set_fold_upsample(int enable);
 /* Cin < 64 stem convolutions (UNet in_conv, VAE inc_dec): 1 = tcgen05 path through a zero-padded 64-channel copy of the
  * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
 int mf_set_stem_on_tc(int enable);
-/* thread mapping of the GroupNorm-apply kernel (tuning knob): 0 flat grid-stride, 1 fixed channel quad per thread,
- * 2 flat with one channel quad per thread */
+/* GroupNorm-apply kernel used by the engine plans (tuning knob): 3 (default) finalises the statistics inside the apply
+ * kernel (one launch per GroupNorm, 8 channels per thread); 0 / 1 / 2 keep a separate finalize launch with a flat
+ * grid-stride / fixed channel quad per thread / one channel quad per thread mapping.  Takes effect at the next plan build. */
 int mf_set_gn_variant(int v);
+/* 1 (default): conv_tc and the fused GroupNorm-apply kernel are launched with programmatic stream serialization
+ * (griddepcontrol): a kernel's set-up overlaps the tail of its predecessor, also inside captured CUDA graphs. */
+int mf_set_pdl(int enable);
 
 /* scheduler tables: fp32[T] device arrays as registered by gaussian_scheduler.py:44-58 */
 typedef struct {

@@ -60,6 +60,7 @@ SIGNATURES = {
     "mf_set_cta_group": (c_int, [c_int]),
     "mf_set_block_n": (c_int, [c_int]),
     "mf_set_stream_k": (c_int, [c_int]),
+    "mf_set_pdl": (c_int, [c_int]),
     "mf_set_fold_upsample": (c_int, [c_int]),
     "mf_set_stem_on_tc": (c_int, [c_int]),
     "mf_set_gn_variant": (c_int, [c_int]),
@@ -140,6 +141,8 @@ def load():
         lib.mf_set_fold_upsample(int(os.environ["MF_FOLD_UPSAMPLE"]))
     if os.environ.get("MF_DEBIAS_EPS"):
         lib.mf_set_debias_eps(float(os.environ["MF_DEBIAS_EPS"]))
+    if os.environ.get("MF_PDL"):
+        lib.mf_set_pdl(int(os.environ["MF_PDL"]))
     if os.environ.get("MF_STREAM_K"):
         lib.mf_set_stream_k(int(os.environ["MF_STREAM_K"]))
     if os.environ.get("MF_GN_VARIANT"):

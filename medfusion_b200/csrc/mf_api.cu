@@ -416,6 +416,10 @@ int mf_set_debias_eps(float eps_per_kblock) {
   mf::g_debias_eps_per_kblock = eps_per_kblock;
   return 0;
 }
+int mf_set_pdl(int enable) {
+  mf::g_pdl = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_gn_variant(int v) {
   mf::g_gn_variant = v;
   return 0;

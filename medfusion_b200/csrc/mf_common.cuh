@@ -52,6 +52,15 @@ __device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
   lo = __float2half_rn(fminf(fmaxf(x - __half2float(hi), -65504.f), 65504.f));  // only clamps when hi saturated
 }
+// two values at once: packed conversions (cvt.rn.f16x2.f32), same results as split16 on each
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(ac, bc);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(fminf(fmaxf(a - hf.x, -65504.f), 65504.f), fminf(fmaxf(b - hf.y, -65504.f), 65504.f));
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ float join16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 // four consecutive channels: 8-byte vector accesses on both planes
 __device__ __forceinline__ float4 ld_join4(const __half* hi, const __half* lo) {
@@ -74,6 +83,10 @@ __device__ __forceinline__ void st_split4(__half* hi, __half* lo, float4 v) {
   *reinterpret_cast<uint2*>(hi) = uh;
   *reinterpret_cast<uint2*>(lo) = ul;
 }
+
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -58,6 +58,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   constexpr int CPW = Cfg::kColsPerWarp;
   constexpr int NB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
+  // Programmatic dependent launch: let the next kernel of the stream be scheduled as this one's CTAs retire (it parks
+  // at its own griddepcontrol.wait until this grid has completed), and run our own set-up — barrier init, TMEM
+  // allocation, cluster handshake — while the previous kernel drains.  Both are no-ops without the launch attribute.
+  pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);  // [kStages] TMA -> MMA (leader CTA's are the live ones)
@@ -122,6 +126,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched only shared memory / TMEM; global reads and writes start below
 
   // Register re-partitioning (setmaxnreg): the TMA / MMA warpgroup needs a handful of registers, the two drain
   // warpgroups hold 128 fp32 running sums per thread.  384 threads x 168 = 128 x 72 + 256 x 216.
@@ -691,13 +696,15 @@ static int launch_t(const ConvTcPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(kTcThreads, 1, 1);
   cfg.dynamicSmemBytes = TcCfg<BLOCK_N, CG>::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   MF_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG>, plan.maps, plan.p));
   return 0;
 }

@@ -416,10 +416,13 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     const float* part = stats.ptr;
     float* mrp = mr.ptr;
     const int N = raw.N, C = raw.C, HW = raw.H * raw.W;
-    push_op([part, mrp, N, chunks, C, groups, HW](cudaStream_t s) {
-      return gn_finalize(part, mrp, N, chunks, C, groups, HW, 1e-5f, s);
-    }, kOpNorm);
+    const bool fused = g_gn_variant == 3 && groups <= 128 && raw.N <= 65535 && 256 % (raw.C / 8) == 0;
+    if (!fused)
+      push_op([part, mrp, N, chunks, C, groups, HW](cudaStream_t s) {
+        return gn_finalize(part, mrp, N, chunks, C, groups, HW, 1e-5f, s);
+      }, kOpNorm);
     GnApplyDesc d{};
+    if (fused) { d.partial = part; d.chunks = chunks; d.eps = 1e-5f; }
     d.raw = raw.ptr; d.mean_rstd = mr.ptr; d.gamma = nl.g->data.p; d.beta = nl.b->data.p;
     d.raw_plane = raw.layout == kNHWCSplit ? raw.plane : 0; d.act = act;
     if (res) {

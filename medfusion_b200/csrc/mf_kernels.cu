@@ -5,6 +5,9 @@ namespace mf {
 static inline int ceil_div_ll(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 __device__ __forceinline__ float swish(float x) { return x / (1.0f + expf(-x)); }
+// streaming variant for the GroupNorm-apply kernel (which is instruction-issue bound, not bandwidth bound): same accurate
+// expf, but the IEEE division (about 14 instructions plus a slow-path call) becomes MUFU.RCP + FMUL (<= 2 ulp).
+__device__ __forceinline__ float swish_stream(float x) { return __fdividef(x, 1.0f + expf(-x)); }
 
 // =================================================================================================
 // Layout packing
@@ -521,12 +524,153 @@ __global__ void __launch_bounds__(256) gn_apply_flat_kernel(const GnApplyDesc d)
   }
 }
 
-int g_gn_variant = 0;
+// fused variant (default): one block = a pixel range of ONE sample.
+//   prologue: the block reduces that sample's partial statistics to (mean, rstd) per group itself — same warp-per-group,
+//             lane-strided fp64 reduction as gn_finalize_kernel, so the numbers are bit-identical and the separate
+//             finalize launch disappears;
+//   body:     a thread handles 8 consecutive channels of a pixel (two 16-byte loads, one 16-byte store per plane),
+//             two pixels in flight per iteration.
+__device__ __forceinline__ void ld_raw8(const GnApplyDesc& d, long long off, float (&x)[8]) {
+  if (d.raw_plane != 0) {
+    const __half* xh = reinterpret_cast<const __half*>(d.raw) + off;
+    const uint4 uh = *reinterpret_cast<const uint4*>(xh);
+    const uint4 ul = *reinterpret_cast<const uint4*>(xh + d.raw_plane);
+    const __half2* h = reinterpret_cast<const __half2*>(&uh);
+    const __half2* l = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(h[j]), b = __half22float2(l[j]);
+      x[2 * j] = a.x + b.x; x[2 * j + 1] = a.y + b.y;
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.raw) + off);
+    const float4 a = p[0], b = p[1];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d) {
+  __shared__ float s_mean[128], s_rstd[128];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.y;
+  const int cpg = d.C / d.G;
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = cpg / 8, c8 = d.C / 8, items = d.chunks * sub;
+    for (int g = warp; g < d.G; g += 8) {
+      double s = 0.0, ss = 0.0;
+      for (int it = lane; it < items; it += 32) {
+        const int ch = it / sub, j = it % sub;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(
+            d.partial + ((static_cast<long long>(n) * d.chunks + ch) * c8 + g * sub + j) * 2));
+        s += static_cast<double>(v.x);
+        ss += static_cast<double>(v.y);
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      }
+      if (lane == 0) {
+        const double cnt = static_cast<double>(cpg) * d.HW;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(d.eps)));
+      }
+    }
+  }
+  __syncthreads();
+  // A thread keeps ONE channel octet for its whole life (256 % (C/8) == 0 is checked by the host): the affine
+  // coefficients a = rstd*gamma, b = beta (+ embedding) stay in registers and the loop body is pure streaming.
+  const int c8n = d.C / 8;
+  const int ppb = 256 / c8n;                                // pixels per block iteration
+  const int c = (threadIdx.x % c8n) * 8;
+  const int psub = threadIdx.x / c8n;
+  const int g = c / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  float ca[8], cb[8], ce[8];
+  {
+    const float4 ga0 = __ldg(reinterpret_cast<const float4*>(d.gamma + c)), ga1 = __ldg(reinterpret_cast<const float4*>(d.gamma + c + 4));
+    const float4 be0 = __ldg(reinterpret_cast<const float4*>(d.beta + c)), be1 = __ldg(reinterpret_cast<const float4*>(d.beta + c + 4));
+    const float ga[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+    const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ca[j] = rstd * ga[j]; cb[j] = be[j]; ce[j] = 0.f; }
+    if (d.emb != nullptr) {
+      const long long erow = (d.emb_index ? d.emb_index[n] : static_cast<long long>(n)) * d.emb_stride;
+      const float4 e0 = __ldg(reinterpret_cast<const float4*>(d.emb + erow + c));
+      const float4 e1 = __ldg(reinterpret_cast<const float4*>(d.emb + erow + c + 4));
+      ce[0] = e0.x; ce[1] = e0.y; ce[2] = e0.z; ce[3] = e0.w; ce[4] = e1.x; ce[5] = e1.y; ce[6] = e1.z; ce[7] = e1.w;
+    }
+  }
+  const long long base = static_cast<long long>(n) * d.HW * d.C + c;
+  for (int pix = blockIdx.x * ppb + psub; pix < d.HW; pix += gridDim.x * ppb) {
+    const long long off = base + static_cast<long long>(pix) * d.C;
+    float x[8];
+    ld_raw8(d, off, x);
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = fmaf(x[j] - mean, ca[j], cb[j]);
+      if (d.act != 0) y[j] = swish_stream(y[j]);
+    }
+    if (d.res_kind == kResSplit) {
+      const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
+      const uint4 uh = *reinterpret_cast<const uint4*>(rh);
+      const uint4 ul = *reinterpret_cast<const uint4*>(rh + d.res_plane);
+      const __half2* h = reinterpret_cast<const __half2*>(&uh);
+      const __half2* l = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(h[j]), b = __half22float2(l[j]);
+        y[2 * j] += a.x + b.x; y[2 * j + 1] += a.y + b.y;
+      }
+    } else if (d.res_kind == kResRaw) {
+      const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
+      const float4 a = rp[0], b = rp[1];
+      y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; y[4] += b.x; y[5] += b.y; y[6] += b.z; y[7] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] += ce[j];
+    uint4 oh, ol;
+    uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
+    uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split16x2(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
+    *reinterpret_cast<uint4*>(d.out + off) = oh;
+    *reinterpret_cast<uint4*>(d.out + d.out_plane + off) = ol;
+  }
+}
+
+int g_gn_variant = 3;
+int g_pdl = 1;
 int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
   MF_REQUIRE(d.C % 4 == 0 && d.C % d.G == 0 && (d.C / d.G) % 4 == 0, "gn_apply channel constraints");
   MF_REQUIRE(d.emb == nullptr || d.emb_stride % 4 == 0, "emb rows must be float4 aligned");
   const long long npix = static_cast<long long>(d.N) * d.HW;
   if (npix == 0) return 0;
+  if (d.partial != nullptr) {
+    MF_REQUIRE(d.C % 8 == 0 && (d.C / d.G) % 8 == 0 && d.G <= 128 && d.chunks >= 1 && 256 % (d.C / 8) == 0,
+               "fused gn_apply: C/G % 8 == 0, G <= 128, C/8 divides 256");
+    MF_REQUIRE(d.N <= 65535, "fused gn_apply: batch too large");
+    const int ppb = 256 / (d.C / 8);
+    // ~8 resident blocks per SM over the whole launch, at least 2 pixels per thread where the sample is big enough
+    int bps = std::max(1, (148 * 8 + d.N - 1) / d.N);
+    bps = std::min(bps, std::max(1, (d.HW + 2 * ppb - 1) / (2 * ppb)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(bps, d.N, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel, d));
+    return 0;
+  }
   const int c4n = d.C / 4;
   const int ppb = c4n < 256 ? 256 / c4n : 1;
   const long long total = npix * c4n;

@@ -52,7 +52,9 @@ struct GnApplyDesc {
   const void* raw;          // [N,HW,C] conv output (+bias), float; or a split tensor (__half planes) when raw_plane != 0
   long long raw_plane;      // != 0: input is a split tensor (hi + lo)
   int act;                  // 1: Swish after the affine (conv blocks), 0: none (attention-block norms)
-  const float* mean_rstd;   // [N][G][2]
+  const float* mean_rstd;   // [N][G][2]  (unused when `partial` is given)
+  const float* partial; int chunks; float eps;   // != nullptr: per-(sample, chunk, 8-channel slab) (sum, sumsq); the kernel
+                                                 // finalises the statistics itself (no gn_finalize launch)
   const float* gamma; const float* beta;  // [C]
   const void* res; long long res_plane; int res_kind;   // split: __half planes, raw: float
   const float* emb; int emb_stride;       // emb[row*emb_stride + c] or nullptr; row = emb_index ? emb_index[n] : n
@@ -61,7 +63,9 @@ struct GnApplyDesc {
   int N, HW, C, G;
 };
 int gn_apply(const GnApplyDesc& d, cudaStream_t s);
-extern int g_gn_variant;  // 0: flat grid-stride (default), 1: fixed channel quad per thread, 2: flat, one quad per thread
+extern int g_pdl;         // 1: conv_tc and the fused gn_apply are launched with programmatic stream serialization
+extern int g_gn_variant;  // engine plans: 3 (default) = statistics finalised inside gn_apply (one launch per GroupNorm);
+                          // 0/1/2 = separate gn_finalize + flat grid-stride / fixed quad per thread / one quad per thread
 
 // nearest x2 upsample of a split tensor (reference: conv_blocks.py:123-125, F.interpolate nearest-exact)
 int upsample2x_split(const __half* in, long long in_plane, __half* out, long long out_plane, int N, int H, int W, int C,
