@@ -138,7 +138,7 @@ def cpu_reference_images_per_sec(timesteps, n_steps_sample=2, b=4):
     with torch.no_grad():
         O.unet_forward(usd, ucfg, x, torch.full((b,), 5), None)  # warm-up (thread pool, oneDNN primitives)
         t0 = time.perf_counter()
-        lat = O.denoise(lambda xx, tt, cc: O.unet_forward(usd, ucfg, xx, tt, cc), tabs, x, noises, n_steps_sample,
+        lat = O.denoise(lambda xx, tt, cc, sc=None: O.unet_forward(usd, ucfg, xx, tt, cc), tabs, x, noises, n_steps_sample,
                         use_ddim=False)
         t1 = time.perf_counter()
         O.vae_decode(vsd, vcfg, lat)

@@ -185,6 +185,25 @@ int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float
                   const float* d_noise_ddim, int objective_is_x0, int clip_x0, float* d_x_prior, float* d_x_0,
                   float* d_x_T, float* d_x_next, int B, int chw, mf_stream_t stream);
 
+/* The optional paths of DiffusionPipeline.forward (diffusion_pipeline.py:240-262, gaussian_scheduler.py:61-77,88-116):
+ *  - learned variance (estimate_variance=True): the estimator returns [B, 2*C, H, W]; pass the tensor itself as d_pred
+ *    (and d_pred_uncond), d_pred_var = d_pred + chw (the second chunk) and pred_batch_stride = 2*chw;
+ *    std = exp(0.5 * (s*log(beta_t) + (1-s)*log(post_var_t))), s = v/2 + 0.5, v = guided variance channels;
+ *  - cold_diffusion: x_prior = x_t - (x_t_est(t) - x_t_est(t-1)), no noise draw. */
+typedef struct {
+  const float* d_pred_var;          /* NULL: fixed small variance */
+  const float* d_pred_var_uncond;   /* NULL unless guidance is active */
+  int64_t pred_batch_stride;        /* 0 = chw */
+  int cold_diffusion;
+  const float* sqrt_alphas_cumprod;             /* fp32[T], cold diffusion only */
+  const float* sqrt_one_minus_alphas_cumprod;   /* fp32[T], cold diffusion only */
+  int T;
+} mf_sched_opts;
+int mf_sched_step_opts(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred, const float* d_pred_uncond,
+                       float guidance_scale, const int64_t* d_t, const float* d_noise, const int64_t* d_t_next,
+                       const float* d_noise_ddim, int objective_is_x0, int clip_x0, float* d_x_prior, float* d_x_0,
+                       float* d_x_T, float* d_x_next, int B, int chw, const mf_sched_opts* opts, mf_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------------
  * Kernel-level ops (test / profiling surface).  Layouts: 0 = NCHW fp32, 1 = NHWC fp32 ("raw"), 2 = NHWC "split":
  * two fp16 planes [2][N,H,W,C], hi = fp16(x), lo = fp16(x - hi), `plane` = elements between the planes.  Split

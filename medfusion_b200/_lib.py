@@ -41,6 +41,12 @@ class SchedTables(ctypes.Structure):
         "posterior_mean_coef2", "posterior_variance", "betas", "alphas_cumprod")]
 
 
+class SchedOpts(ctypes.Structure):
+    _fields_ = [("d_pred_var", c_void_p), ("d_pred_var_uncond", c_void_p), ("pred_batch_stride", c_int64),
+                ("cold_diffusion", c_int), ("sqrt_alphas_cumprod", c_void_p),
+                ("sqrt_one_minus_alphas_cumprod", c_void_p), ("T", c_int)]
+
+
 class StepArgs(ctypes.Structure):
     _fields_ = [
         ("tables", POINTER(SchedTables)), ("d_pred_uncond", c_void_p), ("guidance_scale", c_float),
@@ -92,6 +98,8 @@ SIGNATURES = {
     "mf_vae_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "mf_sched_step": (c_int, [POINTER(SchedTables), _P, _P, _P, c_float, _P, _P, _P, _P, c_int, c_int,
                               _P, _P, _P, _P, c_int, c_int, _P]),
+    "mf_sched_step_opts": (c_int, [POINTER(SchedTables), _P, _P, _P, c_float, _P, _P, _P, _P, c_int, c_int,
+                                   _P, _P, _P, _P, c_int, c_int, POINTER(SchedOpts), _P]),
     "mf_op_pack_split": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "mf_op_unpack_nchw": (c_int, [_P, c_int64, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "mf_op_prep_weight_tc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),

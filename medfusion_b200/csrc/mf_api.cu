@@ -652,10 +652,11 @@ int mf_vae_plan_info(const mf_vae* h, int* n_tc_convs, int* n_simt_convs, int* n
 }
 
 // ---- scheduler ----------------------------------------------------------------------------------
-int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred, const float* d_pred_uncond,
-                  float guidance_scale, const int64_t* d_t, const float* d_noise, const int64_t* d_t_next,
-                  const float* d_noise_ddim, int objective_is_x0, int clip_x0, float* d_x_prior, float* d_x_0,
-                  float* d_x_T, float* d_x_next, int B, int chw, mf_stream_t stream) {
+int mf_sched_step_opts(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred,
+                       const float* d_pred_uncond, float guidance_scale, const int64_t* d_t, const float* d_noise,
+                       const int64_t* d_t_next, const float* d_noise_ddim, int objective_is_x0, int clip_x0,
+                       float* d_x_prior, float* d_x_0, float* d_x_T, float* d_x_next, int B, int chw,
+                       const mf_sched_opts* opts, mf_stream_t stream) {
   MF_REQUIRE(tables && d_x_t && d_pred && d_t, "bad arguments");
   SchedStepDesc d{};
   d.x_t = d_x_t; d.pred = d_pred; d.pred_uncond = d_pred_uncond; d.guidance = guidance_scale;
@@ -673,7 +674,24 @@ int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float
   d.tab.post_var = tables->posterior_variance;
   d.tab.betas = tables->betas;
   d.tab.alphas_cumprod = tables->alphas_cumprod;
+  if (opts != nullptr) {
+    MF_REQUIRE(opts->pred_batch_stride == 0 || opts->pred_batch_stride >= chw, "pred_batch_stride < chw");
+    MF_REQUIRE(!opts->cold_diffusion || (opts->sqrt_alphas_cumprod && opts->sqrt_one_minus_alphas_cumprod && opts->T > 0),
+               "cold_diffusion needs sqrt_alphas_cumprod / sqrt_one_minus_alphas_cumprod / T");
+    MF_REQUIRE(opts->d_pred_var_uncond == nullptr || opts->d_pred_var != nullptr, "d_pred_var_uncond without d_pred_var");
+    d.pred_var = opts->d_pred_var; d.pred_var_uncond = d_pred_uncond ? opts->d_pred_var_uncond : nullptr;
+    d.pred_bstride = opts->pred_batch_stride;
+    d.cold = opts->cold_diffusion;
+    d.sqrt_ac = opts->sqrt_alphas_cumprod; d.sqrt_1mac = opts->sqrt_one_minus_alphas_cumprod; d.T = opts->T;
+  }
   return sched_step(d, static_cast<cudaStream_t>(stream));
+}
+int mf_sched_step(const mf_sched_tables* tables, const float* d_x_t, const float* d_pred, const float* d_pred_uncond,
+                  float guidance_scale, const int64_t* d_t, const float* d_noise, const int64_t* d_t_next,
+                  const float* d_noise_ddim, int objective_is_x0, int clip_x0, float* d_x_prior, float* d_x_0,
+                  float* d_x_T, float* d_x_next, int B, int chw, mf_stream_t stream) {
+  return mf_sched_step_opts(tables, d_x_t, d_pred, d_pred_uncond, guidance_scale, d_t, d_noise, d_t_next, d_noise_ddim,
+                            objective_is_x0, clip_x0, d_x_prior, d_x_0, d_x_T, d_x_next, B, chw, nullptr, stream);
 }
 
 // ---- kernel-level ops (split tensors are fp16 hi/lo planes, passed as void*) ---------------------------------------

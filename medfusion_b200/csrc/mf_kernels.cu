@@ -781,10 +781,20 @@ int linear_small(const LinearDesc& d, cudaStream_t s) {
 // Scheduler step (reference: gaussian_scheduler.py:80-124, diffusion_pipeline.py:240-244, :297-304)
 // =================================================================================================
 // one element of the reverse step; `pred` is the estimator output for this element (before guidance)
+// estimate_x_t (gaussian_scheduler.py:61-77): t < 0 -> x_0, t >= T -> x_T, else sqrt(ac_t) x_0 + sqrt(1-ac_t) x_T
+__device__ __forceinline__ float sched_x_t(const SchedStepDesc& d, float x0, float xT, long long t) {
+  if (t < 0) return x0;
+  if (t >= d.T) return xT;
+  return __fadd_rn(__fmul_rn(d.sqrt_ac[t], x0), __fmul_rn(d.sqrt_1mac[t], xT));
+}
+
+// `pred` is element i of the estimator output in the [B, CHW] numbering of x_t; ip is the same element's position
+// inside the (possibly channel-stacked) estimator tensors.
 __device__ __forceinline__ void sched_element(const SchedStepDesc& d, long long i, int b, float pred) {
   const long long t = d.t[b];
+  const long long ip = d.pred_bstride ? static_cast<long long>(b) * d.pred_bstride + (i - static_cast<long long>(b) * d.CHW) : i;
   if (d.pred_uncond != nullptr) {
-    const float pu = d.pred_uncond[i];
+    const float pu = d.pred_uncond[ip];
     pred = pu + d.guidance * (pred - pu);  // classifier-free guidance combine
   }
   const float xt = d.x_t[i];
@@ -799,11 +809,37 @@ __device__ __forceinline__ void sched_element(const SchedStepDesc& d, long long 
     x0 = __fsub_rn(__fmul_rn(A, xt), __fmul_rn(Bm, pred));
     if (d.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
   }
-  const float mean = __fadd_rn(__fmul_rn(d.tab.coef1[t], x0), __fmul_rn(d.tab.coef2[t], xt));
-  float stdv = 0.f;
-  if (t != 0) stdv = expf(0.5f * logf(fmaxf(d.tab.post_var[t], 1e-20f)));
-  const float nz = d.noise ? d.noise[i] : 0.f;
-  const float prior = __fadd_rn(mean, __fmul_rn(stdv, nz));
+  float prior;
+  if (d.cold) {
+    // gaussian_scheduler.py:88-93: x_T re-estimated from the (always clamped, estimate_x_T default) x_0, then the
+    // deterministic difference of two forward diffusions is removed from x_t; no random draw
+    const float x0c = fminf(fmaxf(x0, -1.f), 1.f);
+    const float xTe = __fdiv_rn(__fsub_rn(__fmul_rn(A, xt), x0c), Bm);
+    const float est_t = sched_x_t(d, x0, xTe, t);
+    const float est_p = sched_x_t(d, x0, xTe, t - 1);
+    prior = __fsub_rn(xt, __fsub_rn(est_t, est_p));
+  } else {
+    const float mean = __fadd_rn(__fmul_rn(d.tab.coef1[t], x0), __fmul_rn(d.tab.coef2[t], xt));
+    float stdv = 0.f;
+    if (t != 0) {
+      const float lo = logf(fmaxf(d.tab.post_var[t], 1e-20f));
+      float logvar = lo;
+      if (d.pred_var != nullptr) {
+        // learned variance (diffusion_pipeline.py:246-256, gaussian_scheduler.py:110-116): v in [-1,1] -> scale in [0,1]
+        float pv = d.pred_var[ip];
+        if (d.pred_var_uncond != nullptr) {
+          const float pvu = d.pred_var_uncond[ip];
+          pv = pvu + d.guidance * (pv - pvu);
+        }
+        const float vs = __fadd_rn(__fmul_rn(pv, 0.5f), 0.5f);
+        const float hi = logf(fmaxf(d.tab.betas[t], 1e-20f));
+        logvar = __fadd_rn(__fmul_rn(vs, hi), __fmul_rn(__fsub_rn(1.f, vs), lo));
+      }
+      stdv = expf(0.5f * logvar);
+    }
+    const float nz = d.noise ? d.noise[i] : 0.f;
+    prior = __fadd_rn(mean, __fmul_rn(stdv, nz));
+  }
   if (d.x_prior) d.x_prior[i] = prior;
   if (d.x_0) d.x_0[i] = x0;
   if (d.x_T) d.x_T[i] = xT;
@@ -828,7 +864,11 @@ __global__ void sched_step_kernel(const SchedStepDesc d) {
   const long long total = static_cast<long long>(d.B) * d.CHW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    sched_element(d, i, static_cast<int>(i / d.CHW), d.pred[i]);
+  {
+    const int b = static_cast<int>(i / d.CHW);
+    const long long ip = d.pred_bstride ? static_cast<long long>(b) * d.pred_bstride + (i - static_cast<long long>(b) * d.CHW) : i;
+    sched_element(d, i, b, d.pred[ip]);
+  }
 }
 
 // =================================================================================================

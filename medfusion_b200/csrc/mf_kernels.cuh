@@ -100,6 +100,11 @@ struct SchedStepDesc {
   float* x_prior; float* x_0; float* x_T; float* x_next;  // outputs (x_next only with t_next)
   int B, CHW;
   SchedTables tab;
+  // optional paths of DiffusionPipeline.forward (diffusion_pipeline.py:240-262, gaussian_scheduler.py:88-116)
+  const float* pred_var; const float* pred_var_uncond;   // learned variance channels (estimate_variance=True) or nullptr
+  long long pred_bstride;    // elements between samples of pred / pred_uncond / pred_var (0: CHW; 2*CHW for chunk(2, dim=1))
+  int cold;                  // cold-diffusion update (no noise draw)
+  const float* sqrt_ac; const float* sqrt_1mac; int T;   // tables estimate_x_t needs (cold diffusion only)
 };
 int sched_step(const SchedStepDesc& d, cudaStream_t s);
 

@@ -54,8 +54,6 @@ class UNet(EngineModule):
             raise NotImplementedError("use_res_block=False (UnetBasicBlock) is not on the accelerated hot path")
         if deep_supervision not in (False, 0):
             raise NotImplementedError("deep_supervision heads are training-only; construct with deep_supervision=False")
-        if use_self_conditioning:
-            raise NotImplementedError("use_self_conditioning=True is not implemented yet")
         if not learnable_interpolation:
             raise NotImplementedError("learnable_interpolation=False (pooling) is not implemented")
         if dropout not in (0, 0.0, None):
@@ -87,7 +85,8 @@ class UNet(EngineModule):
             raise ValueError("cond_embedder emb_dim must equal the time embedding dim")
 
         cfg = _lib.UNetConfig()
-        cfg.in_ch, cfg.out_ch, cfg.depth = in_ch, (out_ch * 2 if estimate_variance else out_ch), depth
+        cfg.in_ch = in_ch * 2 if use_self_conditioning else in_ch                       # unet2.py:65
+        cfg.out_ch, cfg.depth = (out_ch * 2 if estimate_variance else out_ch), depth      # unet2.py:212
         for i in range(depth):
             cfg.hid_chs[i], cfg.kernel_sizes[i], cfg.strides[i] = hid_chs[i], kernel_sizes[i], strides[i]
             cfg.attention[i] = attn_codes[attn[i]]
@@ -121,6 +120,10 @@ class UNet(EngineModule):
         self.sync_params()
         B, _, H, W = x_t.shape
         x = x_t.contiguous().float()
+        if self.use_self_conditioning:
+            # unet2.py:243-246, quirk kept: the second half is zeros on the first call and x_t ITSELF (not the
+            # self_cond tensor) whenever a self_cond is passed
+            x = torch.cat([x, torch.zeros_like(x) if self_cond is None else x], dim=1)
         tt = None if t is None else t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
         cc = None
         if condition is not None and self.cond_spec is not None:

@@ -79,39 +79,69 @@ class GaussianNoiseScheduler(BasicNoiseScheduler):
         return tab
 
     def step(self, x_t, t, pred, *, pred_uncond=None, guidance_scale=1.0, noise=None, t_next=None, noise_ddim=None,
-             objective="x_T", clip_x0=True, want=("x_prior", "x_0", "x_T")):
-        """One fused reverse step. Returns dict with the requested tensors among x_prior, x_0, x_T, x_next."""
+             objective="x_T", clip_x0=True, want=("x_prior", "x_0", "x_T"), learned_variance=False,
+             cold_diffusion=False):
+        """One fused reverse step. Returns dict with the requested tensors among x_prior, x_0, x_T, x_next.
+
+        learned_variance=True: `pred` (and `pred_uncond`) are the estimator's [B, 2*C, ...] outputs; the second channel
+        half is the variance interpolation coefficient (diffusion_pipeline.py:246-256).  cold_diffusion=True: the
+        deterministic update of gaussian_scheduler.py:88-93 (no noise is used)."""
         require_cuda(x_t, "scheduler step")
         x_t = x_t.contiguous()
         pred = pred.contiguous()
         B = x_t.shape[0]
         chw = x_t[0].numel()
+        if pred[0].numel() != (2 * chw if learned_variance else chw):
+            raise ValueError(f"pred has {pred[0].numel()} elements per sample, expected {(2 if learned_variance else 1) * chw}")
         t = t.to(device=x_t.device, dtype=torch.int64).expand(B).contiguous()
         outs = {k: torch.empty_like(x_t) for k in want}
         if t_next is not None:
             t_next = t_next.to(device=x_t.device, dtype=torch.int64).reshape(1).contiguous()
         tab = self._tables()
+        if pred_uncond is not None:
+            pred_uncond = pred_uncond.contiguous()
 
         def ptr(v):
             return None if v is None else v.contiguous().data_ptr()
 
-        _lib.check(_lib.load().mf_sched_step(
+        opts = None
+        if learned_variance or cold_diffusion:
+            opts = _lib.SchedOpts()
+            if learned_variance:
+                opts.d_pred_var = pred.data_ptr() + 4 * chw
+                opts.d_pred_var_uncond = None if pred_uncond is None else pred_uncond.data_ptr() + 4 * chw
+                opts.pred_batch_stride = 2 * chw
+            if cold_diffusion:
+                opts.cold_diffusion = 1
+                opts.sqrt_alphas_cumprod = self.sqrt_alphas_cumprod.data_ptr()
+                opts.sqrt_one_minus_alphas_cumprod = self.sqrt_one_minus_alphas_cumprod.data_ptr()
+                opts.T = int(self.T)
+        _lib.check(_lib.load().mf_sched_step_opts(
             ctypes.byref(tab), x_t.data_ptr(), pred.data_ptr(), ptr(pred_uncond), float(guidance_scale), t.data_ptr(),
             ptr(noise), ptr(t_next), ptr(noise_ddim), 1 if objective == "x_0" else 0, 1 if clip_x0 else 0,
             ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")), B, chw,
-            cuda_stream_ptr()), "mf_sched_step")
+            None if opts is None else ctypes.byref(opts), cuda_stream_ptr()), "mf_sched_step_opts")
         return outs
 
     # --- reference-named views (gaussian_scheduler.py:80-151) ---------------------------------
-    def estimate_x_t_prior_from_x_T(self, x_t, t, x_T, use_log=True, clip_x0=True, var_scale=0, cold_diffusion=False):
-        self._check_step_opts(use_log, var_scale, cold_diffusion)
-        o = self.step(x_t, t, x_T, noise=self.x_final(x_t), objective="x_T", clip_x0=clip_x0, want=("x_prior", "x_0"))
+    def _prior(self, x_t, t, pred, objective, use_log, clip_x0, var_scale, cold_diffusion):
+        self._check_step_opts(use_log)
+        learned = torch.is_tensor(var_scale)
+        if not learned and var_scale != 0:
+            raise NotImplementedError("a scalar var_scale != 0 is not implemented (pass the per-element tensor)")
+        if learned:   # var_scale = v/2 + 0.5 in the pipeline; the kernel takes v stacked behind the prediction
+            v = (var_scale.to(pred.dtype).expand_as(pred) - 0.5) * 2
+            pred = torch.cat([pred, v], dim=1)
+        noise = None if cold_diffusion else self.x_final(x_t)            # gaussian_scheduler.py:99 (not drawn when cold)
+        o = self.step(x_t, t, pred, noise=noise, objective=objective, clip_x0=clip_x0, want=("x_prior", "x_0"),
+                      learned_variance=learned, cold_diffusion=cold_diffusion)
         return o["x_prior"], o["x_0"]
 
+    def estimate_x_t_prior_from_x_T(self, x_t, t, x_T, use_log=True, clip_x0=True, var_scale=0, cold_diffusion=False):
+        return self._prior(x_t, t, x_T, "x_T", use_log, clip_x0, var_scale, cold_diffusion)
+
     def estimate_x_t_prior_from_x_0(self, x_t, t, x_0, use_log=True, clip_x0=True, var_scale=0, cold_diffusion=False):
-        self._check_step_opts(use_log, var_scale, cold_diffusion)
-        o = self.step(x_t, t, x_0, noise=self.x_final(x_t), objective="x_0", clip_x0=clip_x0, want=("x_prior", "x_0"))
-        return o["x_prior"], o["x_0"]
+        return self._prior(x_t, t, x_0, "x_0", use_log, clip_x0, var_scale, cold_diffusion)
 
     def estimate_x_0(self, x_t, x_T, t, clip_x0=True):
         return self.step(x_t, t, x_T, objective="x_T", clip_x0=clip_x0, want=("x_0",))["x_0"]
@@ -131,18 +161,6 @@ class GaussianNoiseScheduler(BasicNoiseScheduler):
         return var_scale * hi + (1 - var_scale) * lo
 
     @staticmethod
-    def _check_step_opts(use_log, var_scale, cold_diffusion):
-        if cold_diffusion:
-            raise NotImplementedError("cold_diffusion sampling is not implemented")
+    def _check_step_opts(use_log):
         if not use_log:
             raise NotImplementedError("use_log=False is not implemented")
-        if not (isinstance(var_scale, (int, float)) and var_scale == 0):
-            raise NotImplementedError("learned variance (var_scale != 0) is not implemented")
-
-    @classmethod
-    def x_final(cls, x):
-        return torch.randn_like(x)
-
-    @classmethod
-    def _clip_x_0(cls, x_0):
-        return x_0.clamp(-1, 1)

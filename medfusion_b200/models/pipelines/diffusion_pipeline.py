@@ -107,10 +107,6 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         sample_every_n_steps=1000,
     ):
         super().__init__()
-        if estimate_variance:
-            raise NotImplementedError("estimate_variance=True (learned variance) is not implemented")
-        if use_self_conditioning:
-            raise NotImplementedError("use_self_conditioning=True is not implemented")
         if estimator_objective not in ("x_T", "x_0"):
             raise ValueError("Unknown Objective")
         est_kwargs = dict(noise_estimator_kwargs or {})
@@ -156,26 +152,25 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         return super().load_state_dict(own, strict=strict, **kw)
 
     # ---------------------------------------------------------------------------------------------
-    def _predict(self, x_t, t, condition, guidance_scale, un_cond):
+    def _predict(self, x_t, t, condition, guidance_scale, un_cond, self_cond=None):
         """Estimator pass(es); returns (pred, pred_uncond|None). CFG combine happens in the step kernel."""
         est = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
         if (condition is not None) and (guidance_scale != 1.0):
-            pred_uncond, _ = est(x_t, t, condition=un_cond, self_cond=None)
-            pred_cond, _ = est(x_t, t, condition=condition, self_cond=None)
+            pred_uncond, _ = est(x_t, t, condition=un_cond, self_cond=self_cond)
+            pred_cond, _ = est(x_t, t, condition=condition, self_cond=self_cond)
             return pred_cond, pred_uncond
-        pred, _ = est(x_t, t, condition=condition, self_cond=None)
+        pred, _ = est(x_t, t, condition=condition, self_cond=self_cond)
         return pred, None
 
     def forward(self, x_t, t, condition=None, self_cond=None, guidance_scale=1.0, cold_diffusion=False, un_cond=None):
         """-> (x_t_prior, x_0, x_T, self_cond)   (diffusion_pipeline.py:232-275)"""
-        if cold_diffusion:
-            raise NotImplementedError("cold_diffusion sampling is not implemented")
         require_cuda(x_t, "DiffusionPipeline.forward(x_t)")
-        pred, pred_u = self._predict(x_t, t, condition, guidance_scale, un_cond)
-        noise = self.noise_scheduler.x_final(x_t)
+        pred, pred_u = self._predict(x_t, t, condition, guidance_scale, un_cond, self_cond)
+        noise = None if cold_diffusion else self.noise_scheduler.x_final(x_t)   # not drawn on the cold path
         o = self.noise_scheduler.step(x_t, t, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
                                       objective=self.estimator_objective, clip_x0=self.clip_x0,
-                                      want=("x_prior", "x_0", "x_T"))
+                                      want=("x_prior", "x_0", "x_T"), learned_variance=self.estimate_variance,
+                                      cold_diffusion=cold_diffusion)
         self_cond_out = o["x_T"] if self.estimator_objective == "x_0" else o["x_0"]
         return o["x_prior"], o["x_0"], o["x_T"], self_cond_out
 
@@ -189,8 +184,7 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         unknown = set(kwargs) - {"guidance_scale", "un_cond", "cold_diffusion"}
         if unknown:  # the reference forwards **kwargs to forward(), which raises TypeError on anything else
             raise TypeError(f"forward() got an unexpected keyword argument '{sorted(unknown)[0]}'")
-        if kwargs.get("cold_diffusion", False):
-            raise NotImplementedError("cold_diffusion sampling is not implemented")
+        cold = bool(kwargs.get("cold_diffusion", False))
         guidance_scale = kwargs.get("guidance_scale", 1.0)
         un_cond = kwargs.get("un_cond", None)
         require_cuda(x_t, "DiffusionPipeline.denoise(x_t)")
@@ -205,7 +199,10 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         x_t = x_t.contiguous().float()
         ts = timesteps_array.flip(0)
         est = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
-        fused = hasattr(est, "forward_step") and getattr(est, "out_ch", 99) <= 8 and not est.estimate_variance
+        # the fused head (+ CUDA graph) covers the canonical configuration; learned variance, self-conditioning and cold
+        # diffusion take the estimator + mf_sched_step_opts path below
+        fused = (hasattr(est, "forward_step") and getattr(est, "out_ch", 99) <= 8 and not est.estimate_variance
+                 and not self.use_self_conditioning and not cold)
         cfg = (condition is not None) and (guidance_scale != 1.0)
         # CUDA-graph path: one captured timestep replayed `steps` times (a second capture without the DDIM re-noise
         # for the last step).  Host-side noise injection (tests) cannot be captured -> eager loop below.
@@ -269,12 +266,16 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
                                      objective=self.estimator_objective, clip_x0=self.clip_x0, want=("x_next",),
                                      uniform_t=True)
             else:
-                pred, pred_u = self._predict(x_t, tb, condition, guidance_scale, un_cond)
-                noise = noise_fn(x_t)
+                # self-conditioning (diffusion_pipeline.py:291-292 + unet2.py:243-246): None on the first step, then
+                # "some tensor" — the estimator only looks at whether it is None
+                sc = x_t if (self.use_self_conditioning and i > 0) else None
+                pred, pred_u = self._predict(x_t, tb, condition, guidance_scale, un_cond, sc)
+                noise = None if cold else noise_fn(x_t)
                 noise2 = noise_fn(x_t) if ddim else None
                 o = sched.step(x_t, tb, pred, pred_uncond=pred_u, guidance_scale=guidance_scale, noise=noise,
                                t_next=t_next, noise_ddim=noise2, objective=self.estimator_objective,
-                               clip_x0=self.clip_x0, want=("x_next",))
+                               clip_x0=self.clip_x0, want=("x_next",), learned_variance=self.estimate_variance,
+                               cold_diffusion=cold)
             x_t = o["x_next"]
         return self._decode(x_t, as_uint8)
 

@@ -197,6 +197,76 @@ def ckpt_fixture():
     print("ckpt skeleton:", len(keys(vae)), "vae keys,", len(keys(pipe)), "pipeline keys")
 
 
+@torch.no_grad()
+def opts_fixture():
+    """The optional paths of DiffusionPipeline.forward (diffusion_pipeline.py:240-273): learned variance, the
+    self-conditioning quirk, cold diffusion, x_0 objective with clipping — scheduler level and 3-step trajectories
+    (no latent decoder: outputs are latents)."""
+    s = GaussianNoiseScheduler(**SCHED)
+    g = gen(31)
+    x_t = torch.randn(5, 8, 16, 16, generator=g)
+    pred = torch.randn(5, 8, 16, 16, generator=g)
+    noise = torch.randn(5, 8, 16, 16, generator=g)
+    pvar = torch.randn(5, 8, 16, 16, generator=g).clamp(-1.3, 1.3)
+    t = torch.tensor([999, 500, 37, 1, 0])
+    sched_out = {}
+    orig = torch.randn_like
+    torch.randn_like = lambda x, **k: noise.clone()
+    try:
+        for obj, fn in (("x_T", s.estimate_x_t_prior_from_x_T), ("x_0", s.estimate_x_t_prior_from_x_0)):
+            for clip in (False, True):
+                p, x0 = fn(x_t, t, pred, clip_x0=clip, var_scale=pvar / 2 + 0.5)
+                sched_out[f"var_{obj}_clip{int(clip)}"] = dict(prior=p, x_0=x0)
+                p, x0 = fn(x_t, t, pred, clip_x0=clip, var_scale=0, cold_diffusion=True)
+                sched_out[f"cold_{obj}_clip{int(clip)}"] = dict(prior=p, x_0=x0)
+    finally:
+        torch.randn_like = orig
+
+    def make_pipe(**over):
+        est = dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder, **fresh(UNET_SMALL))
+        kw = dict(noise_scheduler=GaussianNoiseScheduler, noise_estimator=UNet, latent_embedder=None,
+                  noise_scheduler_kwargs=dict(SCHED), noise_estimator_kwargs=est, estimator_objective="x_T",
+                  estimate_variance=False, use_self_conditioning=False, use_ema=False, do_input_centering=False,
+                  clip_x0=False)
+        kw.update(over)
+        pipe = DiffusionPipeline(**kw).eval()
+        fill_(pipe.noise_estimator)
+        return pipe
+
+    cases = {
+        "learned_var_cond": dict(pipe=dict(estimate_variance=True), n=2, cond=torch.tensor([1, 0]),
+                                 kw=dict(steps=3, use_ddim=True, guidance_scale=1.0)),
+        "learned_var_ddpm": dict(pipe=dict(estimate_variance=True, clip_x0=True), n=2, kw=dict(steps=3, use_ddim=False)),
+        "self_cond_ddim": dict(pipe=dict(use_self_conditioning=True), n=2, kw=dict(steps=3, use_ddim=True)),
+        "self_cond_x0_cfg": dict(pipe=dict(use_self_conditioning=True, estimator_objective="x_0", clip_x0=True), n=2,
+                                 cond=torch.tensor([0, 1]), kw=dict(steps=3, use_ddim=True, guidance_scale=2.0)),
+        "cold_ddim": dict(pipe={}, n=2, kw=dict(steps=3, use_ddim=True, cold_diffusion=True)),
+        "cold_ddpm_x0": dict(pipe=dict(estimator_objective="x_0", clip_x0=True), n=2,
+                             kw=dict(steps=3, use_ddim=False, cold_diffusion=True)),
+    }
+    out = {}
+    for name, c in cases.items():
+        pipe = make_pipe(**c["pipe"])
+        gg = gen(200 + len(out))
+        rec = []
+
+        def fake(x, **k):
+            n = torch.randn(x.shape, generator=gg, dtype=x.dtype)
+            rec.append(n)
+            return n.clone()
+
+        torch.randn_like = fake
+        try:
+            lat = pipe.sample(c["n"], (8, 32, 32), condition=c.get("cond"), **c["kw"])
+        finally:
+            torch.randn_like = orig
+        out[name] = dict(pipe=c["pipe"], kw=c["kw"], cond=c.get("cond"), noises=torch.stack(rec), latent=lat,
+                         keys=[(k, tuple(v.shape)) for k, v in pipe.noise_estimator.state_dict().items()])
+        print("opts", name, len(rec), "draws", float(lat.abs().max()))
+    torch.save(dict(unet_cfg=UNET_SMALL, sched=SCHED, x_t=x_t, pred=pred, noise=noise, pvar=pvar, t=t,
+                    sched_out=sched_out, cases=out), os.path.join(OUT, "sample_opts.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     unet_fixture("unet_small.pt", UNET_SMALL, 1)
@@ -206,5 +276,6 @@ if __name__ == "__main__":
     sched_fixture()
     sample_fixture()
     ckpt_fixture()
+    opts_fixture()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

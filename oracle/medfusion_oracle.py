@@ -159,10 +159,13 @@ def attention(sd, pre, x, emb, groups, heads=8):
 # ------------------------------------------------------------------------------------------------
 # UNet (models/estimators/unet2.py:222-269)
 # ------------------------------------------------------------------------------------------------
-def unet_forward(sd, cfg, x_t, t, cond=None):
-    """cfg: dict(hid_chs, strides, num_res_blocks, groups, pos_emb_dim). Returns y (y_ver is empty)."""
+def unet_forward(sd, cfg, x_t, t, cond=None, self_cond=None):
+    """cfg: dict(hid_chs, strides, num_res_blocks, groups, pos_emb_dim[, use_self_conditioning]).
+    Returns y (y_ver is empty)."""
     hid, strides, nrb, G = cfg["hid_chs"], cfg["strides"], cfg.get("num_res_blocks", 2), cfg.get("groups", 32)
     depth = len(hid)
+    if cfg.get("use_self_conditioning", False):                                        # unet2.py:243-246 (x_t, not self_cond)
+        x_t = torch.cat([x_t, torch.zeros_like(x_t) if self_cond is None else x_t], dim=1)
     emb = time_embedding(sd, t, cfg["pos_emb_dim"])                                   # unet2.py:233
     if cond is not None and "cond_embedder.embedding.weight" in sd:
         emb = emb + F.embedding(cond, sd["cond_embedder.embedding.weight"])            # unet2.py:239-241
@@ -239,18 +242,42 @@ def _ext(tab, t, ndim):
     return tab.gather(0, t).reshape(-1, *((1,) * (ndim - 1)))  # scheduler_base.py:43-46
 
 
-def sched_step(tabs, x_t, t, pred, noise, objective="x_T", clip_x0=False):
-    """estimate_x_t_prior_from_x_T/_x_0 with var_scale = 0 (gaussian_scheduler.py:80-124). Returns (prior, x_0, x_T)."""
+def estimate_x_t(tabs, x_0, t, x_T, T):
+    """gaussian_scheduler.py:61-77 (per-sample clipper: t < 0 -> x_0, t >= T -> x_T)"""
+    out = []
+    for b in range(t.shape[0]):
+        tb = int(t[b])
+        if tb < 0:
+            out.append(x_0[b])
+        elif tb >= T:
+            out.append(x_T[b])
+        else:
+            out.append(tabs["sqrt_alphas_cumprod"][tb] * x_0[b] + tabs["sqrt_one_minus_alphas_cumprod"][tb] * x_T[b])
+    return torch.stack(out)
+
+
+def sched_step(tabs, x_t, t, pred, noise, objective="x_T", clip_x0=False, var_scale=0, cold_diffusion=False):
+    """estimate_x_t_prior_from_x_T/_x_0 (gaussian_scheduler.py:80-124). Returns (prior, x_0, x_T).
+    var_scale: 0 or the per-element tensor pred_var/2+0.5 (diffusion_pipeline.py:254); cold_diffusion: :88-93."""
     nd = x_t.ndim
+    A, Bm = _ext(tabs["sqrt_recip_alphas_cumprod"], t, nd), _ext(tabs["sqrt_recipm1_alphas_cumprod"], t, nd)
     if objective == "x_T":
-        x_0 = _ext(tabs["sqrt_recip_alphas_cumprod"], t, nd) * x_t - _ext(tabs["sqrt_recipm1_alphas_cumprod"], t, nd) * pred
+        x_0 = A * x_t - Bm * pred
         x_0 = x_0.clamp(-1, 1) if clip_x0 else x_0
         x_T = pred
     else:
         x_0 = pred.clamp(-1, 1) if clip_x0 else pred
-        x_T = (_ext(tabs["sqrt_recip_alphas_cumprod"], t, nd) * x_t - x_0) / _ext(tabs["sqrt_recipm1_alphas_cumprod"], t, nd)
+        x_T = (A * x_t - x_0) / Bm
+    if cold_diffusion:
+        T = tabs["betas"].shape[0]
+        x_T_est = (A * x_t - x_0.clamp(-1, 1)) / Bm                 # estimate_x_T with its default clip_x0=True (:90)
+        x_t_est = estimate_x_t(tabs, x_0, t, x_T_est, T)
+        x_t_prior = estimate_x_t(tabs, x_0, t - 1, x_T_est, T)
+        return x_t - (x_t_est - x_t_prior), x_0, x_T
     mean = _ext(tabs["posterior_mean_coef1"], t, nd) * x_0 + _ext(tabs["posterior_mean_coef2"], t, nd) * x_t
-    logvar = torch.log(_ext(tabs["posterior_variance"], t, nd).clamp(min=1e-20))
+    lo = torch.log(_ext(tabs["posterior_variance"], t, nd).clamp(min=1e-20))
+    hi = torch.log(_ext(tabs["betas"], t, nd).clamp(min=1e-20))
+    logvar = var_scale * hi + (1 - var_scale) * lo                    # gaussian_scheduler.py:110-116
     std = torch.exp(0.5 * logvar)
     std[t == 0] = 0.0
     return mean + std * noise, x_0, x_T
@@ -265,9 +292,11 @@ def ddim_renoise(tabs, x_0, x_T, t, t_next, noise):
 
 
 def denoise(unet_fn, tabs, x_T, noises, steps, use_ddim=True, guidance_scale=1.0, cond=None, un_cond=None,
-            objective="x_T", clip_x0=False, T=1000):
-    """DiffusionPipeline.denoise without the latent decode (diffusion_pipeline.py:278-304).
-    `noises` is an iterator yielding the successive randn_like draws (scheduler draw, then DDIM draw)."""
+            objective="x_T", clip_x0=False, T=1000, estimate_variance=False, use_self_conditioning=False,
+            cold_diffusion=False):
+    """DiffusionPipeline.denoise without the latent decode (diffusion_pipeline.py:278-304; forward :232-275).
+    `noises` is an iterator yielding the successive randn_like draws (scheduler draw, then DDIM draw).
+    unet_fn(x_t, t, cond, self_cond) -> prediction ([B, 2C, ...] when estimate_variance)."""
     noises = iter(noises)
     if use_ddim:
         ts_arr = torch.linspace(0, T - 1, steps, dtype=torch.long)
@@ -276,15 +305,25 @@ def denoise(unet_fn, tabs, x_T, noises, steps, use_ddim=True, guidance_scale=1.0
         steps = len(ts_arr)
     x_t = x_T
     B = x_t.shape[0]
+    self_cond = None
     for i, t in enumerate(ts_arr.flip(0)):
         tb = t.expand(B)
-        if cond is not None and guidance_scale != 1.0:                  # diffusion_pipeline.py:240-244
-            pu = unet_fn(x_t, tb, un_cond)
-            pc = unet_fn(x_t, tb, cond)
+        var_scale = 0
+        if cond is not None and guidance_scale != 1.0:                  # diffusion_pipeline.py:240-249
+            pu = unet_fn(x_t, tb, un_cond, self_cond)
+            pc = unet_fn(x_t, tb, cond, self_cond)
             pred = pu + guidance_scale * (pc - pu)
+            if estimate_variance:   # (the reference forgets to chunk `pred` on this branch and fails; the intent is kept)
+                pred, pv = pred.chunk(2, dim=1)
+                var_scale = pv / 2 + 0.5
         else:
-            pred = unet_fn(x_t, tb, cond)
-        x_t, x_0, x_Te = sched_step(tabs, x_t, tb, pred, next(noises), objective, clip_x0)
+            pred = unet_fn(x_t, tb, cond, self_cond)
+            if estimate_variance:                                        # :250-256
+                pred, pv = pred.chunk(2, dim=1)
+                var_scale = pv / 2 + 0.5
+        noise = None if cold_diffusion else next(noises)
+        x_t, x_0, x_Te = sched_step(tabs, x_t, tb, pred, noise, objective, clip_x0, var_scale, cold_diffusion)
+        self_cond = (x_Te if objective == "x_0" else x_0) if use_self_conditioning else None   # :266,271,292
         if use_ddim and (steps - i - 1 > 0):
             x_t = ddim_renoise(tabs, x_0, x_Te, t, ts_arr[steps - i - 2], next(noises))
     return x_t
