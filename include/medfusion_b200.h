@@ -149,6 +149,7 @@ typedef struct {
   int hid_chs[MF_MAX_LEVELS];    /* [64,128,256,512] */
   int strides[MF_MAX_LEVELS];    /* [1,2,2,2]; levels 1.. must be 2 (nearest x2 + conv3x3) */
   int norm_groups;               /* 8 */
+  int in_channels;               /* image channels of the ENCODER half (3); 0 = decoder-only handle (ABI v2) */
 } mf_vae_config;
 
 typedef struct mf_vae mf_vae;
@@ -168,6 +169,13 @@ int mf_vae_decode(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, 
  * d_x_u8[B][H'][W'][out_channels] = uint8((clip(x,-1,1)+1)/2*255); d_x (fp32 NCHW) may be NULL. */
 int mf_vae_decode_u8(mf_vae* h, const float* d_z, float* d_x, uint8_t* d_x_u8, int B, int H, int W, void* d_workspace,
                      size_t workspace_bytes, mf_stream_t stream);
+/* VAE.encode (latent_embedders.py:756-762): x [B,in_channels,H,W] -> z [B,emb,H/f,W/f] = mean + exp(0.5*clamp(logvar,-30,20))
+ * * noise (DiagonalGaussianDistribution, :20-33).  d_noise: the caller's standard-normal draw of z's shape (the reference
+ * calls torch.randn(mean.shape)); NULL gives z = mean.  d_moments (optional): [B,2*emb,h,w] = (mean | logvar).
+ * The encoder has its own plan and workspace (mf_vae_encode_workspace_bytes). */
+size_t mf_vae_encode_workspace_bytes(mf_vae* h, int B, int H, int W);
+int mf_vae_encode(mf_vae* h, const float* d_x, const float* d_noise, float* d_z, float* d_moments, int B, int H, int W,
+                  void* d_workspace, size_t workspace_bytes, mf_stream_t stream);
 int mf_vae_profile(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
                    size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds, double* flops, int max_ops,
                    int* n_ops);

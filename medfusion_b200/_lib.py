@@ -32,6 +32,7 @@ class VAEConfig(ctypes.Structure):
     _fields_ = [
         ("emb_channels", c_int), ("out_channels", c_int), ("depth", c_int),
         ("hid_chs", c_int * MF_MAX_LEVELS), ("strides", c_int * MF_MAX_LEVELS), ("norm_groups", c_int),
+        ("in_channels", c_int),
     ]
 
 
@@ -93,6 +94,8 @@ SIGNATURES = {
     "mf_vae_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_vae_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "mf_vae_decode_u8": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_vae_encode_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
+    "mf_vae_encode": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "mf_vae_profile": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float), POINTER(c_int),
                                POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "mf_vae_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

@@ -289,8 +289,28 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
 // =================================================================================================
 // VAE decoder (reference: latent_embedders.py:718-743, :764-769; conv_blocks.py:444-528 UpBlock)
 // =================================================================================================
+// Encoder half (latent_embedders.py:680-716 ctor, :756-762 encode): its own launch plan / workspace state, while the
+// parameters live in the parent mf_vae's registry (one state_dict, reference key order: inc, encoders, out_enc, ...).
+struct mf_vae_enc_plan : public EngineBase {
+  const mf_vae_config* cfg = nullptr;
+  int in_channels = 3;
+  ResBlockLayer inc;
+  struct Down { ConvLayer down; ResBlockLayer rb; };
+  std::vector<std::unique_ptr<Down>> encoders;  // index i == encoders.{i}
+  ConvLayer out0, out1;
+  const float* io_x = nullptr;      // [B, in_channels, H, W]
+  const float* io_noise = nullptr;  // [B, emb, h, w] standard normal draw, or NULL (z = mean)
+  float* io_z = nullptr;            // [B, emb, h, w]
+  float* io_moments = nullptr;      // optional [B, 2*emb, h, w] (mean | logvar, unclamped)
+  float* moments_ws = nullptr;
+  int n_launches = 0;
+  int build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s);
+};
+
 struct mf_vae : public EngineBase {
   mf_vae_config cfg{};
+  mf_vae_enc_plan enc;
+  bool has_encoder = false;
   ResBlockLayer inc_dec;
   struct Up { ConvLayer up; ResBlockLayer rb; int factor = 2; };
   std::vector<std::unique_ptr<Up>> decoders;  // index i == decoders.{i}
@@ -306,6 +326,23 @@ struct mf_vae : public EngineBase {
 int mf_vae::init(const mf_vae_config& c) {
   cfg = c;
   MF_REQUIRE(c.depth >= 1 && c.depth <= MF_MAX_LEVELS, "depth must be in [1, 8]");
+  if (c.in_channels > 0) {
+    // encoder parameters, registered in the PARENT registry with the reference's names
+    has_encoder = true;
+    enc.cfg = &cfg;
+    enc.in_channels = c.in_channels;
+    MF_REQUIRE(c.strides[0] == 1, "VAE encoder: strides[0] must be 1");
+    init_resblock(*this, enc.inc, "inc", c.in_channels, c.hid_chs[0], 3, 0);
+    for (int i = 1; i < c.depth; ++i) {
+      enc.encoders.emplace_back(new mf_vae_enc_plan::Down());
+      auto& d = *enc.encoders.back();
+      const std::string pre = "encoders." + std::to_string(i - 1);
+      init_conv(*this, d.down, pre + ".down_op.down_op", c.hid_chs[i], c.hid_chs[i - 1], 3, c.strides[i]);
+      init_resblock(*this, d.rb, pre + ".conv_block", c.hid_chs[i], c.hid_chs[i], 3, 0);
+    }
+    init_conv(*this, enc.out0, "out_enc.0.conv", 2 * c.emb_channels, c.hid_chs[c.depth - 1], 3, 1);
+    init_conv(*this, enc.out1, "out_enc.1.conv", 2 * c.emb_channels, 2 * c.emb_channels, 1, 1);
+  }
   init_resblock(*this, inc_dec, "inc_dec", c.emb_channels, c.hid_chs[c.depth - 1], 3, 0);
   for (int i = 0; i < c.depth - 1; ++i) {
     decoders.emplace_back(new Up());
@@ -381,6 +418,77 @@ int mf_vae::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
   return 0;
 }
 
+// ---- VAE encoder plan: inc -> encoders (conv3x3 s2 + res block) -> out_enc (3x3, 1x1) -> reparameterisation
+int mf_vae_enc_plan::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
+  dry = dry_run;
+  base = ws;
+  prep_stream = s;
+  arena = Arena();
+  ops.clear();
+  op_meta.clear();
+  tc_plans.clear();
+  n_tc = n_simt = 0;
+  const mf_vae_config& c = *cfg;
+  const int G = c.norm_groups;
+  const int C0 = c.hid_chs[0];
+  int rc = 0;
+  // ---- inc: UnetResBlock(in_channels -> C0); both stem convs read the NCHW image directly
+  Tens raw = new_tensor(B, H, W, C0, kNHWCRaw);
+  Tens part = new_floats(static_cast<size_t>(B) * std::max(1, conv_tc_stats_chunks(H, W)) * (C0 / 8) * 2);
+  int chunks = 1;
+  rc = add_conv_nchw_in(inc.conv1, &io_x, B, in_channels, H, W, raw, &part, &chunks);
+  if (rc) return rc;
+  MF_REQUIRE(inc.has_res_conv, "VAE encoder with in_channels == hid_chs[0] is not supported");
+  Tens res_raw = new_tensor(B, H, W, C0, kNHWCRaw);
+  rc = add_conv_nchw_in(inc.conv_res, &io_x, B, in_channels, H, W, res_raw, nullptr, nullptr);
+  if (rc) return rc;
+  Tens x1 = new_tensor(B, H, W, C0, kNHWCSplit);
+  rc = add_gn_apply(inc.norm1, G, raw, part, chunks, &res_raw, nullptr, 0, x1);
+  if (rc) return rc;
+  free_tensor(res_raw);
+  rc = add_conv(inc.conv2, x1, nullptr, raw, &part, &chunks);
+  if (rc) return rc;
+  Tens hcur = new_tensor(B, H, W, C0, kNHWCSplit);
+  rc = add_gn_apply(inc.norm2, G, raw, part, chunks, &x1, nullptr, 0, hcur);
+  if (rc) return rc;
+  free_tensor(raw);
+  free_tensor(part);
+  free_tensor(x1);
+  // ---- encoders[i]: BasicDown (conv3x3, stride s) then UnetResBlock   (conv_blocks.py:430-441)
+  for (auto& e : encoders) {
+    const int st = e->down.stride, pd = e->down.k / 2;
+    Tens d = new_tensor(B, (hcur.H + 2 * pd - e->down.k) / st + 1, (hcur.W + 2 * pd - e->down.k) / st + 1, e->down.Cout,
+                        kNHWCSplit);
+    rc = add_conv(e->down, hcur, nullptr, d, nullptr, nullptr);
+    if (rc) return rc;
+    free_tensor(hcur);
+    Tens o;
+    rc = add_resblock(e->rb, G, d, nullptr, nullptr, 0, &o);
+    if (rc) return rc;
+    free_tensor(d);
+    hcur = o;
+  }
+  // ---- out_enc: conv3x3 -> conv1x1 (no norm / activation), moments in NCHW
+  const int E2 = 2 * c.emb_channels;
+  Tens m0 = new_tensor(B, hcur.H, hcur.W, E2, kNHWCRaw);
+  rc = add_conv(out0, hcur, nullptr, m0, nullptr, nullptr);
+  if (rc) return rc;
+  free_tensor(hcur);
+  Tens mom = new_floats(static_cast<size_t>(B) * E2 * m0.H * m0.W);
+  moments_ws = mom.ptr;
+  rc = add_conv_nchw_out(out1, m0, &moments_ws);
+  if (rc) return rc;
+  free_tensor(m0);
+  if (!dry) {
+    const int ehw = c.emb_channels * m0.H * m0.W;
+    push_op([this, B, ehw](cudaStream_t st) { return vae_reparam(moments_ws, io_noise, io_z, io_moments, B, ehw, st); },
+            kOpOther);
+  }
+  free_tensor(mom);
+  n_launches = static_cast<int>(ops.size());
+  return 0;
+}
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -411,7 +519,7 @@ static int prepare_plan(E* h, int B, int H, int W, void* ws, size_t ws_bytes, cu
 extern "C" {
 
 const char* mf_last_error(void) { return mf::get_error(); }
-int mf_abi_version(void) { return 1; }
+int mf_abi_version(void) { return 2; }
 int mf_set_debias_eps(float eps_per_kblock) {
   mf::g_debias_eps_per_kblock = eps_per_kblock;
   return 0;
@@ -633,6 +741,30 @@ int mf_vae_decode_u8(mf_vae* h, const float* d_z, float* d_x, uint8_t* d_x_u8, i
   rc = h->run(s);
   h->io_out_u8 = nullptr;
   return rc;
+}
+size_t mf_vae_encode_workspace_bytes(mf_vae* h, int B, int H, int W) {
+  if (!h->has_encoder) { set_error("this VAE handle was created without an encoder (in_channels == 0)"); return 0; }
+  h->enc.version = h->version;
+  if (h->enc.build(B, H, W, nullptr, true, nullptr)) return 0;
+  const size_t need = h->enc.arena.peak;
+  h->enc.key = typename mf_vae_enc_plan::PlanKey();
+  return need;
+}
+int mf_vae_encode(mf_vae* h, const float* d_x, const float* d_noise, float* d_z, float* d_moments, int B, int H, int W,
+                  void* d_workspace, size_t workspace_bytes, mf_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MF_REQUIRE(h->has_encoder, "this VAE handle was created without an encoder (in_channels == 0)");
+  MF_REQUIRE(d_x && d_z && B > 0 && H > 0 && W > 0, "bad arguments");
+  int rc = h->check_all_set();
+  if (rc) return rc;
+  h->enc.version = h->version;   // parameters (and their prepared layouts) are owned by the parent handle
+  rc = prepare_plan(&h->enc, B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->enc.io_x = d_x;
+  h->enc.io_noise = d_noise;
+  h->enc.io_z = d_z;
+  h->enc.io_moments = d_moments;
+  return h->enc.run(s);
 }
 int mf_vae_profile(mf_vae* h, const float* d_z, float* d_x, int B, int H, int W, void* d_workspace,
                    size_t workspace_bytes, mf_stream_t stream, float* ms, int* kinds, double* flops, int max_ops,

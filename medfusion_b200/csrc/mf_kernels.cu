@@ -942,6 +942,36 @@ int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s) {
   return 0;
 }
 
+// =================================================================================================
+// VAE reparameterisation (latent_embedders.py:20-33 DiagonalGaussianDistribution):
+//   moments [B, 2E, HW] = (mean | logvar);  z = mean + exp(0.5 * clamp(logvar, -30, 20)) * noise
+// =================================================================================================
+__global__ void vae_reparam_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                   float* __restrict__ z, float* __restrict__ moments_out, int B, int EHW) {
+  const long long total = static_cast<long long>(B) * EHW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / EHW, r = i - b * EHW;
+    const float mean = moments[b * 2 * EHW + r];
+    const float lv = moments[b * 2 * EHW + EHW + r];
+    if (moments_out != nullptr) {
+      moments_out[b * 2 * EHW + r] = mean;
+      moments_out[b * 2 * EHW + EHW + r] = lv;
+    }
+    const float stdv = expf(__fmul_rn(0.5f, fminf(fmaxf(lv, -30.f), 20.f)));
+    z[i] = noise != nullptr ? __fadd_rn(mean, __fmul_rn(stdv, noise[i])) : mean;
+  }
+}
+
+int vae_reparam(const float* moments, const float* noise, float* z, float* moments_out, int B, int EHW, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * EHW;
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  vae_reparam_kernel<<<blocks, 256, 0, s>>>(moments, noise, z, moments_out, B, EHW);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int sched_step(const SchedStepDesc& d, cudaStream_t s) {
   const long long total = static_cast<long long>(d.B) * d.CHW;
   if (total == 0) return 0;

@@ -107,6 +107,8 @@ struct SchedStepDesc {
   const float* sqrt_ac; const float* sqrt_1mac; int T;   // tables estimate_x_t needs (cold diffusion only)
 };
 int sched_step(const SchedStepDesc& d, cudaStream_t s);
+// z = mean + exp(0.5*clamp(logvar,-30,20)) * noise from NCHW moments [B,2E,HW] (noise nullptr: z = mean)
+int vae_reparam(const float* moments, const float* noise, float* z, float* moments_out, int B, int EHW, cudaStream_t s);
 
 // ---- narrow 1x1 head (Cout <= 8): split NHWC -> NCHW fp32, optional fused scheduler step ------------------------
 struct HeadDesc {

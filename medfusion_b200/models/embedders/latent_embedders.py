@@ -1,8 +1,9 @@
-"""VAE latent embedder — decoder half only (reference: medical_diffusion/models/embedders/latent_embedders.py:620-855).
+"""VAE latent embedder (reference: medical_diffusion/models/embedders/latent_embedders.py:620-855).
 
-`VAE.decode` (:764-769) is on the sampling hot path and runs as an sm_100a launch plan (mf_vae_decode).
-The encoder / losses / GAN variants are training-side and outside this package's scope;
-`load_state_dict` accepts a full reference VAE state_dict and ignores the encoder-side keys.
+`VAE.decode` (:764-769) is on the sampling hot path and runs as an sm_100a launch plan (mf_vae_decode); `VAE.encode`
+(:756-762, the step on the other side of the latent) is a second plan of the same handle
+(mf_vae_encode).  Losses / perceptual nets / GAN variants are training-side and outside this package's scope;
+`load_state_dict` accepts a full reference VAE state_dict and ignores those entries.
 """
 from __future__ import annotations
 
@@ -14,7 +15,8 @@ from ... import _lib
 from ..._engine import EngineModule, cuda_stream_ptr, require_cuda
 from ...checkpoint import CheckpointMixin
 
-_ENCODER_SIDE_PREFIXES = ("inc.", "encoders.", "out_enc.", "outc_ver.", "perceiver.", "loss_fct.", "quantizer.")
+# training-side entries of a reference VAE state_dict (deep-supervision heads, LPIPS, loss modules)
+_ENCODER_SIDE_PREFIXES = ("outc_ver.", "perceiver.", "loss_fct.", "quantizer.")
 
 
 class VAE(CheckpointMixin, EngineModule):
@@ -67,6 +69,7 @@ class VAE(CheckpointMixin, EngineModule):
             self.up_factor *= s
         cfg = _lib.VAEConfig()
         cfg.emb_channels, cfg.out_channels, cfg.depth = emb_channels, out_channels, depth
+        cfg.in_channels = in_channels
         for i in range(depth):
             cfg.hid_chs[i], cfg.strides[i] = hid_chs[i], strides[i]
         cfg.norm_groups = dict(norm_name[1]).get("num_groups", 8) if isinstance(norm_name, (tuple, list)) else 8
@@ -74,6 +77,7 @@ class VAE(CheckpointMixin, EngineModule):
         _lib.check(_lib.load().mf_vae_create(ctypes.byref(cfg), ctypes.byref(handle)), "mf_vae_create")
         # zero-init: 2nd conv of each res block (conv_blocks.py:336) and the image head (latent_embedders.py:743)
         self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc."))
+        self._enc_ws = {}
 
     # --- checkpoint compatibility -------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -122,8 +126,43 @@ class VAE(CheckpointMixin, EngineModule):
         ws, ws_bytes = self._workspace(B, H, W)
         return self._profile_call("mf_vae_profile", (zc.data_ptr(), x.data_ptr(), B, H, W), (ws, ws_bytes))
 
+    def _encode(self, x, sample=True, want_moments=False):
+        require_cuda(x, "VAE.encode(x)")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError(f"x must be [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        self.sync_params()
+        B, _, H, W = x.shape
+        f = self.up_factor
+        if H % f or W % f:
+            raise ValueError(f"image height/width must be multiples of {f}")
+        xc = x.contiguous().float()
+        z = torch.empty((B, self.emb_channels, H // f, W // f), device=x.device, dtype=torch.float32)
+        # DiagonalGaussianDistribution.forward (latent_embedders.py:26): torch.randn(mean.shape, device=x.device)
+        noise = torch.randn(z.shape, device=x.device) if sample else None
+        mom = torch.empty((B, 2 * self.emb_channels, H // f, W // f), device=x.device) if want_moments else None
+        key = ("enc", B, H, W, torch.cuda.current_device())
+        ws = self._enc_ws.get(key)
+        if ws is None:
+            nbytes = _lib.load().mf_vae_encode_workspace_bytes(self._h, B, H, W)
+            if nbytes == 0:
+                _lib.check(2, "mf_vae_encode_workspace_bytes")
+            self._enc_ws.clear()
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
+            self._enc_ws[key] = ws
+        off = (-ws.data_ptr()) % 1024
+        _lib.check(_lib.load().mf_vae_encode(self._h, xc.data_ptr(), None if noise is None else noise.data_ptr(),
+                                             z.data_ptr(), None if mom is None else mom.data_ptr(), B, H, W,
+                                             ws.data_ptr() + off, ws.numel() - off, cuda_stream_ptr()), "mf_vae_encode")
+        return z, mom
+
     def encode(self, x):
-        raise NotImplementedError("VAE.encode is training-side and out of scope of the sampling hot path")
+        """x [B,in_channels,H,W] -> z [B,emb_channels,H/f,W/f], one reparameterised sample (latent_embedders.py:756-762)"""
+        return self._encode(x)[0]
 
     def forward(self, x_in):
-        raise NotImplementedError("VAE.forward (encode+decode with losses) is training-side; use decode(z)")
+        """-> (out, out_hor, emb_loss) as latent_embedders.py:771-790 (deep supervision heads are not built: out_hor = [])"""
+        z, mom = self._encode(x_in, want_moments=True)
+        mean, logvar = mom.chunk(2, dim=1)
+        logvar = logvar.clamp(-30.0, 20.0)
+        kl = 0.5 * torch.sum(mean.pow(2) + logvar.exp() - 1.0 - logvar) / x_in.shape[0]       # :29-31
+        return self.decode(z), [], kl

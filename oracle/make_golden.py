@@ -267,6 +267,39 @@ def opts_fixture():
                     sched_out=sched_out, cases=out), os.path.join(OUT, "sample_opts.pt"))
 
 
+@torch.no_grad()
+def vae_encode_fixture():
+    """VAE.encode / VAE.forward of the unmodified reference (latent_embedders.py:756-790) with the quantizer's
+    torch.randn draw recorded; weights are the per-key synthetic ones."""
+    m = fill_(VAE(loss=torch.nn.MSELoss, **dict(VAE_CANON, deep_supervision=False)).eval())
+    x = torch.randn(2, 3, 64, 64, generator=gen(41)).clamp(-1, 1)
+    rec = []
+    g = gen(42)
+    orig = torch.randn
+
+    def fake(*shape, **k):
+        shp = shape[0] if len(shape) == 1 and not isinstance(shape[0], int) else shape
+        n = orig(tuple(shp), generator=g)
+        rec.append(n)
+        return n.clone()
+
+    torch.randn = fake
+    try:
+        z = m.encode(x)
+        out, out_hor, emb_loss = m(x)
+    finally:
+        torch.randn = orig
+    h = m.inc(x)
+    for e in m.encoders:
+        h = e(h)
+    mom = m.out_enc(h)
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    torch.save(dict(cfg=dict(VAE_CANON, deep_supervision=False), x=x, noise_encode=rec[0], z=z, moments=mom,
+                    noise_forward=rec[1], out=out, emb_loss=emb_loss, keys=keys),
+               os.path.join(OUT, "vae_encode.pt"))
+    print("vae encode", float(z.abs().max()), float(mom.abs().max()), float(emb_loss), len(out_hor))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     unet_fixture("unet_small.pt", UNET_SMALL, 1)
@@ -277,5 +310,6 @@ if __name__ == "__main__":
     sample_fixture()
     ckpt_fixture()
     opts_fixture()
+    vae_encode_fixture()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

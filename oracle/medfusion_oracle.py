@@ -195,6 +195,25 @@ def unet_forward(sd, cfg, x_t, t, cond=None, self_cond=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# VAE.encode (models/embedders/latent_embedders.py:756-762; DownBlock.forward conv_blocks.py:430-441;
+# DiagonalGaussianDistribution :20-33)
+# ------------------------------------------------------------------------------------------------
+def vae_encode_moments(sd, cfg, x):
+    G, depth = cfg.get("groups", 8), len(cfg["hid_chs"])
+    h = unet_res_block(sd, "inc", x, None, G)
+    for i in range(1, depth):
+        h = conv2d(sd, f"encoders.{i - 1}.down_op.down_op", h, stride=cfg["strides"][i])
+        h = unet_res_block(sd, f"encoders.{i - 1}.conv_block", h, None, G)
+    return conv2d(sd, "out_enc.1.conv", conv2d(sd, "out_enc.0.conv", h))
+
+
+def vae_encode(sd, cfg, x, noise):
+    """noise: the torch.randn(mean.shape) draw of the quantizer (injected)."""
+    mean, logvar = torch.chunk(vae_encode_moments(sd, cfg, x), 2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+
+
+# ------------------------------------------------------------------------------------------------
 # VAE.decode (models/embedders/latent_embedders.py:764-769; UpBlock.forward conv_blocks.py:510-528)
 # ------------------------------------------------------------------------------------------------
 def vae_decode(sd, cfg, z):

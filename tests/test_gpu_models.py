@@ -364,3 +364,45 @@ def test_optional_forward_paths_match_reference_fixture(case):
         next(noises)
     scale = max(1.0, float(c["latent"].abs().max()))
     assert_close(lat.cpu() / scale, c["latent"] / scale, what=case)
+
+
+def test_vae_encode_and_forward_match_reference_fixture():
+    """VAE.encode / VAE.forward (latent_embedders.py:756-790) vs the unmodified reference; the quantizer's
+    torch.randn draw is replayed by seeding around the call."""
+    g = load_golden("vae_encode.pt")
+    keep = ("in_channels", "out_channels", "emb_channels", "spatial_dims", "hid_chs", "kernel_sizes", "strides",
+            "deep_supervision", "use_attention")
+    m = make_vae({k: v for k, v in g["cfg"].items() if k in keep}, DEV)
+    x = g["x"].to(DEV)
+    z_mean, mom = m._encode(x, sample=False, want_moments=True)
+    assert_close(mom.cpu(), g["moments"], what="moments (mean | logvar)")
+    assert torch.equal(z_mean, mom[:, :8])
+    # encode(): z = mean + std * torch.randn(mean.shape) with the device generator -> replay the same draw
+    torch.manual_seed(77)
+    z = m.encode(x)
+    torch.manual_seed(77)
+    n = torch.randn(z.shape, device=DEV)
+    mean, logvar = g["moments"].chunk(2, dim=1)
+    want = mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * n.cpu()
+    assert_close(z.cpu(), want, what="z = mean + std*noise")
+    # forward(): (out, [], kl)
+    torch.manual_seed(78)
+    out, hor, kl = m(x)
+    torch.manual_seed(78)
+    n2 = torch.randn(z.shape, device=DEV)
+    z2 = (mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * n2.cpu()).to(DEV)
+    assert hor == [] and torch.allclose(out, m.decode(z2), rtol=1e-3, atol=1e-5)
+    kl_ref = 0.5 * torch.sum(mean.pow(2) + logvar.clamp(-30, 20).exp() - 1.0 - logvar.clamp(-30, 20)) / x.shape[0]
+    assert abs(float(kl) - float(kl_ref)) <= 1e-4 * abs(float(kl_ref))
+    # the recorded reference draw reproduces the reference's own z and reconstruction
+    z_ref = (mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * g["noise_forward"]).to(DEV)
+    assert_close(m.decode(z_ref).cpu(), g["out"], what="forward reconstruction")
+
+
+def test_vae_encode_full_resolution_roundtrip_shapes():
+    g = load_golden("vae_canonical.pt")
+    m = make_vae(_vae_cfg(g["cfg"]), DEV)
+    x = torch.rand(3, 3, 256, 256, device=DEV) * 2 - 1
+    z = m.encode(x)
+    assert z.shape == (3, 8, 32, 32) and torch.isfinite(z).all()
+    assert m.decode(z).shape == x.shape
