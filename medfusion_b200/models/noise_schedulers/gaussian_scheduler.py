@@ -164,3 +164,11 @@ class GaussianNoiseScheduler(BasicNoiseScheduler):
     def _check_step_opts(use_log):
         if not use_log:
             raise NotImplementedError("use_log=False is not implemented")
+
+    @classmethod
+    def x_final(cls, x):
+        return torch.randn_like(x)
+
+    @classmethod
+    def _clip_x_0(cls, x_0):
+        return x_0.clamp(-1, 1)

@@ -363,7 +363,12 @@ def test_optional_forward_paths_match_reference_fixture(case):
     with pytest.raises(StopIteration):
         next(noises)
     scale = max(1.0, float(c["latent"].abs().max()))
-    assert_close(lat.cpu() / scale, c["latent"] / scale, what=case)
+    # Trajectory tolerance.  The north-star tolerance (rtol 1e-3, atol 1e-5) is per estimator call; the reference's own
+    # update x_0 = A_t x_t - B_t pred has A_999 = 1/sqrt(abar_999) = 158, so an estimator error of 1e-5 at the first step
+    # (t = 999) is a 1.6e-3 error in x_0, and 3.5e-4 after the DDIM re-noise multiplies it by sqrt(abar_499) = 0.22.
+    # Where the latents stay O(1) (no blow-up that the scale normalisation would absorb) that amplification is visible:
+    atol = {"cold_ddim": 1e-3, "self_cond_x0_cfg": 1e-4}.get(case, 1e-5)
+    assert_close(lat.cpu() / scale, c["latent"] / scale, atol=atol, what=case)
 
 
 def test_vae_encode_and_forward_match_reference_fixture():
