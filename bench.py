@@ -296,7 +296,9 @@ def main():
             traffic = json.load(fh).get("dram_bytes_per_launch")
     except Exception:
         pass
-    launches_per_sample = args.timesteps * (unet.plan_info()["launches"] + 1) + vae.plan_info()["launches"]
+    # kernels of this library per sample(): the UNet plan per timestep (the scheduler update rides in the plan's last
+    # kernel, the output head) + the decoder plan; torch's own randn / copy kernels are not counted
+    launches_per_sample = args.timesteps * unet.plan_info()["launches"] + vae.plan_info()["launches"]
 
     if rank == 0:
         cpu = None
