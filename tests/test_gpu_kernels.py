@@ -206,7 +206,9 @@ def test_scheduler_cfg_and_ddim_against_oracle():
         assert_close(o["x_next"].cpu(), nxt, what="ddim re-noise")
 
 
-@pytest.mark.parametrize("B,N,heads,d", [(2, 64, 8, 32), (1, 256, 8, 128), (3, 100, 4, 64)])
+# the last three shapes have enough (batch, head, query-block) work to take the many-queries-per-warp variants
+@pytest.mark.parametrize("B,N,heads,d", [(2, 64, 8, 32), (1, 256, 8, 128), (3, 100, 4, 64), (32, 256, 8, 128),
+                                         (16, 100, 8, 64), (24, 70, 8, 32)])
 def test_attention_core_matches_oracle(B, N, heads, d):
     import ctypes
     import medfusion_oracle as O

@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
 
-CASES = ["unet_canon_b5", "unet_small_b3", "unet_small_b1", "vae_small_b3", "vae_small_b3_u8", "pipe_b3_eager",
+CASES = ["vae_small_encode", "unet_attn_b3", "unet_canon_b5", "unet_small_b3", "unet_small_b1", "vae_small_b3", "vae_small_b3_u8", "pipe_b3_eager",
          "pipe_b3_graph", "pipe_b1_graph", "dataset"]
 
 
@@ -27,6 +27,20 @@ def run(name):
         y = m(x, t, (torch.arange(B) % 2).to(dev))[0]
         torch.cuda.synchronize()
         print(name, float(y.abs().mean()))
+    elif name == "unet_attn_b3":
+        ga = load_golden("unet_attn_small.pt")
+        m = make_unet(ga["cfg"], dev)
+        x = torch.randn(3, 8, 32, 32, generator=gen).to(dev)
+        y = m(x, torch.randint(0, 1000, (3,), generator=gen).to(dev), (torch.arange(3) % 2).to(dev))[0]
+        torch.cuda.synchronize()
+        print(name, float(y.abs().mean()))
+    elif name == "vae_small_encode":
+        from test_gpu_models import _vae_cfg
+        m = make_vae(_vae_cfg(g["vae_cfg"]), dev)
+        z = m.encode(torch.rand(3, 3, 64, 64, generator=gen).to(dev) * 2 - 1)
+        out, _, kl = m(torch.rand(1, 3, 64, 64, generator=gen).to(dev))
+        torch.cuda.synchronize()
+        print(name, float(z.abs().mean()), float(kl))
     elif name.startswith("vae"):
         from test_gpu_models import _vae_cfg
         m = make_vae(_vae_cfg(g["vae_cfg"]), dev)
@@ -63,9 +77,11 @@ if __name__ == "__main__":
         if not ok:
             bad.append(c)
             print("   ", "\n    ".join(p.stderr.strip().splitlines()[-4:])[:800], flush=True)
-    for c in bad[:2]:
+    if os.environ.get("SANITIZE"):
+        bad = [c for c in os.environ["SANITIZE"].split(",") if c]
+    for c in bad[:6]:
         p = subprocess.run(["compute-sanitizer", "--tool", "memcheck", "--print-limit", "3", sys.executable, __file__,
                             "--case", c], capture_output=True, text=True, timeout=900)
         lines = [l for l in (p.stdout + p.stderr).splitlines() if "=========" in l]
-        print("SANITIZER", c)
+        print("SANITIZER", c, "rc", p.returncode)
         print("\n".join(lines[:40])[:5000], flush=True)

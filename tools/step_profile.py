@@ -15,8 +15,12 @@ import bench  # noqa: E402
 dev = "cuda:0"
 B = int(os.environ.get("B", "64"))
 names = {0: "conv_tc", 1: "conv_simt", 2: "groupnorm family", 3: "other (embedding MLP, pack, attention)"}
-u = make_unet(bench.UNET_CFG, dev)
-x = torch.randn(B, 8, 32, 32, device=dev)
+LAT = int(os.environ.get("LATENT", "32"))          # 64 + ATTN=1 = BASELINE.json configs[3] (config 4 of SURVEY.md §8d)
+ucfg = dict(bench.UNET_CFG)
+if os.environ.get("ATTN"):
+    ucfg["use_attention"] = ["none", "none", "none", "spatial"]
+u = make_unet(ucfg, dev)
+x = torch.randn(B, 8, LAT, LAT, device=dev)
 t = torch.full((B,), 500, device=dev, dtype=torch.int64)
 for _ in range(3):
     prof = u.profile(x, t, None)
@@ -26,11 +30,11 @@ for k, n in names.items():
     sel = [p for p in prof if p[1] == k]
     out[n] = {"ms": sum(p[0] for p in sel), "launches": len(sel), "share": sum(p[0] for p in sel) / tot,
               "tflops": (sum(p[2] for p in sel) / max(1e-9, sum(p[0] for p in sel)) / 1e9) if k < 2 else None}
-slow = sorted(((p[0], i, p[1], p[2]) for i, p in enumerate(prof)), reverse=True)[:8]
+slow = sorted(((p[0], i, p[1], p[2]) for i, p in enumerate(prof)), reverse=True)[:int(os.environ.get("TOP", "8"))]
 out["slowest"] = [dict(ms=round(a, 4), index=i, kind=names[k], gflop=round(f / 1e9, 1)) for a, i, k, f in slow]
 print(json.dumps(out))
 v = make_vae(bench.VAE_CFG, dev)
-z = torch.randn(B, 8, 32, 32, device=dev)
+z = torch.randn(B, 8, LAT, LAT, device=dev)
 for _ in range(2):
     pv = v.profile(z)
 totv = sum(p[0] for p in pv)
