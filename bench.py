@@ -118,7 +118,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores (bounded sample, extrapolated)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_images_per_sec(timesteps, n_steps_sample=2, b=4):
+def cpu_reference_images_per_sec(timesteps, n_steps_sample=2, b=4, conditional=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -138,8 +138,9 @@ def cpu_reference_images_per_sec(timesteps, n_steps_sample=2, b=4):
     with torch.no_grad():
         O.unet_forward(usd, ucfg, x, torch.full((b,), 5), None)  # warm-up (thread pool, oneDNN primitives)
         t0 = time.perf_counter()
+        cond = (torch.arange(b) % 2) if conditional else None      # configs[2]: 2-class labels, guidance_scale 1
         lat = O.denoise(lambda xx, tt, cc, sc=None: O.unet_forward(usd, ucfg, xx, tt, cc), tabs, x, noises, n_steps_sample,
-                        use_ddim=False)
+                        use_ddim=False, guidance_scale=1.0, cond=cond)
         t1 = time.perf_counter()
         O.vae_decode(vsd, vcfg, lat)
         t2 = time.perf_counter()
@@ -156,7 +157,8 @@ def run_reference_arm(args):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        ips, cores, sample = cpu_reference_images_per_sec(args.timesteps, n_steps_sample=1 if i < args.warmup else 2)
+        ips, cores, sample = cpu_reference_images_per_sec(args.timesteps, n_steps_sample=1 if i < args.warmup else 2,
+                                                          conditional=args.gpus > 1)
         if i >= args.warmup:
             vals.append(ips)
         if len(vals) >= 2 and i >= args.warmup + 1:
@@ -166,8 +168,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "images/sec (256x256, 1000 DDPM steps)", "value": v, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={args.batch} 256x256, 8x32x32 latent, {args.timesteps} DDPM steps, "
-                               "unconditional (BASELINE.json configs[1])", "impl": "CPU oracle port of the reference"},
+        "config": {"workload": f"batch={args.batch} 256x256, 8x32x32 latent, {args.timesteps} DDPM steps, " +
+                               ("2-class conditional, guidance 1 (BASELINE.json configs[2] shape)" if args.gpus > 1
+                                else "unconditional (BASELINE.json configs[1])"),
+                   "impl": "CPU oracle port of the reference (rank 0 only)"},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
