@@ -646,15 +646,8 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   p.sk_flags = sc.flags;
   // persistent grid: one CTA group per SM (pair); stream-K splits the (tile, K block) units evenly over the groups.
   // With stream-K off every tile gets its own group (classic one-tile-per-CTA launch).
-  // Layers with fewer tiles than SM pairs (the 8x8 level of the UNet: 32-64 tiles for 74 pairs) still use every pair:
-  // the K range of a tile is then shared by several groups (each keeps >= 4 K blocks), the owner adds their partials.
   int groups = p.num_tiles;
-  if (g_stream_k) {
-    const int max_groups = sc.max_ctas / cg;
-    const long long nkb = static_cast<long long>(p.ntaps) * ((d.C0 + d.C1) / kTcBlockK);
-    const long long by_work = std::max<long long>(p.num_tiles, p.num_tiles * nkb / 4);
-    groups = static_cast<int>(std::min<long long>(max_groups, by_work));
-  }
+  if (g_stream_k) groups = std::min(p.num_tiles, sc.max_ctas / cg);
   MF_REQUIRE(groups * cg <= sc.max_ctas || !g_stream_k, "stream-K grid exceeds the scratch allocation");
   if (!g_stream_k && groups * cg > sc.max_ctas) {
     // scratch is indexed by blockIdx.x; without stream-K no partials are ever written, any grid size is fine
