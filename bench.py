@@ -330,7 +330,7 @@ def main():
             "gpu_launches": launches_per_sample * args.steps,
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": "mf::conv_tc_kernel (tcgen05 kind::f16, fp16x3 split, 49 of 51 UNet convs)",
+                "kernel": "mf::conv_tc_kernel (tcgen05 kind::f16, fp16x3 split, 50 of 51 UNet convs)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); the fp32-accurate 3-term "
