@@ -58,7 +58,9 @@ class _StepGraph:
         torch.cuda.current_stream(x.device).wait_stream(side)
         torch.cuda.set_rng_state(rng, x.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread-local capture mode: host threads of the caller (e.g. the PNG writers of sample_dataset, which wait on
+        # CUDA events while the next chunk is being sampled) must not invalidate this capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             body()
         # the captured launches point into the estimator's workspace for this shape and at its prepared weights:
         # keep the former alive with the graph, remember the version of the latter
