@@ -27,13 +27,6 @@ def chunks(lst, n):
         yield lst[i:i + n]
 
 
-def to_uint8_hwc(images):
-    """Host restatement of sample_dataset.py:47-50 for fp32 NCHW images (checker for the fused epilogue)."""
-    x = images.detach().float().clamp(-1, 1)
-    x = (x + 1) / 2 * 255
-    return x.permute(0, 2, 3, 1).to(torch.uint8)
-
-
 def _save_png(arr, path):
     from PIL import Image  # sample_dataset.py:7,51-52
     if arr.shape[-1] == 1:

@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""Bring-up helper: run odd-batch cases one per subprocess; re-run failing ones under compute-sanitizer.
-usage: python tools/ragged_check.py            (driver)   |   python tools/ragged_check.py --case NAME"""
+"""Bring-up helper (test infrastructure, not collected by pytest): run odd-batch cases one per subprocess; re-run failing
+ones — or those named in $SANITIZE — under compute-sanitizer memcheck.
+usage: python tests/ragged_check.py            (driver)   |   python tests/ragged_check.py --case NAME"""
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]   # test_gpu_models imports the oracle
 
 CASES = ["vae_small_encode", "unet_attn_b3", "unet_canon_b5", "unet_small_b3", "unet_small_b1", "vae_small_b3", "vae_small_b3_u8", "pipe_b3_eager",
          "pipe_b3_graph", "pipe_b1_graph", "dataset"]

@@ -265,7 +265,8 @@ def test_generate_dataset_chunks_match_sample_plus_host_conversion(tmp_path):
     one manual_seed, chunks of `sample_batch` (ragged tail), clip/scale/HWC/uint8, files fake_{counter}.png."""
     import numpy as np
     from PIL import Image
-    from medfusion_b200.sample_dataset import chunks, generate_dataset, to_uint8_hwc
+    from medfusion_b200.sample_dataset import chunks, generate_dataset
+    from util import to_uint8_hwc
     g = load_golden("sample_small.pt")
     pipe = _make_pipe(g)
     n = generate_dataset(pipe, 7, tmp_path, label=1, steps=4, guidance_scale=1, sample_batch=3, workers=3)

@@ -4,7 +4,8 @@ import pytest
 import torch
 
 from util import load_golden  # noqa: F401  (path setup)
-from medfusion_b200.sample_dataset import chunks, generate_dataset, to_uint8_hwc
+from medfusion_b200.sample_dataset import chunks, generate_dataset
+from util import to_uint8_hwc
 
 
 def test_chunks_like_the_reference_script():

@@ -52,3 +52,10 @@ def make_vae(cfg, device=None):
     from medfusion_b200.synthetic import fill_
     m = fill_(VAE(**cfg))
     return m.to(device) if device is not None else m
+
+
+def to_uint8_hwc(images):
+    """Host restatement of scripts/helpers/sample_dataset.py:47-50 for fp32 NCHW images (checker for the fused uint8 head)."""
+    x = images.detach().float().clamp(-1, 1)
+    x = (x + 1) / 2 * 255
+    return x.permute(0, 2, 3, 1).to(torch.uint8)
