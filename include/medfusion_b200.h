@@ -15,7 +15,15 @@
  *                        (estimate_x_t_prior_from_x_T / _x_0, estimate_x_0, estimate_mean_t,
  *                        estimate_variance_t) + diffusion_pipeline.py:240-244 (CFG combine)
  *                        + diffusion_pipeline.py:297-304 (DDIM-form re-noise)
+ *   mf_unet_forward_step <- the per-timestep body of DiffusionPipeline.denoise, pipelines/diffusion_pipeline.py:290-304
+ *                        (estimator + forward()'s scheduler dispatch :264-273 + DDIM re-noise) in one call
+ *   mf_sched_step_opts <- the learned-variance / cold-diffusion branches, diffusion_pipeline.py:246-262 and
+ *                        gaussian_scheduler.py:61-77,88-116
+ *   mf_vae_decode_u8  <- VAE.decode + the uint8 conversion of scripts/helpers/sample_dataset.py:47-50
+ *   mf_vae_encode     <- medical_diffusion/models/embedders/latent_embedders.py:756-762 VAE.encode (+ :20-33 quantizer)
  *   mf_op_*           <- the individual torch ops those functions are made of (test surface)
+ *
+ * ABI version 2 (mf_abi_version): v1 + mf_vae_config.in_channels, mf_sched_step_opts, mf_vae_encode*, mf_set_pdl.
  */
 #ifndef MEDFUSION_B200_H_
 #define MEDFUSION_B200_H_
