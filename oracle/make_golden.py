@@ -300,6 +300,27 @@ def vae_encode_fixture():
     print("vae encode", float(z.abs().max()), float(mom.abs().max()), float(emb_loss), len(out_hor))
 
 
+UNET_CONFIG4 = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
+                    strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
+                    cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False,
+                    use_res_block=True, use_attention=["none", "none", "none", "spatial"])
+
+
+@torch.no_grad()
+def config4_fixture():
+    """BASELINE.json configs[3] estimator (8x64x64 latent, spatial attention at the deepest level), one forward at B=1;
+    same inputs as tests/test_gpu_models.py::test_config4_shapes_attention_at_64x64_latent_vs_oracle."""
+    m = make_unet(UNET_CONFIG4)
+    g = gen(4)
+    x = torch.randn(1, 8, 64, 64, generator=g)
+    t = torch.tensor([321])
+    c = torch.tensor([1])
+    y, _ = m(x, t, c)
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    torch.save(dict(cfg=UNET_CONFIG4, x=x, t=t, cond=c, y=y, keys=keys), os.path.join(OUT, "unet_config4.pt"))
+    print("config4", float(y.abs().max()), len(keys))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     unet_fixture("unet_small.pt", UNET_SMALL, 1)
@@ -311,5 +332,6 @@ if __name__ == "__main__":
     ckpt_fixture()
     opts_fixture()
     vae_encode_fixture()
+    config4_fixture()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

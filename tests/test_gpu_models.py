@@ -217,7 +217,8 @@ def test_cuda_graph_sampling_equals_eager(use_ddim, cfg):
 
 def test_config4_shapes_attention_at_64x64_latent_vs_oracle():
     """BASELINE.json configs[3]: 8x64x64 latent, canonical widths, use_attention=['none','none','none','spatial']
-    (6 SpatialTransformer sites, 256 tokens, d = 128 / 64) — one forward at B=1 against the CPU oracle."""
+    (6 SpatialTransformer sites, 256 tokens, d = 128 / 64) — one forward at B=1 against the CPU oracle, which
+    tests/test_oracle_golden.py pins to the unmodified reference on exactly these inputs (tests/golden/unet_config4.pt)."""
     cfg = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
                strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
                cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False, use_res_block=True,
