@@ -97,3 +97,34 @@ def test_best_checkpoint_and_load_weights_helpers(tmp_path):
     fresh.load_pretrained(run)
     assert torch.equal(fresh.state_dict()["inc_dec.block_seq.0.basic_block.conv.weight"],
                        ref.state_dict()["inc_dec.block_seq.0.basic_block.conv.weight"])
+
+
+def test_legacy_serialization_and_unknown_classes_in_containers(tmp_path):
+    """Old (non-zip) torch.save files go through pickle_module.load; classes that cannot be imported — wherever they sit
+    in the hyper-parameter tree — become inert placeholders instead of import errors."""
+    import pickle
+    import types
+
+    mod = types.ModuleType("pytorch_lightning_fake_callbacks")
+
+    class ModelCheckpoint:                      # stands in for a training-side class absent at sampling time
+        def __init__(self, monitor):
+            self.monitor = monitor
+    ModelCheckpoint.__module__ = mod.__name__
+    ModelCheckpoint.__qualname__ = "ModelCheckpoint"
+    mod.ModelCheckpoint = ModelCheckpoint
+    sys.modules[mod.__name__] = mod
+    try:
+        obj = {"state_dict": {"w": torch.arange(4.0)},
+               "hyper_parameters": {"callbacks": [ModelCheckpoint("val/loss")], "loss": torch.nn.L1Loss, "lr": 1e-4}}
+        torch.save(obj, tmp_path / "legacy.ckpt", _use_new_zipfile_serialization=False)
+        torch.save(obj, tmp_path / "zip.ckpt")
+    finally:
+        del sys.modules[mod.__name__]
+    for name in ("legacy.ckpt", "zip.ckpt"):
+        with pytest.raises((ModuleNotFoundError, AttributeError, pickle.UnpicklingError)):
+            torch.load(tmp_path / name, weights_only=False)                       # the stock loader cannot resolve it
+        ck = load_checkpoint(tmp_path / name)
+        assert torch.equal(ck["state_dict"]["w"], torch.arange(4.0))
+        hp = ck["hyper_parameters"]
+        assert is_placeholder(hp["callbacks"][0]) and hp["loss"] is torch.nn.L1Loss and hp["lr"] == 1e-4
