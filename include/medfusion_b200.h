@@ -24,6 +24,7 @@
  *   mf_op_*           <- the individual torch ops those functions are made of (test surface)
  *
  * ABI version 2 (mf_abi_version): v1 + mf_vae_config.in_channels, mf_sched_step_opts, mf_vae_encode*, mf_set_pdl.
+ * ABI version 3: v2 + mf_saturation_count, mf_vqvae_* (VQVAE.decode), mf_unet_forward_step2 (CFG as one 2B batch).
  */
 #ifndef MEDFUSION_B200_H_
 #define MEDFUSION_B200_H_
@@ -44,6 +45,11 @@ typedef void* mf_stream_t; /* cudaStream_t */
  * ---------------------------------------------------------------------------------------------- */
 const char* mf_last_error(void);
 int mf_abi_version(void);
+/* Sticky saturation counter (ABI v3).  Activations travel between kernels as fp16 hi/lo planes; the reference computes
+ * in fp32 range.  Every value that had to be clamped to +-65504 (or was not finite) when a kernel wrote split planes is
+ * counted on the device.  Synchronises `stream`, returns the count since the last reset on the CURRENT device; a
+ * non-zero count means results from that point on are not the reference's (the Python layer raises). */
+int mf_saturation_count(unsigned long long* out_count, int reset, mf_stream_t stream);
 /* Default TMEM drain interval used by the engines' tensor-core convolutions (see mf_op_conv_tc). */
 int mf_set_drain_interval(int k_blocks);
 /* tcgen05 convolutions: 1 = one CTA per 128-pixel tile, 2 = CTA pairs (cta_group::2, 256-row MMA), 0 = auto.

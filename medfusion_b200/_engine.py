@@ -10,8 +10,15 @@ from . import _lib
 from ._params import build_param_tree, param_signature
 
 
-def cuda_stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def cuda_stream_ptr(device=None) -> int:
+    """Raw handle of torch's current stream ON `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(t: torch.Tensor):
+    """Context manager making `t`'s device current: the C side allocates (weights, stream-K scratch) and launches on the
+    current device, so every engine call runs under the device of the tensors it was handed."""
+    return torch.cuda.device(t.device)
 
 
 def require_cuda(t: torch.Tensor, what: str):
@@ -69,15 +76,21 @@ class EngineModule(nn.Module):
             return
         lib = _lib.load()
         sd = dict(self.named_parameters())
-        stream = cuda_stream_ptr()
         setter = getattr(lib, f"{self._prefix}_set_param")
-        for name, shape in self._entries:
-            p = sd[name]
-            require_cuda(p, f"parameter {name}")
-            data = p.detach().contiguous()
-            arr = (ctypes.c_int64 * len(shape))(*shape)
-            _lib.check(setter(self._h, name.encode(), data.data_ptr(), arr, len(shape), stream), f"set_param({name})")
-        self._after_param_sync(stream)
+        dev = self.device
+        with torch.cuda.device(dev):
+            stream = cuda_stream_ptr(dev)
+            for name, shape in self._entries:
+                p = sd[name]
+                require_cuda(p, f"parameter {name}")
+                if p.device != dev:
+                    raise RuntimeError(f"parameter {name} is on {p.device}, the module on {dev}: one engine per device")
+                # the engine reads numel*4 bytes: anything but fp32 (e.g. after .half()) is converted, never reinterpreted
+                data = p.detach().to(torch.float32).contiguous()
+                arr = (ctypes.c_int64 * len(shape))(*shape)
+                _lib.check(setter(self._h, name.encode(), data.data_ptr(), arr, len(shape), stream),
+                           f"set_param({name})")
+            self._after_param_sync(stream)
         self._synced_sig = sig
 
     def _after_param_sync(self, stream):
@@ -89,7 +102,7 @@ class EngineModule(nn.Module):
         """Caller-owned scratch for one (B,H,W) plan.  A few recent shapes are kept so that alternating batch sizes
         return to the SAME address (the engine then rebuilds an identical plan, and CUDA graphs captured against it
         stay valid); graph holders additionally keep their tensor alive themselves."""
-        key = (B, H, W, torch.cuda.current_device())
+        key = (B, H, W, self.device.index)
         ws = self._ws.pop(key, None)
         if ws is None:
             nbytes = getattr(_lib.load(), f"{self._prefix}_workspace_bytes")(self._h, B, H, W)
@@ -112,8 +125,9 @@ class EngineModule(nn.Module):
         kinds = (ctypes.c_int * max_ops)()
         flops = (ctypes.c_double * max_ops)()
         n = ctypes.c_int()
-        _lib.check(getattr(_lib.load(), fn_name)(self._h, *head_args, *tail_args, cuda_stream_ptr(), ms, kinds, flops,
-                                                 max_ops, ctypes.byref(n)), fn_name)
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(_lib.load(), fn_name)(self._h, *head_args, *tail_args, cuda_stream_ptr(self.device), ms,
+                                                     kinds, flops, max_ops, ctypes.byref(n)), fn_name)
         return [(ms[i], kinds[i], flops[i]) for i in range(n.value)]
 
     def plan_info(self):

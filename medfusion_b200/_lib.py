@@ -63,6 +63,7 @@ _P = c_void_p
 SIGNATURES = {
     "mf_last_error": (c_char_p, []),
     "mf_abi_version": (c_int, []),
+    "mf_saturation_count": (c_int, [POINTER(ctypes.c_ulonglong), c_int, _P]),
     "mf_set_drain_interval": (c_int, [c_int]),
     "mf_set_cta_group": (c_int, [c_int]),
     "mf_set_block_n": (c_int, [c_int]),

@@ -6,9 +6,11 @@ whose `hyper_parameters` pickle *class objects* by qualified name (`medical_diff
 `torch.optim.AdamW`, `torch.nn.L1Loss`, sometimes `lpips.LPIPS` / `pytorch_lightning.*`).  None of Lightning, MONAI or
 the reference package is needed here: `load_checkpoint` unpickles with a resolver that
   * maps `medical_diffusion.*` classes to this package's class of the same name,
-  * resolves anything importable (torch.*, collections, numpy) normally,
-  * and replaces everything else (training-side losses, Lightning callbacks) by an inert placeholder class,
-so the file loads without executing or importing training-side code.  `CheckpointMixin` gives the modules the
+  * resolves an allow-list normally (torch.*, collections, numpy, pathlib and plain builtin containers),
+  * and replaces everything else (training-side losses, Lightning callbacks, and any other importable global such as
+    os.system or builtins.eval) by an inert placeholder class,
+so the file loads without importing training-side code and without resolving arbitrary callables.  This narrows, but does
+not remove, the usual pickle caveat: load checkpoints you trust.  `CheckpointMixin` gives the modules the
 reference's loader methods with the reference's names and argument meaning.
 """
 from __future__ import annotations
@@ -60,10 +62,33 @@ def _resolve_reference_class(module, name):
     return _placeholder(module, name)
 
 
+# Globals a Lightning checkpoint of the reference legitimately contains: tensor rebuild helpers, containers, optimizer /
+# loss / module CLASSES stored in `hyper_parameters` (only constructed if this package's constructors ask for them).
+# Anything else (os.system, builtins.eval, subprocess.Popen, ...) resolves to an inert placeholder instead of being
+# imported, so unpickling cannot call into arbitrary code.
+_ALLOWED_MODULE_PREFIXES = ("torch", "collections", "numpy", "pathlib", "argparse", "datetime", "functools",
+                            "medfusion_b200")   # this package's own classes (checkpoints re-saved through it)
+_ALLOWED_BUILTINS = {"set", "frozenset", "slice", "tuple", "list", "dict", "int", "float", "bool", "str", "bytes",
+                     "bytearray", "complex", "range", "object", "type"}
+_FORBIDDEN = {("torch", "load"), ("torch", "save"), ("torch.serialization", "load"), ("functools", "partial"),
+              ("torch.utils.cpp_extension", "load"), ("torch.hub", "load")}
+
+
+def _allowed(module, name):
+    if (module, name) in _FORBIDDEN:
+        return False
+    if module in ("builtins", "__builtin__"):
+        return name in _ALLOWED_BUILTINS
+    root = module.split(".", 1)[0]
+    return root in _ALLOWED_MODULE_PREFIXES
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == "medical_diffusion" or module.startswith("medical_diffusion."):
             return _resolve_reference_class(module, name)
+        if not _allowed(module, name):
+            return _placeholder(module, name)
         try:
             return super().find_class(module, name)
         except (ImportError, AttributeError):

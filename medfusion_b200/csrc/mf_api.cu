@@ -494,6 +494,7 @@ int mf_vae_enc_plan::build(int B, int H, int W, char* ws, bool dry_run, cudaStre
 // =================================================================================================
 template <class E>
 static int prepare_plan(E* h, int B, int H, int W, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (int rcd = h->bind_device()) return rcd;
   if (h->key.B == B && h->key.H == H && h->key.W == W && h->key.base == ws && h->key.version == h->version) return 0;
   // dry run for the size check
   int rc = h->build(B, H, W, nullptr, true, s);
@@ -519,7 +520,17 @@ static int prepare_plan(E* h, int B, int H, int W, void* ws, size_t ws_bytes, cu
 extern "C" {
 
 const char* mf_last_error(void) { return mf::get_error(); }
-int mf_abi_version(void) { return 2; }
+int mf_abi_version(void) { return 3; }
+int mf_saturation_count(unsigned long long* out_count, int reset, mf_stream_t stream) {
+  MF_REQUIRE(out_count != nullptr, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned long long total = 0;
+  int rc = sat_read_kernels(&total, reset, s);
+  if (rc == 0) rc = sat_read_conv_tc(&total, reset, s);
+  if (rc == 0) rc = sat_read_attn(&total, reset, s);
+  *out_count = total;
+  return rc;
+}
 int mf_set_debias_eps(float eps_per_kblock) {
   mf::g_debias_eps_per_kblock = eps_per_kblock;
   return 0;

@@ -267,4 +267,6 @@ int add_channel_bias_split(const __half* in, long long in_plane, const float* bi
   return 0;
 }
 
+MF_DEFINE_SATURATION_READER(sat_read_attn)
+
 }  // namespace mf

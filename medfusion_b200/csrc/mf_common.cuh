@@ -48,19 +48,44 @@ const char* get_error();
 // pre-scaled by a power of two so that their lo parts stay in fp16's normal range.
 // ------------------------------------------------------------------------------------------------
 typedef __half sp_t;  // element type of the split (hi / lo) planes
+// Sticky saturation counter.  The reference computes in fp32 range; the split planes are fp16, so a value beyond
+// +-65504 (or a non-finite one) is clamped and parity is lost from there on.  Every clamp bumps this counter (one
+// instance per translation unit: the library is built without relocatable device code; mf_saturation_count sums
+// them), so the caller can tell that a result left the representable range instead of silently getting a wrong one.
+static __device__ unsigned int g_mf_saturated = 0;
+__device__ __forceinline__ float sat16(float x) {
+  const float c = fminf(fmaxf(x, -65504.f), 65504.f);
+  if (c != x) atomicAdd(&g_mf_saturated, 1u);   // also true for NaN (fmaxf(NaN, a) = a)
+  return c;
+}
 __device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-  lo = __float2half_rn(fminf(fmaxf(x - __half2float(hi), -65504.f), 65504.f));  // only clamps when hi saturated
+  const float xc = sat16(x);
+  hi = __float2half_rn(xc);
+  lo = __float2half_rn(xc - __half2float(hi));   // |lo| <= 2^-11 |hi|: always in range
 }
 // two values at once: packed conversions (cvt.rn.f16x2.f32), same results as split16 on each
 __device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
-  const float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
+  const float ac = sat16(a), bc = sat16(b);
   const __half2 h = __floats2half2_rn(ac, bc);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(fminf(fmaxf(a - hf.x, -65504.f), 65504.f), fminf(fmaxf(b - hf.y, -65504.f), 65504.f));
+  const __half2 l = __floats2half2_rn(ac - hf.x, bc - hf.y);
   hi2 = *reinterpret_cast<const uint32_t*>(&h);
   lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
+// host side of the counter: defined once per translation unit that launches kernels using split16
+#define MF_DEFINE_SATURATION_READER(fn)                                                                     \
+  int fn(unsigned long long* total, int reset, cudaStream_t s) {                                            \
+    unsigned int v = 0;                                                                                     \
+    MF_CUDA_OK(cudaMemcpyFromSymbolAsync(&v, g_mf_saturated, sizeof(v), 0, cudaMemcpyDeviceToHost, s));     \
+    MF_CUDA_OK(cudaStreamSynchronize(s));                                                                   \
+    if (reset && v != 0) {                                                                                  \
+      const unsigned int z = 0;                                                                             \
+      MF_CUDA_OK(cudaMemcpyToSymbolAsync(g_mf_saturated, &z, sizeof(z), 0, cudaMemcpyHostToDevice, s));     \
+      MF_CUDA_OK(cudaStreamSynchronize(s));                                                                 \
+    }                                                                                                       \
+    *total += v;                                                                                            \
+    return 0;                                                                                               \
+  }
 __device__ __forceinline__ float join16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 // four consecutive channels: 8-byte vector accesses on both planes
 __device__ __forceinline__ float4 ld_join4(const __half* hi, const __half* lo) {

@@ -495,25 +495,36 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 }
 
 // stream-K scratch: one [128][256] fp32 partial tile and one flag per CTA of the persistent grid
-struct StreamKScratch {
-  float* partials = nullptr;
-  int* flags = nullptr;
-  int max_ctas = 0;
-};
-static int get_streamk_scratch(StreamKScratch* out) {
-  static StreamKScratch sc;
+int streamk_scratch_alloc(StreamKScratch* sc) {
+  int dev = 0, sms = 0;
+  MF_CUDA_OK(cudaGetDevice(&dev));
+  MF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  sc->max_ctas = sms;
+  sc->device = dev;
+  MF_CUDA_OK(cudaMalloc(&sc->partials, static_cast<size_t>(sms) * kTcBlockM * 256 * sizeof(float)));
+  MF_CUDA_OK(cudaMalloc(&sc->flags, static_cast<size_t>(sms) * sizeof(int)));
+  MF_CUDA_OK(cudaMemset(sc->flags, 0, static_cast<size_t>(sms) * sizeof(int)));
+  return 0;
+}
+void streamk_scratch_free(StreamKScratch* sc) {
+  if (sc->partials) cudaFree(sc->partials);
+  if (sc->flags) cudaFree(sc->flags);
+  *sc = StreamKScratch();
+}
+// library-owned scratch for stand-alone mf_op_* launches: one per device (never shared across devices; launches that
+// use it must be stream-ordered with each other, which the single-stream test surface is)
+static int get_streamk_scratch(const StreamKScratch** out) {
   static std::mutex mu;
+  static StreamKScratch per_device[64];
   std::lock_guard<std::mutex> lock(mu);
-  if (sc.partials == nullptr) {
-    int dev = 0, sms = 0;
-    MF_CUDA_OK(cudaGetDevice(&dev));
-    MF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    sc.max_ctas = sms;
-    MF_CUDA_OK(cudaMalloc(&sc.partials, static_cast<size_t>(sms) * kTcBlockM * 256 * sizeof(float)));
-    MF_CUDA_OK(cudaMalloc(&sc.flags, static_cast<size_t>(sms) * sizeof(int)));
-    MF_CUDA_OK(cudaMemset(sc.flags, 0, static_cast<size_t>(sms) * sizeof(int)));
+  int dev = 0;
+  MF_CUDA_OK(cudaGetDevice(&dev));
+  MF_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  if (per_device[dev].partials == nullptr) {
+    int rc = streamk_scratch_alloc(&per_device[dev]);
+    if (rc) return rc;
   }
-  *out = sc;
+  *out = &per_device[dev];
   return 0;
 }
 
@@ -637,11 +648,12 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   p.m_groups = (m_tiles + cg - 1) / cg;
   p.n_tiles = d.Cout / bn;
   p.num_tiles = p.m_groups * p.n_tiles * (d.up2 ? 4 : 1);
-  StreamKScratch sc;
-  {
-    int rcs = get_streamk_scratch(&sc);
+  const StreamKScratch* scp = d.scratch;
+  if (scp == nullptr) {
+    int rcs = get_streamk_scratch(&scp);
     if (rcs) return rcs;
   }
+  const StreamKScratch& sc = *scp;
   p.sk_partials = sc.partials;
   p.sk_flags = sc.flags;
   // persistent grid: one CTA group per SM (pair); stream-K splits the (tile, K block) units evenly over the groups.
@@ -721,5 +733,7 @@ int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
   set_error("conv_tc_launch: bad block_n / cta_group");
   return 2;
 }
+
+MF_DEFINE_SATURATION_READER(sat_read_conv_tc)
 
 }  // namespace mf

@@ -93,7 +93,21 @@ struct ConvTcDesc {
   int cta_group;            // 0 -> default (auto), 1 or 2
   int block_n;              // 0 -> default (auto), 64 / 128 / 256 output channels per tile
   int up2;                  // 1: input is HxW, output 2Hx2W = conv3x3(nearest_x2(input)); w_planes from prep_weight_up_tc
+  // stream-K scratch owned by the caller (an engine keeps its own, so two engines on different streams or devices never
+  // share partial-sum tiles); nullptr: the per-device scratch of the library (stand-alone mf_op_* calls)
+  const struct StreamKScratch* scratch;
 };
+
+// one [128][256] fp32 partial tile and one flag per CTA of the persistent grid
+struct StreamKScratch {
+  float* partials = nullptr;
+  int* flags = nullptr;
+  int max_ctas = 0;   // SM count of the device the scratch lives on
+  int device = -1;
+};
+// allocate on the CURRENT device (flags zeroed); release with streamk_scratch_free
+int streamk_scratch_alloc(StreamKScratch* sc);
+void streamk_scratch_free(StreamKScratch* sc);
 
 extern int g_default_drain_interval;
 extern int g_default_cta_group;

@@ -49,6 +49,20 @@ void Arena::release(size_t off, size_t bytes) {
   free_list.swap(merged);
 }
 
+// ---- device binding -------------------------------------------------------------------------------
+int EngineBase::bind_device() {
+  int dev = 0;
+  MF_CUDA_OK(cudaGetDevice(&dev));
+  if (device < 0) device = dev;
+  MF_REQUIRE(device == dev, "this engine handle lives on device " + std::to_string(device) + " but the current device is " +
+                                std::to_string(dev) + " (one handle per device; set the device before calling)");
+  return 0;
+}
+const StreamKScratch* EngineBase::scratch() {
+  if (sk_scratch.partials == nullptr && streamk_scratch_alloc(&sk_scratch) != 0) return nullptr;
+  return &sk_scratch;
+}
+
 // ---- parameters ----------------------------------------------------------------------------------
 Param* EngineBase::add_param(const std::string& name, std::vector<int64_t> shape) {
   params.emplace_back(new Param());
@@ -65,6 +79,7 @@ int EngineBase::set_param(const char* name, const float* d_data, const int64_t* 
     set_error(std::string("unknown parameter '") + name + "'");
     return 2;
   }
+  if (int rcd = bind_device()) return rcd;
   Param* p = it->second;
   bool same = static_cast<int>(p->shape.size()) == ndim;
   for (int i = 0; same && i < ndim; ++i) same = p->shape[i] == shape[i];
@@ -230,6 +245,8 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
       d.res = res->ptr; d.res_plane = res->plane; d.res_kind = res->layout == kNHWCSplit ? 1 : 2;
     }
     d.emb = emb; d.emb_stride = emb_stride;
+    d.scratch = scratch();
+    MF_REQUIRE(d.scratch != nullptr, "stream-K scratch allocation failed");
     tc_plans.emplace_back(new ConvTcPlan());
     ConvTcPlan* plan = tc_plans.back().get();
     rc = conv_tc_build(d, plan);
@@ -288,6 +305,8 @@ int EngineBase::add_upconv2x(ConvLayer& L, const Tens& in, Tens* out) {
     d.Cout = L.Cout; d.ksize = 3;
     d.bias = L.b->data.p;
     d.out = o.ptr; d.out_plane = o.plane; d.out_mode = kOutSplit;
+    d.scratch = scratch();
+    MF_REQUIRE(d.scratch != nullptr, "stream-K scratch allocation failed");
     tc_plans.emplace_back(new ConvTcPlan());
     ConvTcPlan* plan = tc_plans.back().get();
     int rc = conv_tc_build(d, plan);
@@ -337,6 +356,8 @@ int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, i
       d.bias = L.b->data.p;
       d.out = out.ptr; d.out_plane = out.plane; d.out_mode = out.layout == kNHWCSplit ? kOutSplit : kOutRaw;
       d.stats = stats ? stats->ptr : nullptr;
+      d.scratch = scratch();
+      MF_REQUIRE(d.scratch != nullptr, "stream-K scratch allocation failed");
       tc_plans.emplace_back(new ConvTcPlan());
       ConvTcPlan* plan = tc_plans.back().get();
       rc = conv_tc_build(d, plan);

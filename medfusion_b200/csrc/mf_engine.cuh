@@ -121,7 +121,13 @@ struct OpMeta { int kind; double flops; };
 
 class EngineBase {
  public:
-  virtual ~EngineBase() = default;
+  virtual ~EngineBase() { streamk_scratch_free(&sk_scratch); }
+  // stream-K partial tiles of THIS engine's convolutions, on the device the engine first ran on (a process-
+  // global scratch was shared by every engine, stream and device)
+  StreamKScratch sk_scratch;
+  int device = -1;     // device the parameters / plans live on (set by the first set_param / build)
+  int bind_device();   // records the current device on first use, errors if a later call runs on another one
+  const StreamKScratch* scratch();
   std::vector<std::unique_ptr<Param>> params;
   std::map<std::string, Param*> by_name;
   int version = 0;  // bumped by set_param; invalidates derived weight layouts and plans

@@ -981,4 +981,6 @@ int sched_step(const SchedStepDesc& d, cudaStream_t s) {
   return 0;
 }
 
+MF_DEFINE_SATURATION_READER(sat_read_kernels)
+
 }  // namespace mf

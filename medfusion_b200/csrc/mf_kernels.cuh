@@ -122,4 +122,9 @@ struct HeadDesc {
 // step != nullptr: every output element is fed to the scheduler update as `pred` (step->pred is ignored)
 int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s);
 
+// saturation counters of the three kernel translation units (see mf_common.cuh); *total is incremented
+int sat_read_kernels(unsigned long long* total, int reset, cudaStream_t s);
+int sat_read_conv_tc(unsigned long long* total, int reset, cudaStream_t s);
+int sat_read_attn(unsigned long long* total, int reset, cudaStream_t s);
+
 }  // namespace mf

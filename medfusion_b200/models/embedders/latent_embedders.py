@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from ... import _lib
-from ..._engine import EngineModule, cuda_stream_ptr, require_cuda
+from ..._engine import EngineModule, cuda_stream_ptr, on_device, require_cuda
 from ...checkpoint import CheckpointMixin
 
 # training-side entries of a reference VAE state_dict (deep-supervision heads, LPIPS, loss modules)
@@ -95,9 +95,10 @@ class VAE(CheckpointMixin, EngineModule):
         zc = z.contiguous().float()
         x = torch.empty((B, self.out_channels, H * self.up_factor, W * self.up_factor), device=z.device,
                         dtype=torch.float32)
-        ws, ws_bytes = self._workspace(B, H, W)
-        _lib.check(_lib.load().mf_vae_decode(self._h, zc.data_ptr(), x.data_ptr(), B, H, W, ws, ws_bytes,
-                                             cuda_stream_ptr()), "mf_vae_decode")
+        with on_device(zc):
+            ws, ws_bytes = self._workspace(B, H, W)
+            _lib.check(_lib.load().mf_vae_decode(self._h, zc.data_ptr(), x.data_ptr(), B, H, W, ws, ws_bytes,
+                                                 cuda_stream_ptr(zc.device)), "mf_vae_decode")
         return x
 
     def decode_uint8(self, z, also_float=False):
@@ -110,10 +111,11 @@ class VAE(CheckpointMixin, EngineModule):
         Ho, Wo = H * self.up_factor, W * self.up_factor
         img = torch.empty((B, Ho, Wo, self.out_channels), device=z.device, dtype=torch.uint8)
         x = torch.empty((B, self.out_channels, Ho, Wo), device=z.device, dtype=torch.float32) if also_float else None
-        ws, ws_bytes = self._workspace(B, H, W)
-        _lib.check(_lib.load().mf_vae_decode_u8(self._h, zc.data_ptr(), None if x is None else x.data_ptr(),
-                                                img.data_ptr(), B, H, W, ws, ws_bytes, cuda_stream_ptr()),
-                   "mf_vae_decode_u8")
+        with on_device(zc):
+            ws, ws_bytes = self._workspace(B, H, W)
+            _lib.check(_lib.load().mf_vae_decode_u8(self._h, zc.data_ptr(), None if x is None else x.data_ptr(),
+                                                    img.data_ptr(), B, H, W, ws, ws_bytes, cuda_stream_ptr(zc.device)),
+                       "mf_vae_decode_u8")
         return (img, x) if also_float else img
 
     def profile(self, z):
@@ -140,19 +142,22 @@ class VAE(CheckpointMixin, EngineModule):
         # DiagonalGaussianDistribution.forward (latent_embedders.py:26): torch.randn(mean.shape, device=x.device)
         noise = torch.randn(z.shape, device=x.device) if sample else None
         mom = torch.empty((B, 2 * self.emb_channels, H // f, W // f), device=x.device) if want_moments else None
-        key = ("enc", B, H, W, torch.cuda.current_device())
+        key = ("enc", B, H, W, x.device.index)
         ws = self._enc_ws.get(key)
         if ws is None:
-            nbytes = _lib.load().mf_vae_encode_workspace_bytes(self._h, B, H, W)
+            with on_device(xc):
+                nbytes = _lib.load().mf_vae_encode_workspace_bytes(self._h, B, H, W)
             if nbytes == 0:
                 _lib.check(2, "mf_vae_encode_workspace_bytes")
             self._enc_ws.clear()
             ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
             self._enc_ws[key] = ws
         off = (-ws.data_ptr()) % 1024
-        _lib.check(_lib.load().mf_vae_encode(self._h, xc.data_ptr(), None if noise is None else noise.data_ptr(),
-                                             z.data_ptr(), None if mom is None else mom.data_ptr(), B, H, W,
-                                             ws.data_ptr() + off, ws.numel() - off, cuda_stream_ptr()), "mf_vae_encode")
+        with on_device(xc):
+            _lib.check(_lib.load().mf_vae_encode(self._h, xc.data_ptr(), None if noise is None else noise.data_ptr(),
+                                                 z.data_ptr(), None if mom is None else mom.data_ptr(), B, H, W,
+                                                 ws.data_ptr() + off, ws.numel() - off, cuda_stream_ptr(xc.device)),
+                       "mf_vae_encode")
         return z, mom
 
     def encode(self, x):

@@ -13,7 +13,7 @@ import ctypes
 import torch
 
 from ... import _lib
-from ..._engine import EngineModule, cuda_stream_ptr, require_cuda
+from ..._engine import EngineModule, cuda_stream_ptr, on_device, require_cuda
 from ..embedders import TimeEmbbeding
 
 
@@ -76,6 +76,7 @@ class UNet(EngineModule):
         self.num_res_blocks = num_res_blocks
         self.in_ch, self.out_ch = in_ch, out_ch
         self.estimate_variance = estimate_variance
+        self._hid0, self._k0, self._s0 = int(hid_chs[0]), int(kernel_sizes[0]), int(strides[0])
 
         self.time_spec = time_embedder(**dict(time_embedder_kwargs or {})) if time_embedder is not None else None
         self.cond_spec = cond_embedder(**dict(cond_embedder_kwargs or {})) if cond_embedder is not None else None
@@ -118,6 +119,7 @@ class UNet(EngineModule):
         if self.time_spec is not None and t is None:
             raise NotImplementedError("t=None with a time embedder is not supported")
         self.sync_params()
+        self._check_inputs(x_t, t, condition)
         B, _, H, W = x_t.shape
         x = x_t.contiguous().float()
         if self.use_self_conditioning:
@@ -133,13 +135,36 @@ class UNet(EngineModule):
         self._forward_into(x, tt, cc, y)
         return y, []
 
+    def _check_inputs(self, x_t, t, condition):
+        """The kernels index the embedding table with `condition` and the sinusoid / scheduler tables with `t`: out-of-range
+        values would read out of bounds where nn.Embedding / gather raise in the reference.  One host check per public
+        call (skipped while a CUDA graph is being captured: the captured values were checked by the warm-up call)."""
+        if x_t.device != self.device:
+            raise RuntimeError(f"input on {x_t.device}, module on {self.device}")
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if condition is not None and self.cond_spec is not None:
+            lo, hi = int(condition.min()), int(condition.max())
+            if lo < 0 or hi >= self.cond_spec.num_classes:
+                raise IndexError(f"condition values must be in [0, {self.cond_spec.num_classes}), got [{lo}, {hi}]")
+        if t is not None and torch.is_tensor(t) and t.numel() > 0 and int(t.min()) < 0:
+            raise IndexError("timesteps must be >= 0")
+
+    def supports_fused_step(self):
+        """Mirror of the C-side requirements of mf_unet_forward_step (narrow 1x1 head with the scheduler update in its
+        epilogue): out_ch <= 8, first level a multiple of 64 channels, odd stem kernel with stride 1, no learned
+        variance, x_t and the estimate of the same channel count."""
+        return (self.out_ch <= 8 and not self.estimate_variance and not self.use_self_conditioning
+                and self._hid0 % 64 == 0 and self._k0 % 2 == 1 and self._s0 == 1 and self.in_ch == self.out_ch)
+
     def _forward_into(self, x, t, cond, y):
         """Hot-loop entry: contiguous CUDA tensors of the right dtype, no checks, no parameter sync."""
         B, _, H, W = x.shape
-        ws, ws_bytes = self._workspace(B, H, W)
-        _lib.check(_lib.load().mf_unet_forward(self._h, x.data_ptr(), None if t is None else t.data_ptr(),
-                                               None if cond is None else cond.data_ptr(), y.data_ptr(), B, H, W, ws,
-                                               ws_bytes, cuda_stream_ptr()), "mf_unet_forward")
+        with on_device(x):
+            ws, ws_bytes = self._workspace(B, H, W)
+            _lib.check(_lib.load().mf_unet_forward(self._h, x.data_ptr(), None if t is None else t.data_ptr(),
+                                                   None if cond is None else cond.data_ptr(), y.data_ptr(), B, H, W, ws,
+                                                   ws_bytes, cuda_stream_ptr(x.device)), "mf_unet_forward")
 
     def forward_step(self, x_t, t, condition, scheduler, *, pred_uncond=None, guidance_scale=1.0, noise=None,
                      t_next=None, noise_ddim=None, objective="x_T", clip_x0=True, want=("x_next",), want_pred=False,
@@ -171,10 +196,11 @@ class UNet(EngineModule):
                              ptr(keep[2]), 1 if objective == "x_0" else 0, 1 if clip_x0 else 0,
                              ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")),
                              1 if uniform_t else 0)
-        ws, ws_bytes = self._workspace(B, H, W)
-        _lib.check(_lib.load().mf_unet_forward_step(self._h, x.data_ptr(), tt.data_ptr(), ptr(cc), ptr(pred), B, H, W, ws,
-                                                    ws_bytes, ctypes.byref(args), cuda_stream_ptr()),
-                   "mf_unet_forward_step")
+        with on_device(x):
+            ws, ws_bytes = self._workspace(B, H, W)
+            _lib.check(_lib.load().mf_unet_forward_step(self._h, x.data_ptr(), tt.data_ptr(), ptr(cc), ptr(pred), B, H, W,
+                                                        ws, ws_bytes, ctypes.byref(args), cuda_stream_ptr(x.device)),
+                       "mf_unet_forward_step")
         if want_pred:
             outs["pred"] = pred
         return outs

@@ -116,11 +116,13 @@ class GaussianNoiseScheduler(BasicNoiseScheduler):
                 opts.sqrt_alphas_cumprod = self.sqrt_alphas_cumprod.data_ptr()
                 opts.sqrt_one_minus_alphas_cumprod = self.sqrt_one_minus_alphas_cumprod.data_ptr()
                 opts.T = int(self.T)
-        _lib.check(_lib.load().mf_sched_step_opts(
-            ctypes.byref(tab), x_t.data_ptr(), pred.data_ptr(), ptr(pred_uncond), float(guidance_scale), t.data_ptr(),
-            ptr(noise), ptr(t_next), ptr(noise_ddim), 1 if objective == "x_0" else 0, 1 if clip_x0 else 0,
-            ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")), B, chw,
-            None if opts is None else ctypes.byref(opts), cuda_stream_ptr()), "mf_sched_step_opts")
+        with torch.cuda.device(x_t.device):
+            _lib.check(_lib.load().mf_sched_step_opts(
+                ctypes.byref(tab), x_t.data_ptr(), pred.data_ptr(), ptr(pred_uncond), float(guidance_scale),
+                t.data_ptr(), ptr(noise), ptr(t_next), ptr(noise_ddim), 1 if objective == "x_0" else 0,
+                1 if clip_x0 else 0, ptr(outs.get("x_prior")), ptr(outs.get("x_0")), ptr(outs.get("x_T")),
+                ptr(outs.get("x_next")), B, chw, None if opts is None else ctypes.byref(opts),
+                cuda_stream_ptr(x_t.device)), "mf_sched_step_opts")
         return outs
 
     # --- reference-named views (gaussian_scheduler.py:80-151) ---------------------------------

@@ -131,6 +131,10 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         self.clip_x0 = clip_x0
         self.use_ema = use_ema
         self.use_cuda_graph = True    # capture one timestep as a CUDA graph inside denoise() (medfusion_b200 extension)
+        # after every denoise(): read the sticky saturation counter of the kernels (one stream sync per call) and raise
+        # FloatingPointError if a value left the fp16 range of the split planes — the reference is fp32-range, so the
+        # result would silently differ from it
+        self.check_saturation = True
         self._step_graphs = {}
         if use_ema:
             # weight selection only (diffusion_pipeline.py:234-237): a second estimator holding the averaged weights under
@@ -182,7 +186,6 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         custom_noise = kwargs.pop("_noise_fn", None)
         graph_ok = kwargs.pop("_cuda_graph", self.use_cuda_graph)
         as_uint8 = kwargs.pop("_uint8", False)
-        noise_fn = custom_noise or self.noise_scheduler.x_final
         unknown = set(kwargs) - {"guidance_scale", "un_cond", "cold_diffusion"}
         if unknown:  # the reference forwards **kwargs to forward(), which raises TypeError on anything else
             raise TypeError(f"forward() got an unexpected keyword argument '{sorted(unknown)[0]}'")
@@ -190,7 +193,30 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         guidance_scale = kwargs.get("guidance_scale", 1.0)
         un_cond = kwargs.get("un_cond", None)
         require_cuda(x_t, "DiffusionPipeline.denoise(x_t)")
+        est0 = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
+        if hasattr(est0, "_check_inputs"):      # label range, once per call (the loop itself never synchronises)
+            est0._check_inputs(x_t, None, condition)
+            if un_cond is not None:
+                est0._check_inputs(x_t, None, un_cond)
+        check_sat = self.check_saturation and not torch.cuda.is_current_stream_capturing()
+        if check_sat:
+            from ... import saturation_count
+            saturation_count(reset=True, device=x_t.device)
+        out = self._denoise(x_t, steps, condition, use_ddim, custom_noise, graph_ok, as_uint8, cold, guidance_scale,
+                            un_cond, kwargs)
+        if check_sat:
+            n_sat = saturation_count(reset=True, device=x_t.device)
+            if n_sat:
+                raise FloatingPointError(
+                    f"medfusion_b200: {n_sat} value(s) exceeded the fp16 range (+-65504) of the split activation planes "
+                    "during denoise(); the reference computes in fp32 range, so this result would not match it "
+                    "(set pipeline.check_saturation = False to get the clamped result)")
+        return out
+
+    def _denoise(self, x_t, steps, condition, use_ddim, custom_noise, graph_ok, as_uint8, cold, guidance_scale, un_cond,
+                 kwargs):
         sched = self.noise_scheduler
+        noise_fn = custom_noise or self.noise_scheduler.x_final
         if use_ddim:
             steps = sched.timesteps if steps is None else steps
             timesteps_array = torch.linspace(0, sched.T - 1, steps, dtype=torch.long, device=x_t.device)
@@ -203,15 +229,18 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         est = self.ema_model.averaged_model if self.use_ema else self.noise_estimator
         # the fused head (+ CUDA graph) covers the canonical configuration; learned variance, self-conditioning and cold
         # diffusion take the estimator + mf_sched_step_opts path below
-        fused = (hasattr(est, "forward_step") and getattr(est, "out_ch", 99) <= 8 and not est.estimate_variance
-                 and not self.use_self_conditioning and not cold)
+        fused = (hasattr(est, "forward_step") and est.supports_fused_step() and not self.use_self_conditioning
+                 and not cold and x_t.shape[1] == est.in_ch)
         cfg = (condition is not None) and (guidance_scale != 1.0)
         # CUDA-graph path: one captured timestep replayed `steps` times (a second capture without the DDIM re-noise
         # for the last step).  Host-side noise injection (tests) cannot be captured -> eager loop below.
         if fused and graph_ok and (custom_noise is None or getattr(custom_noise, "graph_safe", False)) and steps > 2:
             def get_graph(ddim):
+                # a noise function may carry a stable `cache_key` (the sharded one does: (lo, hi, full shape)), so that
+                # repeated sample(shard=True) calls reuse the captured graphs instead of re-capturing
+                nkey = getattr(custom_noise, "cache_key", id(custom_noise))
                 key = (id(est), tuple(x_t.shape), condition is not None, un_cond is not None, float(guidance_scale),
-                       ddim, self.estimator_objective, self.clip_x0, id(custom_noise))
+                       ddim, self.estimator_objective, self.clip_x0, nkey)
                 g = self._step_graphs.get(key)
                 est.sync_params()
                 if g is not None and g.param_sig != est._synced_sig:   # weights changed since the capture
@@ -235,8 +264,8 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
                 import warnings                              # same kernels, just launched one by one
                 warnings.warn(f"medfusion_b200: CUDA-graph capture of the timestep failed ({exc}); running eagerly")
                 self.use_cuda_graph = False
-                return self.denoise(x_t, steps=steps if use_ddim else steps, condition=condition, use_ddim=use_ddim,
-                                    _noise_fn=custom_noise, _cuda_graph=False, _uint8=as_uint8, **kwargs)
+                return self._denoise(x_t, steps, condition, use_ddim, custom_noise, False, as_uint8, cold,
+                                     guidance_scale, un_cond, kwargs)
             g.x.copy_(x_t)
             for i in range(n_main):
                 g.t.copy_(ts[i].expand(B))

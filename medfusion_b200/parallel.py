@@ -26,6 +26,8 @@ def make_sharded_noise_fn(template: torch.Tensor, lo: int, hi: int):
         return torch.randn_like(template)[lo:hi].contiguous()
 
     noise_fn.graph_safe = True   # pure device-side torch ops: may be captured into the per-timestep CUDA graph
+    # stable identity for the CUDA-graph cache of denoise(): a fresh closure per call must not force a re-capture
+    noise_fn.cache_key = ("sharded", lo, hi, tuple(template.shape), str(template.device))
     return noise_fn
 
 

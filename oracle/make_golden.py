@@ -321,17 +321,105 @@ def config4_fixture():
     print("config4", float(y.abs().max()), len(keys))
 
 
+@torch.no_grad()
+def traj_fixture():
+    """Canonical-width 50-step trajectories of the unmodified reference: B=2, injected noise
+    (regenerated from a seed by the test: only the seed is stored), latents only (no decoder).  Every x_t the
+    estimator saw is recorded through a forward pre-hook, so the GPU test can compare free-running snapshots AND do a
+    teacher-forced per-step comparison.
+      ddim50_clip_cond: use_ddim=True, steps=50, clip_x0=True (the ctor default, diffusion_pipeline.py:37), 2-class
+                        condition with guidance_scale=1.  Without clipping a random-weight estimator makes the DDIM
+                        trajectory grow like 1/sqrt(alphas_cumprod) (|x| ~ 6e5 after 50 steps); with the clamp
+                        latents stay O(1) and the absolute tolerance is meaningful.
+      ddpm50:           use_ddim=False, steps=50 (ancestral steps t=49..0), clip_x0=False, unconditional."""
+    cases = {
+        "ddim50_clip_cond": dict(pipe=dict(clip_x0=True), kw=dict(steps=50, use_ddim=True, guidance_scale=1.0),
+                                 cond=torch.tensor([1, 0]), seed=301),
+        "ddpm50": dict(pipe=dict(clip_x0=False), kw=dict(steps=50, use_ddim=False), cond=None, seed=302),
+    }
+    out = {}
+    orig = torch.randn_like
+    for name, c in cases.items():
+        pipe = DiffusionPipeline(noise_scheduler=GaussianNoiseScheduler, noise_estimator=UNet, latent_embedder=None,
+                                 noise_scheduler_kwargs=dict(SCHED),
+                                 noise_estimator_kwargs=dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder,
+                                                             **fresh(UNET_CANON)),
+                                 estimator_objective="x_T", estimate_variance=False, use_self_conditioning=False,
+                                 use_ema=False, do_input_centering=False, **c["pipe"]).eval()
+        fill_(pipe.noise_estimator)
+        xs, ts = [], []
+
+        def record(_module, args):           # a pre-hook must return None, or its value replaces the inputs
+            xs.append(args[0].clone())
+            ts.append(args[1].clone())
+
+        pipe.noise_estimator.register_forward_pre_hook(record)
+        g = gen(c["seed"])
+        n_draws = [0]
+
+        def fake(x, **k):
+            n_draws[0] += 1
+            return torch.randn(x.shape, generator=g, dtype=x.dtype)
+
+        torch.randn_like = fake
+        try:
+            lat = pipe.sample(2, (8, 32, 32), condition=c["cond"], **c["kw"])
+        finally:
+            torch.randn_like = orig
+        out[name] = dict(pipe=c["pipe"], kw=c["kw"], cond=c["cond"], seed=c["seed"], n_draws=n_draws[0],
+                         x_in=torch.stack(xs), t_in=torch.stack([t.reshape(-1)[0] for t in ts]), latent=lat,
+                         keys=[(k, tuple(v.shape)) for k, v in pipe.noise_estimator.state_dict().items()])
+        print("traj", name, n_draws[0], "draws", [round(float(x.abs().max()), 2) for x in xs[::10]], float(lat.abs().max()))
+    torch.save(dict(unet_cfg=UNET_CANON, sched=SCHED, cases=out), os.path.join(OUT, "traj_canonical.pt"))
+
+
+@torch.no_grad()
+def forward_fixture():
+    """DiffusionPipeline.forward values (diffusion_pipeline.py:232-275): the 4-tuple
+    (x_t_prior, x_0, x_T, self_cond) for seeded inputs, the scheduler's randn_like draw replaced by a stored tensor."""
+    g = gen(51)
+    x_t = torch.randn(3, 8, 32, 32, generator=g)
+    noise = torch.randn(3, 8, 32, 32, generator=g)
+    t = torch.tensor([700, 250, 0])
+    cases = {
+        "uncond": dict(pipe={}, call={}),
+        "cond_g1": dict(pipe={}, call=dict(condition=torch.tensor([1, 0, 1]))),
+        "cfg3_uncond_labels": dict(pipe={}, call=dict(condition=torch.tensor([1, 0, 1]), guidance_scale=3.0,
+                                                      un_cond=torch.tensor([0, 1, 0]))),
+        "x0_objective_clip": dict(pipe=dict(estimator_objective="x_0", clip_x0=True), call={}),
+    }
+    out = {}
+    orig = torch.randn_like
+    torch.randn_like = lambda x, **k: noise.clone()
+    try:
+        for name, c in cases.items():
+            kw = dict(noise_scheduler=GaussianNoiseScheduler, noise_estimator=UNet, latent_embedder=None,
+                      noise_scheduler_kwargs=dict(SCHED),
+                      noise_estimator_kwargs=dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder,
+                                                  **fresh(UNET_SMALL)),
+                      estimator_objective="x_T", estimate_variance=False, use_self_conditioning=False, use_ema=False,
+                      do_input_centering=False, clip_x0=False)
+            kw.update(c["pipe"])
+            pipe = DiffusionPipeline(**kw).eval()
+            fill_(pipe.noise_estimator)
+            prior, x0, xT, sc = pipe(x_t, t, **c["call"])
+            out[name] = dict(pipe=c["pipe"], call=c["call"], x_t_prior=prior, x_0=x0, x_T=xT, self_cond=sc)
+            print("forward", name, float(prior.abs().max()), float(x0.abs().max()), float(xT.abs().max()))
+    finally:
+        torch.randn_like = orig
+    torch.save(dict(unet_cfg=UNET_SMALL, sched=SCHED, x_t=x_t, t=t, noise=noise, cases=out),
+               os.path.join(OUT, "forward_small.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    unet_fixture("unet_small.pt", UNET_SMALL, 1)
-    unet_fixture("unet_canonical.pt", UNET_CANON, 2)
-    unet_fixture("unet_attn_small.pt", UNET_ATTN, 3)
-    vae_fixture()
-    sched_fixture()
-    sample_fixture()
-    ckpt_fixture()
-    opts_fixture()
-    vae_encode_fixture()
-    config4_fixture()
+    ALL = dict(unet_small=lambda: unet_fixture("unet_small.pt", UNET_SMALL, 1),
+               unet_canonical=lambda: unet_fixture("unet_canonical.pt", UNET_CANON, 2),
+               unet_attn_small=lambda: unet_fixture("unet_attn_small.pt", UNET_ATTN, 3),
+               vae=vae_fixture, sched=sched_fixture, sample=sample_fixture, ckpt=ckpt_fixture, opts=opts_fixture,
+               vae_encode=vae_encode_fixture, config4=config4_fixture, traj=traj_fixture, forward=forward_fixture)
+    todo = sys.argv[1:] or list(ALL)      # python oracle/make_golden.py [fixture names]
+    for name in todo:
+        ALL[name]()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

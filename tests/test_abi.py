@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.mf_abi_version() == 2
+    assert lib.mf_abi_version() == 3
     assert set(_lib.SIGNATURES) == set(declared)
 
 

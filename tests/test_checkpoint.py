@@ -128,3 +128,23 @@ def test_legacy_serialization_and_unknown_classes_in_containers(tmp_path):
         assert torch.equal(ck["state_dict"]["w"], torch.arange(4.0))
         hp = ck["hyper_parameters"]
         assert is_placeholder(hp["callbacks"][0]) and hp["loss"] is torch.nn.L1Loss and hp["lr"] == 1e-4
+
+
+def test_unpickler_does_not_resolve_arbitrary_importable_globals(tmp_path):
+    """only an allow-list (torch, numpy, collections, plain containers, this package) is resolved; any other
+    importable global inside a checkpoint becomes an inert placeholder instead of being imported and called."""
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    p = tmp_path / "evil.ckpt"
+    with open(p, "wb") as fh:
+        pickle.dump({"state_dict": {}, "hyper_parameters": {"x": Evil()}}, fh)
+    from medfusion_b200.checkpoint import _PickleModule
+    with open(p, "rb") as fh:
+        obj = _PickleModule.load(fh)
+    assert not (tmp_path / "pwned").exists()
+    assert is_placeholder(obj["hyper_parameters"]["x"])
