@@ -1,19 +1,30 @@
 #!/usr/bin/env python
-"""Headline benchmark: images/sec of 256x256 sampling with 1000 DDPM steps (BASELINE.json configs[1]).
+"""Benchmark of the hot path: images/sec of latent-DDPM sampling (BASELINE.json), per configuration.
 
-    python bench.py --gpus 1 --steps K --warmup W            # B200-native arm (this repo)
-    python bench.py --impl reference --gpus 1 ...            # reference arm: the CPU oracle port on host cores
-    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # weak scaling, 64 images per GPU
+    python bench.py --gpus 1 --steps K --warmup W [--config 2]          # B200-native arm (this repo)
+    python bench.py --impl reference --gpus 1 ... [--config 2]          # reference arm: the reference's own CPU path
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...    # weak scaling, fixed images per GPU
 
-A "step" is ONE complete `DiffusionPipeline.sample()` of the per-GPU batch: x_T ~ N(0,I) -> 1000 ancestral
-DDPM timesteps (UNet noise estimate + scheduler update each) -> VAE.decode -> [64,3,256,256] images.
-`value` = images/s with the latents already on the device and the images left on the device;
-`e2e`   = the same call with x_T coming from pinned host memory and the images copied back to pinned host memory
-          inside the timed region.
-Rank 0 prints exactly one JSON line.
+--config selects the BASELINE.json configuration (default 2 = the one `metric` is quoted on; per-GPU batch fixed, so
+the same workload runs at every N):
+    1      scripts/sample.py-like CPU case: B=4, latent 8x32x32, 50 DDIM steps, unconditional
+    2      B=64/GPU, 1000 ancestral DDPM steps, unconditional                       (headline)
+    3      B=64/GPU, 1000 steps, 2-class LabelEmbedder condition, guidance_scale 1 (configs[2]: 512 over 8 GPUs)
+    3cfg8  scripts/sample.py:45 workload: B=16, 150 DDIM steps, condition, guidance_scale 8 (two estimator passes)
+    4      B=32/GPU, latent 8x64x64 -> 512x512, 250 DDIM steps, spatial attention at the deepest level (128 over 4 GPUs)
+    5      VAE.decode only, B=128/GPU (1024 over 8 GPUs)
+
+A "step" is ONE complete `DiffusionPipeline.sample()` of the per-GPU batch (config 5: one `VAE.decode`).
+`value` = images/s with the inputs already on the device and the images left on the device;
+`e2e`   = the same call through the public API with x_T (z) coming from pinned host memory and the images copied back to
+          pinned host memory inside the timed region.
+Rank 0 prints exactly one JSON line.  `--impl reference`: rank 0 times the unmodified reference (oracle/_ref, staged by
+__graft_entry__.build(); the oracle port if absent) on the host cores; one "step" there is a bounded sample of the
+workload (>= 20 timesteps in total at the stated batch + one decode), extrapolated linearly and labelled as such.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -28,12 +39,36 @@ UNET_CFG = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024]
                 strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
                 cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False,
                 use_res_block=True, use_attention="none")
+UNET_CFG_ATTN = dict(UNET_CFG, use_attention=["none", "none", "none", "spatial"])
 VAE_CFG = dict(in_channels=3, out_channels=3, emb_channels=8, spatial_dims=2, hid_chs=[64, 128, 256, 512],
                kernel_sizes=[3, 3, 3, 3], strides=[1, 2, 2, 2], deep_supervision=False, use_attention="none")
 SCHED = dict(timesteps=1000, beta_start=0.002, beta_end=0.02, schedule_strategy="scaled_linear")
-LATENT = (8, 32, 32)
-UNET_GFLOP_PER_SAMPLE_STEP = 51.202   # BASELINE.md §2 (reference formulation, 2*MAC)
-VAE_GFLOP_PER_SAMPLE = 62.923
+
+# algorithmic GFLOP per sample (reference formulation, 2 * MAC)
+GF = {"unet32": 51.202, "unet64_attn": 262.616, "vae32": 62.923, "vae64": 251.692}
+
+# Random-init estimators make the DDIM-form trajectory grow like 1/sqrt(alphas_cumprod) (|x| ~ 6e5 after 50 steps without
+# clipping: beyond the fp16 range of the split planes, and meaningless anyway), so the DDIM configurations run with the
+# constructor's default clip_x0=True; the ancestral 1000-step configurations keep train_diffusion.py's clip_x0=False.
+CONFIGS = {
+    "1": dict(label="configs[0]: scripts/sample.py-like CPU case", B=4, latent=(8, 32, 32), timesteps=50, ddim=True,
+              conditional=False, guidance=1.0, attn=False, clip_x0=True, img=256),
+    "2": dict(label="configs[1]: batch=64/GPU 256x256, 1000 ancestral DDPM steps, unconditional", B=64,
+              latent=(8, 32, 32), timesteps=1000, ddim=False, conditional=False, guidance=1.0, attn=False,
+              clip_x0=False, img=256),
+    "3": dict(label="configs[2]: batch=64/GPU (512 over 8 GPUs), 1000 steps, 2-class condition, guidance 1", B=64,
+              latent=(8, 32, 32), timesteps=1000, ddim=False, conditional=True, guidance=1.0, attn=False,
+              clip_x0=False, img=256),
+    "3cfg8": dict(label="scripts/sample.py:45 workload: batch=16, 150 DDIM steps, condition, guidance 8 (2 passes)",
+                  B=16, latent=(8, 32, 32), timesteps=150, ddim=True, conditional=True, guidance=8.0, attn=False,
+                  clip_x0=True, img=256),
+    "4": dict(label="configs[3]: batch=32/GPU (128 over 4 GPUs) 512x512, 8x64x64 latent, 250 DDIM steps, spatial "
+                    "attention at the deepest level", B=32, latent=(8, 64, 64), timesteps=250, ddim=True,
+              conditional=False, guidance=1.0, attn=True, clip_x0=True, img=512),
+    "5": dict(label="configs[4]: VAE.decode only, batch=128/GPU (1024 over 8 GPUs), 8x32x32 -> 3x256x256", B=128,
+              latent=(8, 32, 32), timesteps=0, ddim=False, conditional=False, guidance=1.0, attn=False,
+              clip_x0=False, img=256, decode_only=True),
+}
 
 
 def parse_args():
@@ -42,9 +77,28 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
-    ap.add_argument("--timesteps", type=int, default=1000, help="DDPM timesteps per sample() (1000 = the named config)")
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (0 = the configuration's)")
+    ap.add_argument("--timesteps", type=int, default=0, help="timesteps per sample() (0 = the configuration's)")
+    ap.add_argument("--no-comparator", action="store_true", help="skip the torch+cuDNN fp32 GPU comparator leg")
     return ap.parse_args()
+
+
+def resolve_config(args):
+    c = dict(CONFIGS[args.config])
+    if args.batch:
+        c["B"] = args.batch
+    if args.timesteps and not c.get("decode_only"):
+        c["timesteps"] = args.timesteps
+    c["unet_gf"] = GF["unet64_attn"] if c["attn"] else GF["unet32"]
+    c["vae_gf"] = GF["vae64"] if c["latent"][1] == 64 else GF["vae32"]
+    c["passes"] = 2 if (c["conditional"] and c["guidance"] != 1.0) else 1
+    c["unet_cfg"] = UNET_CFG_ATTN if c["attn"] else UNET_CFG
+    return c
+
+
+def alg_flops_per_image(c):
+    return (c["timesteps"] * c["passes"] * c["unet_gf"] + c["vae_gf"]) * 1e9
 
 
 def usable_cores():
@@ -115,68 +169,96 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores (bounded sample, extrapolated)
+# reference arm / cpu baseline / GPU comparator: the reference's own implementation (oracle/ref_runner.py)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_images_per_sec(timesteps, n_steps_sample=2, b=4, conditional=False):
+def reference_images_per_sec(c, device, n_timesteps, b_steps, b_decode, threads=None):
+    """Bounded sample of configuration `c` through the reference: n_timesteps reverse steps at batch b_steps and one
+    decode at batch b_decode, extrapolated linearly to c['timesteps'] steps at batch c['B'] -> dict."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    import medfusion_oracle as O
-    from medfusion_b200.synthetic import synth_tensor
-    from util import unet_oracle_cfg, vae_oracle_cfg
-    from golden_keys import unet_keys, vae_keys
-    cores = usable_cores()
-    torch.set_num_threads(cores)
-    usd = {k: synth_tensor(k, s) for k, s in unet_keys(UNET_CFG)}
-    vsd = {k: synth_tensor(k, s) for k, s in vae_keys(VAE_CFG)}
-    ucfg, vcfg = unet_oracle_cfg(UNET_CFG), vae_oracle_cfg(VAE_CFG)
-    tabs = O.scheduler_tables(SCHED["timesteps"], SCHED["schedule_strategy"], SCHED["beta_start"], SCHED["beta_end"])
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(b, *LATENT, generator=g)
-    noises = [torch.randn(b, *LATENT, generator=g) for _ in range(n_steps_sample + 1)]
-    with torch.no_grad():
-        O.unet_forward(usd, ucfg, x, torch.full((b,), 5), None)  # warm-up (thread pool, oneDNN primitives)
-        t0 = time.perf_counter()
-        cond = (torch.arange(b) % 2) if conditional else None      # configs[2]: 2-class labels, guidance_scale 1
-        lat = O.denoise(lambda xx, tt, cc, sc=None: O.unet_forward(usd, ucfg, xx, tt, cc), tabs, x, noises, n_steps_sample,
-                        use_ddim=False, guidance_scale=1.0, cond=cond)
-        t1 = time.perf_counter()
-        O.vae_decode(vsd, vcfg, lat)
-        t2 = time.perf_counter()
-    per_step, dec = (t1 - t0) / n_steps_sample, (t2 - t1)
-    ips = b / (timesteps * per_step + dec)
-    sample = (f"oracle port (torch CPU fp32), B={b}: {n_steps_sample} of {timesteps} DDPM timesteps "
-              f"({per_step:.3f} s each) + 1 VAE.decode ({dec:.2f} s), extrapolated linearly to {timesteps} timesteps")
-    return ips, cores, sample
+    import ref_runner
+    r = ref_runner.ReferenceRunner(c["unet_cfg"], VAE_CFG, SCHED, c["clip_x0"], device=device, threads=threads)
+    B = c["B"]
+    dec_s = r.time_decode(b_decode, c["latent"]) if device == "cpu" else min(r.time_decode(b_decode, c["latent"])
+                                                                             for _ in range(2))
+    step_s = 0.0
+    if not c.get("decode_only"):
+        if device != "cpu":
+            r.time_timesteps(b_steps, c["latent"], 2, use_ddim=c["ddim"], conditional=c["conditional"],
+                             guidance_scale=c["guidance"])   # cuDNN autotune / allocator warm-up
+        step_s = r.time_timesteps(b_steps, c["latent"], n_timesteps, use_ddim=c["ddim"], conditional=c["conditional"],
+                                  guidance_scale=c["guidance"]) / n_timesteps
+    total_s = c["timesteps"] * step_s * (B / b_steps) + dec_s * (B / b_decode)
+    what = "the unmodified reference (oracle/_ref)" if r.kind == "reference" else "oracle port of the reference"
+    sample = (f"{what}, torch {'CPU' if device == 'cpu' else 'CUDA (cuDNN/cuBLAS, TF32 off)'} fp32: "
+              + ("" if c.get("decode_only") else f"{n_timesteps} of {c['timesteps']} timesteps at B={b_steps} "
+                 f"({step_s:.3f} s each) + ") + f"1 VAE.decode at B={b_decode} ({dec_s:.2f} s), extrapolated linearly to "
+              f"{c['timesteps']} timesteps at B={B}")
+    return dict(value=B / total_s, kind=r.kind, sample=sample, step_s=step_s, decode_s=dec_s,
+                measured_s=step_s * n_timesteps + dec_s)
 
 
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def run_reference_arm(args, c):
+    """Rank 0 only.  One bench "step" = ts_per_step timesteps at the stated batch (>= 20 timesteps over the K timed
+    steps); the decode is timed once at min(B, 16) and scaled.  ms_per_step is the MEASURED time of one such step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    vals = []
-    for i in range(args.warmup + args.steps):
-        ips, cores, sample = cpu_reference_images_per_sec(args.timesteps, n_steps_sample=1 if i < args.warmup else 2,
-                                                          conditional=args.gpus > 1)
-        if i >= args.warmup:
-            vals.append(ips)
-        if len(vals) >= 2 and i >= args.warmup + 1:
-            break  # bounded: the extrapolation does not change with more repeats
-    v = statistics.mean(vals)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_runner
+    cores = usable_cores()
+    r = ref_runner.ReferenceRunner(c["unet_cfg"], VAE_CFG, SCHED, c["clip_x0"], device="cpu", threads=cores)
+    B = c["B"]
+    b_dec = min(B, 16)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    t_wall0 = time.perf_counter()
+    if c.get("decode_only"):
+        for _ in range(min(W, 1)):
+            r.time_decode(b_dec, c["latent"])
+        per = [r.time_decode(b_dec, c["latent"]) for _ in range(min(K, 3))]
+        dec_s, step_s, ts_per_step = statistics.mean(per), 0.0, 0
+        measured_step_s = dec_s
+        total_s = dec_s * (B / b_dec)
+    else:
+        ts_per_step = max(1, math.ceil(20 / K))
+        kw = dict(use_ddim=c["ddim"], conditional=c["conditional"], guidance_scale=c["guidance"])
+        for _ in range(min(W, 2)):                         # warm-up: thread pool, oneDNN primitive cache
+            r.time_timesteps(B, c["latent"], 1, **kw)
+        per = [r.time_timesteps(B, c["latent"], ts_per_step, **kw) for _ in range(K)]
+        dec_s = r.time_decode(b_dec, c["latent"])
+        measured_step_s = statistics.mean(per)
+        step_s = measured_step_s / ts_per_step
+        total_s = c["timesteps"] * step_s + dec_s * (B / b_dec)
+    v = B / total_s
+    what = "the unmodified reference (oracle/_ref)" if r.kind == "reference" else "oracle port of the reference"
+    sample = (f"{what}, torch CPU fp32, {cores} threads: " +
+              ("" if c.get("decode_only") else f"{K} timed steps x {ts_per_step} timestep(s) at B={B} "
+               f"({step_s:.3f} s per timestep) + ") +
+              f"VAE.decode at B={b_dec} ({dec_s:.2f} s, scaled x{B / b_dec:g}); extrapolated linearly to "
+              f"{c['timesteps']} timesteps + decode at B={B}")
     out = {
-        "impl": "reference", "metric": "images/sec (256x256, 1000 DDPM steps)", "value": v, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={args.batch} 256x256, 8x32x32 latent, {args.timesteps} DDPM steps, " +
-                               ("2-class conditional, guidance 1 (BASELINE.json configs[2] shape)" if args.gpus > 1
-                                else "unconditional (BASELINE.json configs[1])"),
-                   "impl": "CPU oracle port of the reference (rank 0 only)"},
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric_name(c), "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1000.0 * measured_step_s, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(c), "bench_config": args.config,
+                   "impl": what + " on the host cores (rank 0 only)",
+                   "step": "a bounded sample of the workload (see cpu_baseline.sample); value is the linear extrapolation",
+                   "extrapolated_full_sample_s": total_s, "wall_s": time.perf_counter() - t_wall0},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": r.kind, "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def metric_name(c):
+    if c.get("decode_only"):
+        return "images/sec (VAE.decode 8x32x32 -> 3x256x256)"
+    return f"images/sec ({c['img']}x{c['img']}, {c['timesteps']} {'DDIM-form' if c['ddim'] else 'DDPM'} steps)"
+
+
+def workload_name(c):
+    return c["label"] + (f" [B={c['B']}/GPU, {c['timesteps']} timesteps]" if not c.get("decode_only") else f" [B={c['B']}/GPU]")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -184,8 +266,9 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    c = resolve_config(args)
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, c)
         return
 
     import torch
@@ -210,31 +293,56 @@ def main():
                              noise_scheduler_kwargs=dict(SCHED),
                              noise_estimator_kwargs=dict(time_embedder=TimeEmbbeding, cond_embedder=LabelEmbedder,
                                                          **{k: (dict(v) if isinstance(v, dict) else v)
-                                                            for k, v in UNET_CFG.items()}),
+                                                            for k, v in c["unet_cfg"].items()}),
                              estimator_objective="x_T", estimate_variance=False, use_self_conditioning=False,
-                             use_ema=False, do_input_centering=False, clip_x0=False)
+                             use_ema=False, do_input_centering=False, clip_x0=c["clip_x0"])
     fill_(pipe.noise_estimator)                # random-init weights with the zero-init tensors re-randomised
     pipe.latent_embedder = fill_(VAE(**VAE_CFG))
     pipe = pipe.to(dev)
+    unet, vae = pipe.noise_estimator, pipe.latent_embedder
 
-    B = args.batch
+    B, LAT, IMG = c["B"], c["latent"], c["img"]
     Bg = B * n_gpus
-    conditional = n_gpus > 1                   # configs[2]: 2-class LabelEmbedder, guidance_scale = 1
-    cond_full = (torch.arange(Bg, device=dev) % 2) if conditional else None
-    kw = dict(steps=args.timesteps, use_ddim=False)
-    if conditional:
-        kw["guidance_scale"] = 1.0
+    decode_only = bool(c.get("decode_only"))
+    cond_full = (torch.arange(Bg, device=dev) % 2) if c["conditional"] else None
+    kw = dict(steps=c["timesteps"], use_ddim=c["ddim"])
+    if c["conditional"]:
+        kw["guidance_scale"] = c["guidance"]
+    z_res = torch.randn(B, *LAT, device=dev) if decode_only else None
 
     def one_sample():
+        if decode_only:        # config 5: every rank decodes its own 128 latents; no collective on this path
+            return vae.decode(z_res)
         if distributed:
-            return pipe.sample(Bg, LATENT, condition=cond_full, shard=True, **kw)
-        return pipe.sample(B, LATENT, condition=None, **kw)
+            return pipe.sample(Bg, LAT, condition=cond_full, shard=True, **kw)
+        return pipe.sample(B, LAT, condition=cond_full, **kw)
 
     def sync_all():
         torch.cuda.synchronize()
         if distributed:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---- multi-rank output parity (untimed): the sharded result must equal the single-GPU result of the same seed ----
+    shard_parity = None
+    if distributed and not decode_only:
+        nb = 8 * n_gpus
+        cpar = (torch.arange(nb, device=dev) % 2) if c["conditional"] else None
+        pkw = dict(steps=3, use_ddim=False)
+        if c["conditional"]:
+            pkw["guidance_scale"] = c["guidance"]
+        torch.manual_seed(1234)
+        img_sh = pipe.sample(nb, LAT, condition=cpar, shard=True, **pkw)
+        torch.manual_seed(1234)
+        img_1 = pipe.sample(nb, LAT, condition=cpar, **pkw)          # the whole batch on this GPU alone
+        d = (img_sh - img_1).abs()
+        bad = int((d > 1e-5 + 1e-3 * img_1.abs()).sum())
+        stats = torch.tensor([float(d.max()), float(bad)], device=dev)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        shard_parity = {"max_abs_err": float(stats[0]), "violations_rtol1e-3_atol1e-5": int(stats[1]),
+                        "ok": int(stats[1]) == 0, "batch": nb, "timesteps": 3,
+                        "what": "sample(shard=True) over all ranks vs the same seed on one GPU, every rank checks"}
+        del img_sh, img_1
 
     torch.manual_seed(0)
     for _ in range(args.warmup):
@@ -255,16 +363,17 @@ def main():
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_s = float(elapsed_ms) / 1000.0
     value = Bg * args.steps / elapsed_s
-    assert img.shape == (Bg, 3, 256, 256) and bool(torch.isfinite(img).all())
+    n_img_out = B if decode_only else Bg
+    assert img.shape == (n_img_out, 3, IMG, IMG) and bool(torch.isfinite(img).all())
 
     # ---- timed region 2: end to end through the public API with host buffers -------------------------
-    h_xT = torch.randn(B, *LATENT).pin_memory()
-    h_img = torch.empty(B, 3, 256, 256).pin_memory()
+    h_in = torch.randn(B, *LAT).pin_memory()
+    h_img = torch.empty(B, 3, IMG, IMG).pin_memory()
     cond_local = None if cond_full is None else cond_full[rank * B:(rank + 1) * B].contiguous()
 
     def one_e2e():
-        x_T = h_xT.to(dev, non_blocking=True)
-        out = pipe.denoise(x_T, condition=cond_local, **kw)
+        x_in = h_in.to(dev, non_blocking=True)
+        out = vae.decode(x_in) if decode_only else pipe.denoise(x_in, condition=cond_local, **kw)
         h_img.copy_(out, non_blocking=True)
         return out
 
@@ -282,69 +391,95 @@ def main():
     e2e_value = Bg * args.steps / (float(e2e_ms) / 1000.0)
 
     # ---- roofline of the dominant kernel (conv_tc_kernel: tcgen05 implicit-GEMM conv), measured live -----
-    unet, vae = pipe.noise_estimator, pipe.latent_embedder
-    x = torch.randn(B, *LATENT, device=dev)
-    t = torch.full((B,), 500, device=dev, dtype=torch.int64)
-    prof = []
-    for _ in range(3):
-        prof = unet.profile(x, t, None)
+    if decode_only:
+        prof = []
+        for _ in range(3):
+            prof = vae.profile(z_res)
+    else:
+        x = torch.randn(B, *LAT, device=dev)
+        t = torch.full((B,), 500, device=dev, dtype=torch.int64)
+        prof = []
+        for _ in range(3):
+            prof = unet.profile(x, t, None if cond_full is None else cond_local)
     tc = [(ms, fl) for ms, kind, fl in prof if kind == 0]
     step_ms = sum(ms for ms, _, _ in prof)
     tc_ms, tc_flops = sum(m for m, _ in tc), sum(f for _, f in tc)
     peaks, peak_src = measured_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            tj = json.load(fh)
+        traffic = tj.get("dram_bytes_per_launch_vae" if decode_only else "dram_bytes_per_launch")
+        traffic_src = tj.get("source")
     except Exception:
         pass
-    # kernels of this library per sample(): the UNet plan per timestep (the scheduler update rides in the plan's last
-    # kernel, the output head) + the decoder plan; torch's own randn / copy kernels are not counted
-    launches_per_sample = args.timesteps * unet.plan_info()["launches"] + vae.plan_info()["launches"]
+    # kernels of this library per step: the estimator plan per timestep and pass (the scheduler update rides in the
+    # plan's last kernel, the output head) + the decoder plan; torch's own randn / copy kernels are not counted
+    launches_per_step = vae.plan_info()["launches"]
+    if not decode_only:
+        launches_per_step += c["timesteps"] * c["passes"] * unet.plan_info()["launches"]
 
     if rank == 0:
-        cpu = None
+        cpu, gpu_cmp = None, None
         if n_gpus == 1:
-            ips, cores, sample = cpu_reference_images_per_sec(args.timesteps)
-            cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
-        alg_flops_per_step = B * (args.timesteps * UNET_GFLOP_PER_SAMPLE_STEP + VAE_GFLOP_PER_SAMPLE) * 1e9
+            # bounded CPU sample (~10-30 s): a few timesteps at a reduced batch, decode at B=4, scaled linearly in B
+            r = reference_images_per_sec(c, "cpu", n_timesteps=3, b_steps=min(B, 8), b_decode=min(B, 4),
+                                         threads=usable_cores())
+            cpu = {"value": r["value"], "unit": "images/s", "cores": usable_cores(), "kind": r["kind"],
+                   "sample": r["sample"] + f" (batch scaled linearly; {r['measured_s']:.1f} s measured)"}
+            if not args.no_comparator:
+                try:   # the stock torch + cuDNN fp32 path of the same reference code on this GPU (TF32 disabled)
+                    g = reference_images_per_sec(c, f"cuda:{local_rank}", n_timesteps=10, b_steps=B, b_decode=min(B, 64))
+                    gpu_cmp = {"value": g["value"], "unit": "images/s", "kind": g["kind"] + " on torch+cuDNN fp32, TF32 off",
+                               "sample": g["sample"]}
+                except Exception as exc:   # e.g. out of memory next to the resident engines
+                    gpu_cmp = {"unavailable": repr(exc)[:200]}
+        alg_flops_per_step = B * alg_flops_per_image(c)
         out = {
-            "metric": "images/sec (256x256, 1000 DDPM steps)", "value": value, "unit": "images/s", "n_gpus": n_gpus,
+            "metric": metric_name(c), "value": value, "unit": "images/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed_s / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16x3 split, fp32 accumulate (fp32 parity)",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16x3 split, fp32 accumulate (fp32 parity)", "data": "synthetic",
             "config": {
-                "workload": (f"batch={B}/GPU 256x256, 8x32x32 latent, {args.timesteps} ancestral DDPM steps, "
-                             + ("2-class conditional, guidance 1 (BASELINE.json configs[2] shape)" if conditional
-                                else "unconditional (BASELINE.json configs[1])")),
-                "global_batch": Bg, "parallelism": f"batch-shard x{n_gpus}, one all-gather of images",
-                "step": "one full sample(): x_T -> timesteps x (UNet + scheduler) -> VAE.decode",
-                "l2": "working set per timestep (0.8 GB fp16 hi/lo weights + ~2 GB activations) exceeds the 126 MB L2",
+                "workload": workload_name(c), "bench_config": args.config,
+                "global_batch": Bg, "parallelism": (f"independent replicas x{n_gpus} (no collective)" if decode_only else
+                                                    f"batch-shard x{n_gpus}, one all-gather of images"),
+                "step": ("one VAE.decode of the per-GPU batch" if decode_only else
+                         "one full sample(): x_T -> timesteps x (UNet + scheduler) -> VAE.decode"),
+                "l2": "working set per launch sequence (fp16 hi/lo weights + activations, > 1 GB) exceeds the 126 MB L2",
+                "clip_x0": c["clip_x0"],
                 "algorithmic_tflop_per_step": alg_flops_per_step / 1e12,
                 "job_algorithmic_tflops": alg_flops_per_step * n_gpus * args.steps / elapsed_s / 1e12,
             },
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h_xT.numel() * 4 * n_gpus,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h_in.numel() * 4 * n_gpus,
                     "d2h_bytes_per_step": h_img.numel() * 4 * n_gpus},
-            "gpu_launches": launches_per_sample * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": "mf::conv_tc_kernel (tcgen05 kind::f16, fp16x3 split, 50 of 51 UNet convs)",
+                "kernel": "mf::conv_tc_kernel (tcgen05 kind::f16, fp16x3 split) — all tensor-core convolutions of one "
+                          + ("VAE.decode" if decode_only else "UNet timestep"),
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}); the fp32-accurate 3-term "
                                "split issues 3 fp16 MMAs per product, so frac <= 1/3 by construction",
                 "issued_f16_tflops": 3.0 * achieved_tf,
-                "kernel_share_of_unet_step": tc_ms / step_ms if step_ms else None,
-                "avg_launch_ms": tc_ms / max(1, len(tc)), "launches_per_unet_step": len(tc),
+                "kernel_share_of_step": tc_ms / step_ms if step_ms else None,
+                "avg_launch_ms": tc_ms / max(1, len(tc)), "launches_per_plan": len(tc),
             },
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if gpu_cmp is not None:
+            out["gpu_comparator"] = gpu_cmp
+        if shard_parity is not None:
+            out["shard_parity"] = shard_parity
         print(json.dumps(out), flush=True)
     if distributed:
         dist.destroy_process_group()
+    if shard_parity is not None and not shard_parity["ok"]:
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":
