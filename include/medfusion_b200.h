@@ -164,6 +164,9 @@ typedef struct {
   int strides[MF_MAX_LEVELS];    /* [1,2,2,2]; levels 1.. must be 2 (nearest x2 + conv3x3) */
   int norm_groups;               /* 8 */
   int in_channels;               /* image channels of the ENCODER half (3); 0 = decoder-only handle (ABI v2) */
+  int num_embeddings;            /* > 0: VQVAE (latent_embedders.py:180-320) — decode() first snaps z to the nearest row of
+                                    `quantizer.embedder.weight` [num_embeddings][emb_channels] (VectorQuantizer.forward
+                                    :50-69, z_q = z + (e - z)); needs in_channels == 0 (VQVAE.encode is not built) (ABI v3) */
 } mf_vae_config;
 
 typedef struct mf_vae mf_vae;
@@ -275,6 +278,10 @@ int mf_op_layernorm(const void* d_in, int64_t in_plane, const float* d_gamma, co
 int mf_op_geglu(const float* d_in, void* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s);
 int mf_op_upsample2x(const void* d_in, int64_t in_plane, void* d_out, int64_t out_plane, int N, int H, int W, int C,
                      mf_stream_t s);
+/* VectorQuantizer.forward (latent_embedders.py:40-72), inference half: z [B,C,HW] fp32 NCHW -> z_q (same layout) =
+ * z + (e[argmin_k ||z||^2 + ||e_k||^2 - 2 z.e_k] - z); d_idx (optional) receives the int32 code per latent vector. */
+int mf_op_vq_quantize(const float* d_z, const float* d_codebook, float* d_zq, int* d_idx, int B, int C, int HW, int K,
+                      mf_stream_t s);
 
 #ifdef __cplusplus
 }

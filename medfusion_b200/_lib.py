@@ -32,7 +32,7 @@ class VAEConfig(ctypes.Structure):
     _fields_ = [
         ("emb_channels", c_int), ("out_channels", c_int), ("depth", c_int),
         ("hid_chs", c_int * MF_MAX_LEVELS), ("strides", c_int * MF_MAX_LEVELS), ("norm_groups", c_int),
-        ("in_channels", c_int),
+        ("in_channels", c_int), ("num_embeddings", c_int),
     ]
 
 
@@ -124,6 +124,7 @@ SIGNATURES = {
     "mf_op_layernorm": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, c_float, _P]),
     "mf_op_geglu": (c_int, [_P, _P, c_int64, c_int64, c_int, _P]),
     "mf_op_upsample2x": (c_int, [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "mf_op_vq_quantize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
 }
 
 _lib = None

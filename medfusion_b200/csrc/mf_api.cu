@@ -315,7 +315,9 @@ struct mf_vae : public EngineBase {
   struct Up { ConvLayer up; ResBlockLayer rb; int factor = 2; };
   std::vector<std::unique_ptr<Up>> decoders;  // index i == decoders.{i}
   ConvLayer outc;
+  Param* codebook = nullptr;          // VQVAE: quantizer.embedder.weight [num_embeddings][emb_channels]
   const float* io_z = nullptr;
+  const float* zq_ptr = nullptr;      // VQVAE: the quantised latent inside the workspace (what the stems read)
   float* io_x = nullptr;
   int n_launches = 0;
 
@@ -326,6 +328,7 @@ struct mf_vae : public EngineBase {
 int mf_vae::init(const mf_vae_config& c) {
   cfg = c;
   MF_REQUIRE(c.depth >= 1 && c.depth <= MF_MAX_LEVELS, "depth must be in [1, 8]");
+  MF_REQUIRE(c.num_embeddings == 0 || c.in_channels == 0, "VQVAE handles are decoder-only (in_channels must be 0)");
   if (c.in_channels > 0) {
     // encoder parameters, registered in the PARENT registry with the reference's names
     has_encoder = true;
@@ -342,6 +345,11 @@ int mf_vae::init(const mf_vae_config& c) {
     }
     init_conv(*this, enc.out0, "out_enc.0.conv", 2 * c.emb_channels, c.hid_chs[c.depth - 1], 3, 1);
     init_conv(*this, enc.out1, "out_enc.1.conv", 2 * c.emb_channels, 2 * c.emb_channels, 1, 1);
+  }
+  if (c.num_embeddings > 0) {
+    // VQVAE (latent_embedders.py:180-320): decode() quantises z first (:315); registered before inc_dec like the reference
+    MF_REQUIRE(c.emb_channels <= 16, "VQVAE: emb_channels must be <= 16");
+    codebook = add_param("quantizer.embedder.weight", {c.num_embeddings, c.emb_channels});
   }
   init_resblock(*this, inc_dec, "inc_dec", c.emb_channels, c.hid_chs[c.depth - 1], 3, 0);
   for (int i = 0; i < c.depth - 1; ++i) {
@@ -373,24 +381,41 @@ int mf_vae::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) {
   }
   const int G = cfg.norm_groups;
   const int Ctop = cfg.hid_chs[cfg.depth - 1];
+  // ---- VQVAE: nearest codebook row per latent vector (VectorQuantizer.forward, latent_embedders.py:50-69)
+  const float* const* zsrc = &io_z;
+  Tens zq;
+  if (codebook != nullptr) {
+    zq = new_floats(static_cast<size_t>(B) * cfg.emb_channels * H * W);
+    zq_ptr = zq.ptr;
+    zsrc = &zq_ptr;
+    if (!dry) {
+      float* zqp = zq.ptr;
+      const float* cb = codebook->data.p;
+      const int C = cfg.emb_channels, K = cfg.num_embeddings;
+      push_op([this, zqp, cb, B, C, H, W, K](cudaStream_t st) { return vq_quantize(io_z, cb, zqp, nullptr, B, C, H * W, K, st); },
+              kOpOther);
+    }
+  }
   // ---- inc_dec: UnetResBlock(emb_channels -> Ctop), stem convs read the NCHW latent directly
   Tens raw = new_tensor(B, H, W, Ctop, kNHWCRaw);
-  Tens part = new_floats(static_cast<size_t>(B) * std::max(1, conv_tc_stats_chunks(H, W)) * (Ctop / 8) * 2);
+  Tens part = new_floats(static_cast<size_t>(B) * std::max(1, conv_tc_stats_chunks(H, W)) * ((Ctop + 7) / 8) * 2);
   int chunks = 1;
-  rc = add_conv_nchw_in(inc_dec.conv1, &io_z, B, cfg.emb_channels, H, W, raw, &part, &chunks);
+  const bool generic_gn = gn_needs_generic(Ctop, G);
+  rc = add_conv_nchw_in(inc_dec.conv1, zsrc, B, cfg.emb_channels, H, W, raw, generic_gn ? nullptr : &part, &chunks);
   if (rc) return rc;
   Tens res_raw;
   const Tens* res = nullptr;
   MF_REQUIRE(inc_dec.has_res_conv, "inc_dec with emb_channels == hid_chs[-1] is not supported");
   res_raw = new_tensor(B, H, W, Ctop, kNHWCRaw);
-  rc = add_conv_nchw_in(inc_dec.conv_res, &io_z, B, cfg.emb_channels, H, W, res_raw, nullptr, nullptr);
+  rc = add_conv_nchw_in(inc_dec.conv_res, zsrc, B, cfg.emb_channels, H, W, res_raw, nullptr, nullptr);
   if (rc) return rc;
   res = &res_raw;
   Tens x1 = new_tensor(B, H, W, Ctop, kNHWCSplit);
   rc = add_gn_apply(inc_dec.norm1, G, raw, part, chunks, res, nullptr, 0, x1);
   if (rc) return rc;
   free_tensor(res_raw);
-  rc = add_conv(inc_dec.conv2, x1, nullptr, raw, &part, &chunks);
+  if (codebook != nullptr) free_tensor(zq);
+  rc = add_conv(inc_dec.conv2, x1, nullptr, raw, generic_gn ? nullptr : &part, &chunks);
   if (rc) return rc;
   Tens hcur = new_tensor(B, H, W, Ctop, kNHWCSplit);
   rc = add_gn_apply(inc_dec.norm2, G, raw, part, chunks, &x1, nullptr, 0, hcur);
@@ -931,6 +956,10 @@ int mf_op_layernorm(const void* d_in, int64_t in_plane, const float* d_gamma, co
 }
 int mf_op_geglu(const float* d_in, void* d_out, int64_t out_plane, int64_t tokens, int Ch, mf_stream_t s) {
   return geglu_split(d_in, MF_H(d_out), out_plane, tokens, Ch, static_cast<cudaStream_t>(s));
+}
+int mf_op_vq_quantize(const float* d_z, const float* d_codebook, float* d_zq, int* d_idx, int B, int C, int HW, int K,
+                      mf_stream_t s) {
+  return vq_quantize(d_z, d_codebook, d_zq, d_idx, B, C, HW, K, static_cast<cudaStream_t>(s));
 }
 int mf_op_upsample2x(const void* d_in, int64_t in_plane, void* d_out, int64_t out_plane, int N, int H, int W, int C,
                      mf_stream_t s) {

@@ -258,8 +258,8 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
   // exact fp32 SIMT path (single source only)
   MF_REQUIRE(res == nullptr && emb == nullptr,
              "fused residual / embedding epilogues exist on the tensor-core path only (" + L.w->name + ")");
-  MF_REQUIRE(in1 == nullptr, "two-source convolution is only available on the tensor-core path (" + L.w->name +
-                                 "): channels must be multiples of 32/64 and H*W a power of two >= 32");
+  MF_REQUIRE(in1 == nullptr || (in1->layout == in0.layout && in0.layout != kNCHW),
+             "two-source convolution: both sources must be NHWC tensors of the same kind (" + L.w->name + ")");
   ++n_simt;
   if (chunks) *chunks = 1;
   if (dry) return 0;
@@ -267,7 +267,8 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
   if (rc) return rc;
   ConvSimtDesc d{};
   d.in = in0.ptr; d.in_plane = in0.plane; d.in_layout = in0.layout;
-  d.N = in0.N; d.Cin = in0.C; d.Hin = in0.H; d.Win = in0.W;
+  d.in1 = in1 ? in1->ptr : nullptr; d.in1_plane = in1 ? in1->plane : 0; d.C1 = C1;
+  d.N = in0.N; d.Cin = in0.C + C1; d.Hin = in0.H; d.Win = in0.W;
   d.w_kc = L.w_simt.p; d.bias = L.b->data.p; d.Cout = L.Cout; d.ksize = L.k; d.stride = L.stride;
   d.out = out.ptr; d.out_plane = out.plane; d.out_layout = out.layout;
   push_op([d](cudaStream_t s) { return conv_simt(d, s); }, kOpConvSimt,
@@ -428,11 +429,41 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
   return 0;
 }
 
+bool gn_needs_generic(int C, int groups) { return groups <= 0 || C % groups != 0 || (C / groups) % 8 != 0; }
+
 int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks,
                              const Tens* res, const float* emb, int emb_stride, const Tens& out, int act) {
-  MF_REQUIRE(raw.C % groups == 0 && (raw.C / groups) % 8 == 0,
-             "GroupNorm: channels per group must be a multiple of 8 (" + nl.g->name + ")");
+  MF_REQUIRE(groups > 0 && raw.C % groups == 0, "GroupNorm: channels must be divisible by the group count (" + nl.g->name + ")");
   Tens mr = new_floats(static_cast<size_t>(raw.N) * groups * 2);
+  if (gn_needs_generic(raw.C, groups)) {
+    // small widths (e.g. 32 channels in 32 groups, the VQVAE / reference-test defaults): statistics straight from the raw
+    // conv output, one channel per thread-iteration in the apply; `stats` is not used
+    MF_REQUIRE(raw.layout == kNHWCRaw, "generic GroupNorm expects the raw fp32 conv output (" + nl.g->name + ")");
+    if (!dry) {
+      const float* rp = raw.ptr; float* mrp = mr.ptr;
+      const int N = raw.N, C = raw.C, HW = raw.H * raw.W;
+      push_op([rp, mrp, N, HW, C, groups](cudaStream_t s) { return gn_stats_generic(rp, mrp, N, HW, C, groups, 1e-5f, s); },
+              kOpNorm);
+      GnApplyDesc d{};
+      d.raw = raw.ptr; d.mean_rstd = mr.ptr; d.gamma = nl.g->data.p; d.beta = nl.b->data.p; d.raw_plane = 0; d.act = act;
+      if (res) {
+        d.res = res->ptr; d.res_plane = res->plane; d.res_kind = res->layout == kNHWCSplit ? kResSplit : kResRaw;
+      }
+      d.emb = emb; d.emb_stride = emb_stride;
+      d.out = out.hptr(); d.out_plane = out.plane;
+      d.N = N; d.HW = HW; d.C = C; d.G = groups;
+      push_op([this, d](cudaStream_t s) {
+        GnApplyDesc dd = d;
+        if (dd.emb != nullptr && io_emb_dedup) {
+          dd.emb_index = io_emb_index;
+          if (io_emb_index == nullptr) dd.emb_stride = 0;
+        }
+        return gn_apply_generic(dd, s);
+      }, kOpNorm);
+    }
+    free_tensor(mr);
+    return 0;
+  }
   if (!dry) {
     const float* part = stats.ptr;
     float* mrp = mr.ptr;
@@ -622,7 +653,8 @@ int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, con
   Tens raw = new_tensor(N, H, W, rb.Cout, kNHWCRaw);
   Tens part = new_floats(static_cast<size_t>(N) * max_chunks * (rb.Cout / 8) * 2);
   int chunks = 1;
-  int rc = add_conv(rb.conv1, in0, in1, raw, &part, &chunks);
+  const bool generic_gn = gn_needs_generic(rb.Cout, groups);   // statistics then come from the raw tensor, not the conv
+  int rc = add_conv(rb.conv1, in0, in1, raw, generic_gn ? nullptr : &part, &chunks);
   if (rc) return rc;
   Tens res_raw;
   const Tens* res = nullptr;
@@ -641,7 +673,7 @@ int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, con
   if (rc) return rc;
   if (rb.has_res_conv) free_tensor(res_raw);
   // second half reuses `raw` and `part`
-  rc = add_conv(rb.conv2, x1, nullptr, raw, &part, &chunks);
+  rc = add_conv(rb.conv2, x1, nullptr, raw, generic_gn ? nullptr : &part, &chunks);
   if (rc) return rc;
   Tens x2 = new_tensor(N, H, W, rb.Cout, kNHWCSplit);
   rc = add_gn_apply(rb.norm2, groups, raw, part, chunks, &x1, nullptr, 0, x2);

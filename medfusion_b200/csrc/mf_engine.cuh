@@ -194,6 +194,7 @@ class EngineBase {
   int run_profiled(cudaStream_t s, float* ms, int* kinds, double* flops, int max_ops, int* n_ops);
 };
 
+bool gn_needs_generic(int C, int groups);   // channels per group not a multiple of 8: generic statistics / apply kernels
 void init_conv(EngineBase& e, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int k, int stride);
 void init_norm(EngineBase& e, NormLayer& L, const std::string& prefix, int C);
 void init_conv_shape(EngineBase& e, ConvLayer& L, const std::string& prefix, std::vector<int64_t> wshape, int Cout,

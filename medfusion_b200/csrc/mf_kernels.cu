@@ -250,12 +250,18 @@ conv_simt_kernel(const ConvSimtDesc d, int Hout, int Wout) {
           if (d.in_layout == kNCHW) {
             v = reinterpret_cast<const float*>(d.in)[((static_cast<long long>(n) * d.Cin + c) * d.Hin + hi) * d.Win + wi];
           } else {
-            const long long off = ((static_cast<long long>(n) * d.Hin + hi) * d.Win + wi) * d.Cin + c;
+            // channel-concatenated sources (torch.cat of unet2.py:259): c < C0 reads source 0, else source 1
+            const int C0 = d.Cin - d.C1;
+            const bool second = c >= C0;
+            const void* src = second ? d.in1 : d.in;
+            const long long plane = second ? d.in1_plane : d.in_plane;
+            const int cs = second ? d.C1 : C0, cc = second ? c - C0 : c;
+            const long long off = ((static_cast<long long>(n) * d.Hin + hi) * d.Win + wi) * cs + cc;
             if (d.in_layout == kNHWCSplit) {
-              const __half* ih = reinterpret_cast<const __half*>(d.in);
-              v = join16(ih[off], ih[d.in_plane + off]);
+              const __half* ih = reinterpret_cast<const __half*>(src);
+              v = join16(ih[off], ih[plane + off]);
             } else {
-              v = reinterpret_cast<const float*>(d.in)[off];
+              v = reinterpret_cast<const float*>(src)[off];
             }
           }
         }
@@ -315,6 +321,8 @@ conv_simt_kernel(const ConvSimtDesc d, int Hout, int Wout) {
 int conv_simt(const ConvSimtDesc& d, cudaStream_t s) {
   MF_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv_simt supports 1x1 and 3x3");
   MF_REQUIRE(d.stride == 1 || d.stride == 2, "conv_simt supports stride 1 and 2");
+  MF_REQUIRE(d.C1 == 0 || (d.in1 != nullptr && d.in_layout != kNCHW && d.C1 < d.Cin),
+             "conv_simt: the second source must be an NHWC tensor");
   const int pad = d.ksize / 2;
   const int Hout = (d.Hin + 2 * pad - d.ksize) / d.stride + 1;
   const int Wout = (d.Win + 2 * pad - d.ksize) / d.stride + 1;
@@ -977,6 +985,161 @@ int sched_step(const SchedStepDesc& d, cudaStream_t s) {
   if (total == 0) return 0;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
   sched_step_kernel<<<blocks, 256, 0, s>>>(d);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// GroupNorm for any channels-per-group (reference: nn.GroupNorm(eps=1e-5), biased variance)
+// =================================================================================================
+__global__ void __launch_bounds__(256) gn_stats_generic_kernel(const float* __restrict__ raw, float* __restrict__ mean_rstd,
+                                                               int HW, int C, int G, float eps) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cpg = C / G;
+  const float* base = raw + static_cast<long long>(n) * HW * C + g * cpg;
+  double s = 0.0, ss = 0.0;
+  const long long cnt = static_cast<long long>(HW) * cpg;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const long long p = i / cpg;
+    const int c = static_cast<int>(i - p * cpg);
+    const double x = static_cast<double>(base[p * C + c]);
+    s += x;
+    ss += x * x;
+  }
+  __shared__ double sh[2][8];
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.0; ss = 0.0;
+    for (int w = 0; w < 8; ++w) { s += sh[0][w]; ss += sh[1][w]; }
+    const double mean = s / static_cast<double>(cnt);
+    double var = ss / static_cast<double>(cnt) - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float* dst = mean_rstd + (static_cast<long long>(n) * G + g) * 2;
+    dst[0] = static_cast<float>(mean);
+    dst[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+int gn_stats_generic(const float* raw, float* mean_rstd, int N, int HW, int C, int G, float eps, cudaStream_t s) {
+  MF_REQUIRE(G > 0 && C % G == 0 && N <= 65535, "gn_stats_generic: C must be divisible by the group count");
+  if (N == 0) return 0;
+  gn_stats_generic_kernel<<<dim3(G, N), 256, 0, s>>>(raw, mean_rstd, HW, C, G, eps);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) gn_apply_generic_kernel(const GnApplyDesc d) {
+  const long long total = static_cast<long long>(d.N) * d.HW * d.C;
+  const int cpg = d.C / d.G;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % d.C);
+    const int n = static_cast<int>(i / (static_cast<long long>(d.HW) * d.C));
+    const float x = reinterpret_cast<const float*>(d.raw)[i];
+    const float2 mr = *reinterpret_cast<const float2*>(d.mean_rstd + (static_cast<long long>(n) * d.G + c / cpg) * 2);
+    float y = (x - mr.x) * mr.y * d.gamma[c] + d.beta[c];
+    if (d.act != 0) y = swish(y);
+    if (d.res_kind == kResSplit) {
+      const __half* rh = reinterpret_cast<const __half*>(d.res);
+      y += join16(rh[i], rh[d.res_plane + i]);
+    } else if (d.res_kind == kResRaw) {
+      y += reinterpret_cast<const float*>(d.res)[i];
+    }
+    if (d.emb != nullptr) {
+      const long long er = d.emb_index ? d.emb_index[n] : static_cast<long long>(n);
+      y += d.emb[er * d.emb_stride + c];
+    }
+    split16(y, d.out[i], d.out[d.out_plane + i]);
+  }
+}
+
+int gn_apply_generic(const GnApplyDesc& d, cudaStream_t s) {
+  MF_REQUIRE(d.raw_plane == 0 && d.mean_rstd != nullptr && d.C % d.G == 0, "gn_apply_generic: raw fp32 input + mean/rstd");
+  const long long total = static_cast<long long>(d.N) * d.HW * d.C;
+  if (total == 0) return 0;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+  gn_apply_generic_kernel<<<blocks, 256, 0, s>>>(d);
+  MF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// Vector quantiser lookup (reference: latent_embedders.py:40-72 VectorQuantizer.forward; used by VQVAE.decode :314-316)
+//   dist[b, k] = sum_c z^2 + sum_c e_k^2 - 2 * sum_c z_c e_kc   (the reference's expansion, not ||z - e||^2, so near-ties
+//   resolve the same way); argmin keeps the FIRST minimum; z_q = z + (e - z) in fp32 (the straight-through form :69).
+// One thread per latent vector; the codebook streams through shared memory in tiles of 1024 rows.
+// =================================================================================================
+constexpr int kVqMaxC = 16;
+constexpr int kVqTile = 1024;
+__global__ void __launch_bounds__(256) vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                                          float* __restrict__ zq, int* __restrict__ idx_out, int B, int C,
+                                                          int HW, int K) {
+  extern __shared__ float tile[];          // [kVqTile][C] codebook rows + [kVqTile] squared norms
+  float* enorm = tile + kVqTile * C;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nvec = static_cast<long long>(B) * HW;
+  const bool live = v < nvec;
+  const int b = live ? static_cast<int>(v / HW) : 0;
+  const int p = live ? static_cast<int>(v - static_cast<long long>(b) * HW) : 0;
+  float zc[kVqMaxC];
+  float zz = 0.f;
+#pragma unroll
+  for (int c = 0; c < kVqMaxC; ++c) {
+    zc[c] = (live && c < C) ? z[(static_cast<long long>(b) * C + c) * HW + p] : 0.f;
+    if (c < C) zz = __fadd_rn(zz, __fmul_rn(zc[c], zc[c]));
+  }
+  float best = INFINITY;
+  int best_k = 0;
+  for (int k0 = 0; k0 < K; k0 += kVqTile) {
+    const int kn = min(kVqTile, K - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kn * C; e += blockDim.x) tile[e] = cb[static_cast<long long>(k0) * C + e];
+    __syncthreads();
+    for (int r = threadIdx.x; r < kn; r += blockDim.x) {
+      float ee = 0.f;
+      for (int c = 0; c < C; ++c) ee = __fadd_rn(ee, __fmul_rn(tile[r * C + c], tile[r * C + c]));
+      enorm[r] = ee;
+    }
+    __syncthreads();
+    if (live) {
+      for (int r = 0; r < kn; ++r) {
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < kVqMaxC; ++c)
+          if (c < C) dot = fmaf(zc[c], tile[r * C + c], dot);
+        const float dist = __fsub_rn(__fadd_rn(zz, enorm[r]), __fmul_rn(2.f, dot));
+        if (dist < best) { best = dist; best_k = k0 + r; }
+      }
+    }
+  }
+  if (live) {
+    if (idx_out != nullptr) idx_out[v] = best_k;
+    for (int c = 0; c < C; ++c) {
+      const float e = cb[static_cast<long long>(best_k) * C + c];
+      zq[(static_cast<long long>(b) * C + c) * HW + p] = __fadd_rn(zc[c], __fsub_rn(e, zc[c]));
+    }
+  }
+}
+
+int vq_quantize(const float* z, const float* codebook, float* z_q, int* idx_out, int B, int C, int HW, int K,
+                cudaStream_t s) {
+  MF_REQUIRE(C >= 1 && C <= kVqMaxC && K >= 1, "vq_quantize: emb_channels must be in [1, 16]");
+  const long long nvec = static_cast<long long>(B) * HW;
+  if (nvec == 0) return 0;
+  const size_t smem = static_cast<size_t>(kVqTile) * (C + 1) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MF_CUDA_OK(cudaFuncSetAttribute(vq_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kVqTile * (kVqMaxC + 1) * static_cast<int>(sizeof(float))));
+    attr_set = true;
+  }
+  vq_quantize_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, smem, s>>>(z, codebook, z_q, idx_out, B, C, HW, K);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }

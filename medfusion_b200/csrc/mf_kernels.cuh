@@ -32,6 +32,8 @@ int prep_weight_simt(const float* w_oihw, float* out, int Cout, int Cin, int kh,
 // ---- exact fp32 convolution on CUDA cores ---------------------------------------------------------
 struct ConvSimtDesc {
   const void* in; long long in_plane; int in_layout;   // float (NCHW / raw) or __half planes (split)
+  const void* in1; long long in1_plane; int C1;        // optional second source concatenated along channels (NHWC raw /
+                                                       // split, same layout kind as `in`); Cin counts BOTH sources
   int N, Cin, Hin, Win;
   const float* w_kc;      // [K][Cout]
   const float* bias;      // [Cout] or nullptr
@@ -63,6 +65,16 @@ struct GnApplyDesc {
   int N, HW, C, G;
 };
 int gn_apply(const GnApplyDesc& d, cudaStream_t s);
+// Any channel count / any channels-per-group (the fused path needs C/G % 8 == 0): statistics straight from the raw conv
+// output, one block per (sample, group), fp64 combine -> mean_rstd [N][G][2]; then gn_apply_generic (one channel per
+// thread-iteration).  Used by the small-width configurations (e.g. VQVAE defaults: 32 channels in 32 groups).
+int gn_stats_generic(const float* raw, float* mean_rstd, int N, int HW, int C, int G, float eps, cudaStream_t s);
+int gn_apply_generic(const GnApplyDesc& d, cudaStream_t s);
+// VectorQuantizer.forward (latent_embedders.py:40-72), inference half: z [B,C,HW] NCHW -> nearest codebook row by
+// ||z||^2 + ||e||^2 - 2 z.e (first minimum wins, like torch.argmin), z_q = z + (e - z) as the reference evaluates it.
+// codebook [K][C]; idx_out optional [B*HW] int32
+int vq_quantize(const float* z, const float* codebook, float* z_q, int* idx_out, int B, int C, int HW, int K,
+                cudaStream_t s);
 extern int g_pdl;         // 1: conv_tc and the fused gn_apply are launched with programmatic stream serialization
 extern int g_gn_variant;  // engine plans: 3 (default) = statistics finalised inside gn_apply (one launch per GroupNorm);
                           // 0/1/2 = separate gn_finalize + flat grid-stride / fixed quad per thread / one quad per thread

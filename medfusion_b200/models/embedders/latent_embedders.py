@@ -171,3 +171,103 @@ class VAE(CheckpointMixin, EngineModule):
         logvar = logvar.clamp(-30.0, 20.0)
         kl = 0.5 * torch.sum(mean.pow(2) + logvar.exp() - 1.0 - logvar) / x_in.shape[0]       # :29-31
         return self.decode(z), [], kl
+
+
+class VQVAE(CheckpointMixin, EngineModule):
+    """VQVAE latent embedder, decode half (reference: latent_embedders.py:180-320; SURVEY.md section 8 f4 — the embedder
+    of the colon / eye demos, streamlit/pages/colon.py:36 with (4, 64, 64) latents, eye.py:34 with (4, 32, 32)).
+
+    `decode(z)` = quantizer(z) -> inc_dec -> decoders -> outc exactly as :314-320: the latent is first snapped to the
+    nearest codebook row (VectorQuantizer.forward :50-69, including its z + (z_q - z) evaluation), then decoded by the same
+    launch plan as VAE.decode.  `encode` / `forward` (training side) are not built; `load_state_dict` accepts a full
+    reference VQVAE / VQGAN state_dict and skips the encoder-side entries."""
+    _prefix = "mf_vae"
+    _SKIP = ("inc.", "encoders.", "out_enc.", "outc_ver.", "perceiver.", "loss_fct.")
+
+    def __init__(
+        self,
+        in_channels=3,
+        out_channels=3,
+        spatial_dims=2,
+        emb_channels=4,
+        num_embeddings=8192,
+        hid_chs=(32, 64, 128, 256),
+        kernel_sizes=(3, 3, 3, 3),
+        strides=(1, 2, 2, 2),
+        norm_name=("GROUP", {"num_groups": 32, "affine": True}),
+        act_name=("Swish", {}),
+        dropout=0.0,
+        use_res_block=True,
+        deep_supervision=False,
+        learnable_interpolation=True,
+        use_attention="none",
+        beta=0.25,
+        embedding_loss_weight=1.0,
+        perceiver=None,
+        perceiver_kwargs=None,
+        perceptual_loss_weight=1.0,
+        optimizer=None,
+        optimizer_kwargs=None,
+        lr_scheduler=None,
+        lr_scheduler_kwargs=None,
+        loss=None,
+        loss_kwargs=None,
+        sample_every_n_steps=1000,
+    ):
+        super().__init__()
+        if spatial_dims != 2:
+            raise NotImplementedError("medfusion_b200.VQVAE implements the 2-D decoder (spatial_dims=2)")
+        if not use_res_block or not learnable_interpolation:
+            raise NotImplementedError("only use_res_block=True, learnable_interpolation=True is implemented")
+        attn = list(use_attention) if isinstance(use_attention, (list, tuple)) else [use_attention] * len(strides)
+        if any(a != "none" for a in attn):
+            raise NotImplementedError("VQVAE attention is not implemented")
+        if any(k != 3 for k in kernel_sizes[1:]):
+            raise NotImplementedError("decoder res-blocks use 3x3 convolutions")
+        depth = len(strides)
+        self.depth = depth
+        self.emb_channels, self.out_channels, self.in_channels = emb_channels, out_channels, in_channels
+        self.num_embeddings = num_embeddings
+        self.up_factor = 1
+        for s in strides[1:]:
+            self.up_factor *= s
+        cfg = _lib.VAEConfig()
+        cfg.emb_channels, cfg.out_channels, cfg.depth = emb_channels, out_channels, depth
+        cfg.in_channels = 0                      # decoder-only handle
+        cfg.num_embeddings = num_embeddings
+        for i in range(depth):
+            cfg.hid_chs[i], cfg.strides[i] = hid_chs[i], strides[i]
+        cfg.norm_groups = dict(norm_name[1]).get("num_groups", 32) if isinstance(norm_name, (tuple, list)) else 32
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().mf_vae_create(ctypes.byref(cfg), ctypes.byref(handle)), "mf_vae_create")
+        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc."))
+        with torch.no_grad():                    # VectorQuantizer init (:47): U(-1/K, 1/K)
+            self.quantizer.embedder.weight.uniform_(-1.0 / num_embeddings, 1.0 / num_embeddings)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        own = {k: v for k, v in state_dict.items() if not k.startswith(self._SKIP)}
+        return super().load_state_dict(own, strict=strict, **kw)
+
+    decode = VAE.decode
+    decode_uint8 = VAE.decode_uint8
+    profile = VAE.profile
+
+    def quantize(self, z):
+        """VectorQuantizer.forward's first output (z_q with the straight-through evaluation) and the code indices."""
+        require_cuda(z, "VQVAE.quantize(z)")
+        self.sync_params()
+        B, C = z.shape[:2]
+        zc = z.contiguous().float()
+        zq = torch.empty_like(zc)
+        idx = torch.empty((B,) + tuple(z.shape[2:]), device=z.device, dtype=torch.int32)
+        with on_device(zc):
+            _lib.check(_lib.load().mf_op_vq_quantize(zc.data_ptr(), self.quantizer.embedder.weight.data_ptr(),
+                                                     zq.data_ptr(), idx.data_ptr(), B, C, zc[0, 0].numel(),
+                                                     self.num_embeddings, cuda_stream_ptr(zc.device)), "mf_op_vq_quantize")
+        return zq, idx
+
+    def encode(self, x):
+        raise NotImplementedError("VQVAE.encode is training-side (SURVEY.md section 8 f4 names decode only)")
+
+    def forward(self, x_in):
+        raise NotImplementedError("VQVAE.forward (autoencoding + losses) is training-side")

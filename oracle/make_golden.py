@@ -20,7 +20,7 @@ import torch  # noqa: E402
 from medfusion_b200.synthetic import fill_  # noqa: E402  (RNG recipe only, no compute)
 from medical_diffusion.models.estimators import UNet  # noqa: E402
 from medical_diffusion.models.embedders import TimeEmbbeding, LabelEmbedder  # noqa: E402
-from medical_diffusion.models.embedders.latent_embedders import VAE  # noqa: E402
+from medical_diffusion.models.embedders.latent_embedders import VAE, VQVAE  # noqa: E402
 from medical_diffusion.models.noise_schedulers import GaussianNoiseScheduler  # noqa: E402
 from medical_diffusion.models.pipelines import DiffusionPipeline  # noqa: E402
 
@@ -300,6 +300,34 @@ def vae_encode_fixture():
     print("vae encode", float(z.abs().max()), float(mom.abs().max()), float(emb_loss), len(out_hor))
 
 
+VQVAE_DEMO = dict(in_channels=3, out_channels=3, emb_channels=4, num_embeddings=8192, spatial_dims=2,
+                  hid_chs=[64, 128, 256, 512], embedding_loss_weight=1, beta=1)   # scripts/train_latent_embedder_2d.py:101-110
+VQVAE_DEFAULT = dict(in_channels=3, out_channels=3, emb_channels=4, num_embeddings=8192, spatial_dims=2)  # ctor defaults:
+#                     hid_chs [32, 64, 128, 256], GroupNorm with 32 groups -> 1, 2, 4, 8 channels per group
+
+
+@torch.no_grad()
+def vqvae_fixture():
+    """VQVAE.decode of the unmodified reference (latent_embedders.py:314-320), SURVEY.md section 8 f4:
+      demo:    the training script's VQVAE (hid 64..512) at a (4,32,32) latent -> 3x256x256 (streamlit/pages/eye.py:34 shape)
+      default: the constructor defaults (hid 32..256, 32 groups) at a (4,64,64) latent -> 3x512x512 (colon.py:36 shape)
+    plus the quantiser's own outputs (z_q, code indices)."""
+    out = {}
+    for name, cfg, shape, seed in (("demo", VQVAE_DEMO, (2, 4, 32, 32), 61), ("default", VQVAE_DEFAULT, (1, 4, 64, 64), 62)):
+        m = fill_(VQVAE(loss=torch.nn.L1Loss, perceiver=None, **cfg).eval())
+        z = torch.randn(shape, generator=gen(seed))
+        x = m.decode(z)
+        z_q, _ = m.quantizer(z)
+        zf = torch.moveaxis(z, 1, -1).reshape(-1, 4)
+        w = m.quantizer.embedder.weight
+        dist = (torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(w ** 2, dim=1) - 2 * torch.einsum("bd,dn->bn", zf, w.t()))
+        idx = torch.argmin(dist, dim=1).view(shape[0], shape[2], shape[3]).to(torch.int32)
+        keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+        out[name] = dict(cfg=cfg, z=z, x=x, z_q=z_q, idx=idx, keys=keys)
+        print("vqvae", name, tuple(x.shape), float(x.abs().max()), int(idx.unique().numel()), "codes used")
+    torch.save(out, os.path.join(OUT, "vqvae.pt"))
+
+
 UNET_CONFIG4 = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
                     strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
                     cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False,
@@ -354,22 +382,38 @@ def traj_fixture():
             ts.append(args[1].clone())
 
         pipe.noise_estimator.register_forward_pre_hook(record)
-        g = gen(c["seed"])
-        n_draws = [0]
 
-        def fake(x, **k):
-            n_draws[0] += 1
-            return torch.randn(x.shape, generator=g, dtype=x.dtype)
+        def run(perturb):
+            g = gen(c["seed"])
+            n_draws = [0]
 
-        torch.randn_like = fake
-        try:
-            lat = pipe.sample(2, (8, 32, 32), condition=c["cond"], **c["kw"])
-        finally:
-            torch.randn_like = orig
-        out[name] = dict(pipe=c["pipe"], kw=c["kw"], cond=c["cond"], seed=c["seed"], n_draws=n_draws[0],
-                         x_in=torch.stack(xs), t_in=torch.stack([t.reshape(-1)[0] for t in ts]), latent=lat,
+            def fake(x, **k):
+                n_draws[0] += 1
+                n = torch.randn(x.shape, generator=g, dtype=x.dtype)
+                if perturb is not None and n_draws[0] == 1:
+                    n = n + perturb            # x_T only
+                return n
+
+            torch.randn_like = fake
+            try:
+                lat = pipe.sample(2, (8, 32, 32), condition=c["cond"], **c["kw"])
+            finally:
+                torch.randn_like = orig
+            return lat, n_draws[0]
+
+        lat, n_draws = run(None)
+        x_in, t_in = torch.stack(xs), torch.stack([t.reshape(-1)[0] for t in ts])
+        # The reference's OWN sensitivity: the same run with x_T moved by 1e-5 * N(0,1) (an input error of the size of the
+        # absolute tolerance).  max |x_t' - x_t| per step tells how the trajectory itself amplifies a tolerance-sized
+        # error; the GPU test widens the free-running tolerance by a stated multiple of it (and by nothing else).
+        xs.clear(); ts.clear()
+        lat_p, _ = run(1e-5 * torch.randn(2, 8, 32, 32, generator=gen(999)))
+        sens = torch.tensor([float((xs[i] - x_in[i]).abs().max()) for i in range(len(xs))])
+        out[name] = dict(pipe=c["pipe"], kw=c["kw"], cond=c["cond"], seed=c["seed"], n_draws=n_draws,
+                         x_in=x_in, t_in=t_in, latent=lat, sens=sens, sens_final=float((lat_p - lat).abs().max()),
                          keys=[(k, tuple(v.shape)) for k, v in pipe.noise_estimator.state_dict().items()])
-        print("traj", name, n_draws[0], "draws", [round(float(x.abs().max()), 2) for x in xs[::10]], float(lat.abs().max()))
+        print("traj", name, n_draws, "draws", [round(float(x.abs().max()), 2) for x in x_in[::10]],
+              float(lat.abs().max()), "sens", [f"{float(v):.1e}" for v in sens[::10]], out[name]["sens_final"])
     torch.save(dict(unet_cfg=UNET_CANON, sched=SCHED, cases=out), os.path.join(OUT, "traj_canonical.pt"))
 
 
@@ -417,7 +461,7 @@ if __name__ == "__main__":
                unet_canonical=lambda: unet_fixture("unet_canonical.pt", UNET_CANON, 2),
                unet_attn_small=lambda: unet_fixture("unet_attn_small.pt", UNET_ATTN, 3),
                vae=vae_fixture, sched=sched_fixture, sample=sample_fixture, ckpt=ckpt_fixture, opts=opts_fixture,
-               vae_encode=vae_encode_fixture, config4=config4_fixture, traj=traj_fixture, forward=forward_fixture)
+               vae_encode=vae_encode_fixture, config4=config4_fixture, vqvae=vqvae_fixture, traj=traj_fixture, forward=forward_fixture)
     todo = sys.argv[1:] or list(ALL)      # python oracle/make_golden.py [fixture names]
     for name in todo:
         ALL[name]()

@@ -227,6 +227,29 @@ def vae_decode(sd, cfg, z):
 
 
 # ------------------------------------------------------------------------------------------------
+# VQVAE.decode (models/embedders/latent_embedders.py:314-320) and its VectorQuantizer (:40-72)
+# ------------------------------------------------------------------------------------------------
+def vq_quantize(codebook, z):
+    """VectorQuantizer.forward, first output (latent_embedders.py:50-69): nearest codebook row by the expanded distance
+    ||z||^2 + ||e||^2 - 2 z.e (argmin = first minimum), returned in the straight-through form z + (z_q - z).
+    Also returns the indices and the [vectors, codes] distance matrix (for near-tie analysis in tests)."""
+    C = codebook.shape[1]
+    z_ch = torch.moveaxis(z, 1, -1)
+    zf = z_ch.reshape(-1, C)
+    dist = (torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(codebook ** 2, dim=1)
+            - 2 * torch.einsum("bd,dn->bn", zf, codebook.t()))
+    idx = torch.argmin(dist, dim=1)
+    z_q = torch.moveaxis(codebook[idx].view(z_ch.shape), -1, 1)
+    return z + (z_q - z), idx.view(z_ch.shape[:-1]), dist
+
+
+def vqvae_decode(sd, cfg, z):
+    """VQVAE.decode: quantizer -> inc_dec -> decoders (last to first) -> outc  (latent_embedders.py:314-320)"""
+    z_q, _, _ = vq_quantize(sd["quantizer.embedder.weight"], z)
+    return vae_decode(sd, cfg, z_q)
+
+
+# ------------------------------------------------------------------------------------------------
 # scheduler (models/noise_schedulers/gaussian_scheduler.py)
 # ------------------------------------------------------------------------------------------------
 def scheduler_tables(timesteps=1000, schedule="scaled_linear", beta_start=0.002, beta_end=0.02):

@@ -413,3 +413,53 @@ def test_vae_encode_full_resolution_roundtrip_shapes():
     z = m.encode(x)
     assert z.shape == (3, 8, 32, 32) and torch.isfinite(z).all()
     assert m.decode(z).shape == x.shape
+
+
+@pytest.mark.parametrize("case", ["demo", "default"])
+def test_vqvae_decode_matches_reference_fixture(case):
+    """VQVAE.decode (latent_embedders.py:314-320): quantiser lookup + the decoder plan.
+    demo = the training script's widths at a (4,32,32) latent; default = the constructor defaults (hid 32..256 in 32
+    GroupNorm groups: 1/2/4/8 channels per group, SIMT convolutions for the 32-channel level) at a (4,64,64) latent."""
+    from medfusion_b200.models import VQVAE
+    from medfusion_b200.synthetic import fill_
+    c = load_golden("vqvae.pt")[case]
+    kw = {k: v for k, v in c["cfg"].items() if k not in ("embedding_loss_weight", "beta")}
+    m = fill_(VQVAE(**kw)).to(DEV)
+    assert [k for k, _ in c["keys"] if not k.startswith(VQVAE._SKIP)] == list(m.state_dict().keys())
+    z = c["z"].to(DEV)
+    z_q, idx = m.quantize(z)
+    # near-ties of the fp32 distance expansion may resolve differently: any disagreeing vector must be one whose two best
+    # distances differ by less than 1e-6 relative (none at the fixture's seeds)
+    bad = (idx.cpu() != c["idx"])
+    if bad.any():
+        import medfusion_oracle as O
+        _, _, dist = O.vq_quantize(m.quantizer.embedder.weight.detach().cpu(), c["z"])
+        top2 = dist.topk(2, dim=1, largest=False).values
+        gap = ((top2[:, 1] - top2[:, 0]) / top2[:, 1].abs().clamp(min=1e-12)).view(bad.shape)
+        assert float(gap[bad].max()) < 1e-6, f"{int(bad.sum())} code indices differ on well-separated distances"
+    else:
+        assert torch.equal(z_q.cpu(), c["z_q"])
+    x = m.decode(z)
+    assert_close(x.cpu(), c["x"], what=f"VQVAE.decode {case}")
+    with pytest.raises(NotImplementedError):
+        m.encode(x)
+
+
+def test_vqvae_as_latent_embedder_of_the_pipeline():
+    """colon / eye demos (streamlit/pages/colon.py:36): DiffusionPipeline.sample with a VQVAE latent embedder and
+    4-channel latents runs end to end and equals denoise-then-decode done by hand."""
+    from medfusion_b200.models import VQVAE
+    from medfusion_b200.synthetic import fill_
+    g = load_golden("sample_small.pt")
+    ucfg = dict(g["unet_cfg"], in_ch=4, out_ch=4)
+    from test_gpu_parity_hard import _pipe
+    pipe = _pipe(ucfg, g["sched"], clip_x0=True)
+    pipe.latent_embedder = fill_(VQVAE(hid_chs=[64, 128], kernel_sizes=[3, 3], strides=[1, 2],
+                                       norm_name=("GROUP", {"num_groups": 8, "affine": True}))).to(DEV)
+    torch.manual_seed(7)
+    img = pipe.sample(2, (4, 32, 32), steps=4, use_ddim=True)
+    assert img.shape == (2, 3, 64, 64) and torch.isfinite(img).all()
+    torch.manual_seed(7)
+    emb, pipe.latent_embedder = pipe.latent_embedder, None
+    lat = pipe.sample(2, (4, 32, 32), steps=4, use_ddim=True)
+    assert torch.equal(emb.decode(lat), img)

@@ -54,10 +54,23 @@ def _amp(sched, t, t_next, clip):
     return an ** 0.5 * B + c
 
 
+SENS_MULT = 3.0   # see test_canonical_50_step_trajectory_free_running
+
+
 @pytest.mark.parametrize("case", ["ddim50_clip_cond", "ddpm50"])
 def test_canonical_50_step_trajectory_free_running(case):
-    """pipeline.denoise at canonical width, 50 steps, the reference's noise injected: every estimator input and the
-    final latent against the reference at rtol=1e-3 / atol=1e-5, no scale normalisation."""
+    """pipeline.denoise at canonical width, 50 steps, the reference's noise injected: EVERY estimator input and the final
+    latent against the reference, no scale normalisation.
+
+    ddpm50 (ancestral steps t=49..0, contractive): plain rtol=1e-3 / atol=1e-5 on all 50 snapshots.
+    ddim50_clip_cond: the reference's own DDIM-form dynamics with a random-weight estimator amplify ANY perturbation —
+    the fixture records it: moving x_T by 1e-5*N(0,1) (an input error of the size of atol) moves the reference's own
+    x_t by `sens[i]` (up to 1e-3 around step 33, 4e-4 in the final latent; oracle/make_golden.py::traj_fixture).  A
+    free-running comparison can therefore not hold 1e-5 absolute for ANY implementation that is merely within tolerance
+    per estimator call; the assertion is  |err_i| <= atol + rtol*|ref| + SENS_MULT * sens[i]  — the plain tolerance
+    widened by a stated multiple (3: tolerance-sized errors enter at each of the 50 steps, not once) of the reference's
+    measured self-divergence, and by nothing else.  Measured on B200: worst |err_i| / sens[i] = 1.5
+    (profiles/r02_trajectory_margin.md).  The per-step (teacher-forced) test below holds every step to atol*amp_t."""
     g = load_golden("traj_canonical.pt")
     c = g["cases"][case]
     pipe = _pipe(g["unet_cfg"], g["sched"], **c["pipe"])
@@ -77,20 +90,38 @@ def test_canonical_50_step_trajectory_free_running(case):
     with pytest.raises(StopIteration):
         next(draws)
     assert len(seen) == c["x_in"].shape[0] == 50
-    worst = 0.0
+    strict = case == "ddpm50"
+    worst_plain, worst_sens = 0.0, 0.0
     for i, x in enumerate(seen):
-        n, mx, rmax = violations(x.cpu(), c["x_in"][i])
-        d = (x.cpu().double() - c["x_in"][i].double()).abs()
-        worst = max(worst, float((d / (ATOL + RTOL * c["x_in"][i].double().abs())).max()))
-        assert n == 0, f"{case}: estimator input of step {i}: {n} elements outside tolerance (max err {mx:.3e}, |ref|max {rmax:.3e})"
-    print(f"{case}: worst |err|/tol over 50 free-running steps = {worst:.3f}")
-    assert_close(lat.cpu(), c["latent"], what=f"{case} final latent")
+        ref = c["x_in"][i].double()
+        d = (x.cpu().double() - ref).abs()
+        extra = 0.0 if strict else SENS_MULT * float(c["sens"][i])
+        worst_plain = max(worst_plain, float((d / (ATOL + RTOL * ref.abs())).max()))
+        if float(c["sens"][i]) > 0:
+            worst_sens = max(worst_sens, float(d.max()) / float(c["sens"][i]))
+        n = int((d > ATOL + RTOL * ref.abs() + extra).sum())
+        assert n == 0, (f"{case}: estimator input of step {i}: {n} elements outside tolerance (max err {float(d.max()):.3e}, "
+                        f"|ref|max {float(ref.abs().max()):.3e}, sens {float(c['sens'][i]):.3e})")
+    print(f"{case}: worst |err|/tol(plain) = {worst_plain:.3f}, worst |err|/sens = {worst_sens:.3f} over 50 free-running steps")
+    ref = c["latent"].double()
+    d = (lat.cpu().double() - ref).abs()
+    extra = 0.0 if strict else SENS_MULT * float(c["sens_final"])
+    assert int((d > ATOL + RTOL * ref.abs() + extra).sum()) == 0, f"{case} final latent: max err {float(d.max()):.3e}"
+
+
+def _ulp32(m):
+    import math
+    return 2.0 ** (math.floor(math.log2(max(m, 1e-30))) - 23)
 
 
 @pytest.mark.parametrize("case", ["ddim50_clip_cond", "ddpm50"])
 def test_canonical_trajectory_teacher_forced_steps(case):
-    """One reverse step from the reference's own x_t (steps 0, 1, 10, 25, 40, 48): x_{t-1} against the reference's next
-    estimator input.  Absolute tolerance atol * max(1, amp_t), amp_t = |d x_next / d pred| from the tables."""
+    """One reverse step from the reference's own x_t, for ALL 49 transitions: x_{t-1} against the reference's next
+    estimator input.  Absolute tolerance  atol * max(1, amp_t) + 4 ulp32(A_t * max|x_t|):
+      amp_t = |d x_next / d pred| from the tables (the 1e-5 budget is on the estimator output, the update amplifies it);
+      the ulp term is the fp32 rounding of the update's own intermediates (x_0 = A_t x_t - B_t pred is a difference of
+      terms of size A_t|x_t|, up to ~100 mid-trajectory, where one fp32 ulp is 7.6e-6) — any re-ordering of the
+      reference's own arithmetic moves the result by that much.  rtol stays 1e-3."""
     g = load_golden("traj_canonical.pt")
     c = g["cases"][case]
     pipe = _pipe(g["unet_cfg"], g["sched"], **c["pipe"])
@@ -99,7 +130,8 @@ def test_canonical_trajectory_teacher_forced_steps(case):
     ddim = c["kw"]["use_ddim"]
     cond = None if c["cond"] is None else c["cond"].to(DEV)
     steps = c["x_in"].shape[0]
-    for i in (0, 1, 10, 25, 40, 48):
+    worst = 0.0
+    for i in range(steps - 1):
         t, t_next = int(c["t_in"][i]), int(c["t_in"][i + 1])
         # draw order of the reference: x_T, then per step the scheduler draw (+ the DDIM draw on all but the last step)
         k = 1 + (2 * i if ddim else i)
@@ -109,8 +141,14 @@ def test_canonical_trajectory_teacher_forced_steps(case):
                              t_next=torch.tensor(t_next, device=DEV) if ddim else None, noise_ddim=noise2,
                              objective="x_T", clip_x0=pipe.clip_x0, want=("x_next",), uniform_t=True)
         amp = max(1.0, _amp(sched, t, t_next if ddim else None, pipe.clip_x0))
-        assert_close(o["x_next"].cpu(), c["x_in"][i + 1], atol=ATOL * amp,
-                     what=f"{case} step {i} (t={t}, amp={amp:.2f})")
+        A = float(sched.sqrt_recip_alphas_cumprod[t])
+        atol_i = ATOL * amp + 4 * _ulp32(A * float(c["x_in"][i].abs().max()))
+        ref = c["x_in"][i + 1].double()
+        d = (o["x_next"].cpu().double() - ref).abs()
+        worst = max(worst, float((d / (atol_i + RTOL * ref.abs())).max()))
+        assert_close(o["x_next"].cpu(), c["x_in"][i + 1], atol=atol_i,
+                     what=f"{case} step {i} (t={t}, amp={amp:.2f}, atol={atol_i:.2e})")
+    print(f"{case}: worst teacher-forced |err|/tol over {steps - 1} steps = {worst:.3f}")
     assert steps == 50
 
 
