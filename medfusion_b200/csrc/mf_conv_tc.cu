@@ -22,15 +22,22 @@ struct TcCfg {
   static constexpr int kBRows = BLOCK_N / CG;            // weight rows this CTA stages (a CTA pair splits B)
   static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kAuxBytes = 2560;                 // barriers, TMEM slot, stats scratch
-  static constexpr int kStagesFit = (225 * 1024 - kAuxBytes - 1024) / kStageBytes;
+  // epilogue staging: per column half one [128 rows][128 B] tile (32 fp32 channels, or 32 fp16 channels hi | lo) that a
+  // single thread hands to the TMA store engine — the global write is one bulk tensor store per 16 KB, not 32
+  // row-strided STG.128 per thread (profiles/r02_conv_tc_ncu_32x32_before.md: the old epilogue cost 24 k cycles per tile)
+  static constexpr int kStagingHalf = kTcBlockM * 128;
+  static constexpr int kStagingBytes = 2 * kStagingHalf;
+  static constexpr int kRedBytes = 4 * (BLOCK_N / 8) * 2 * 4;   // GroupNorm partial sums [4 quarters][BLOCK_N/8][2]
+  static constexpr int kAuxBytes = 512 + kRedBytes + BLOCK_N * 4;   // barriers + TMEM slot | red | bias
+  static constexpr int kSmemMax = 227 * 1024;
+  static constexpr int kStagesFit = (kSmemMax - kAuxBytes - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kAuxBytes;
   static constexpr int kAccBufs = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);  // ring of partial-sum accumulators
   static constexpr int kTmemCols = kAccBufs * BLOCK_N;   // 512 columns for BLOCK_N >= 128
   static constexpr int kColsPerWarp = BLOCK_N / 2;       // 8 drain warps: 4 lane quarters x 2 column halves
   static_assert(kStages >= 2, "pipeline needs at least two stages");
-  static_assert(4 * (BLOCK_N / 8) * 2 * 4 + 512 <= kAuxBytes, "aux region too small");
+  static_assert(kSmemBytes <= kSmemMax, "shared memory budget");
 };
 
 // Why the accumulation leaves the tensor core: tcgen05.mma adds into its fp32 TMEM accumulator with
@@ -57,19 +64,27 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, CG>;
   constexpr int CPW = Cfg::kColsPerWarp;
   constexpr int NB = Cfg::kAccBufs;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Programmatic dependent launch: let the next kernel of the stream be scheduled as this one's CTAs retire (it parks
   // at its own griddepcontrol.wait until this grid has completed), and run our own set-up — barrier init, TMEM
   // allocation, cluster handshake — while the previous kernel drains.  Both are no-ops without the launch attribute.
   pdl_launch_dependents();
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* aux = smem + Cfg::kStages * Cfg::kStageBytes;
+  // swizzled TMA tiles need 1024-byte alignment; the dynamic segment starts at the CTA's shared window (no static
+  // shared memory in this kernel), which is aligned — checked, not assumed
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("mf: conv_tc dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;   // [2 column halves][16 KB]
+  uint8_t* aux = staging + Cfg::kStagingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);  // [kStages] TMA -> MMA (leader CTA's are the live ones)
   uint64_t* empty_bar = full_bar + Cfg::kStages;           // [kStages] MMA -> TMA (every CTA)
   uint64_t* acc_full_bar = empty_bar + Cfg::kStages;       // [NB] MMA -> drain (every CTA)
   uint64_t* acc_empty_bar = acc_full_bar + NB;             // [NB] drain -> MMA (leader CTA's)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + NB);
   float* red = reinterpret_cast<float*>(aux + 512);        // [4 quarters][BLOCK_N/8][2]
+  float* bias_s = reinterpret_cast<float*>(aux + 512 + Cfg::kRedBytes);   // [BLOCK_N] bias of the current tile's columns
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +123,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.a[1]);
     tma_prefetch_desc(&maps.w);
+    tma_prefetch_desc(&maps.o[0]);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -266,6 +282,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       const int kb0 = static_cast<int>(u - static_cast<long long>(tile) * nkb);
       const int kb1 = static_cast<int>(min(static_cast<long long>(nkb), kb0 + (u_end - u)));
       const int nchunks = (kb1 - kb0 + drain - 1) / drain;
+      // this tile's bias value for column `te`: requested now, consumed by the epilogue a whole K loop later
+      float bias_reg = 0.f;
+      if (kb0 == 0 && p.bias != nullptr && te < BLOCK_N)
+        bias_reg = __ldg(p.bias + static_cast<int>((tile / p.m_groups) % p.n_tiles) * BLOCK_N + te);
       float acc[CPW];
 #pragma unroll
       for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
@@ -297,7 +317,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
         for (int i = 0; i < CPW; i += 4)
           __stcg(reinterpret_cast<float4*>(prow + i), make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        named_bar_sync(1, 256);
         if (te == 0) {
           int* flag = p.sk_flags + blockIdx.x;
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
@@ -318,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
                 if (++spins > (1 << 28)) { printf("mf: stream-K flag timeout cta=%d waits for %d\n", blockIdx.x, other_cta); __trap(); }
               } while (v == 0);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            named_bar_sync(1, 256);
             const float* orow = p.sk_partials + static_cast<long long>(other_cta) * (kTcBlockM * 256) +
                                 static_cast<long long>(row) * BLOCK_N + col0;
 #pragma unroll
@@ -326,12 +346,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
               const float4 o = __ldcg(reinterpret_cast<const float4*>(orow + i));
               acc[i] += o.x; acc[i + 1] += o.y; acc[i + 2] += o.z; acc[i + 3] += o.w;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            named_bar_sync(1, 256);
             if (te == 0) p.sk_flags[other_cta] = 0;   // re-arm for the next launch (CUDA-graph replay safe)
             covered = min(tile_end, g2_end);
           }
         }
-        // ---- epilogue from registers
+        // ---- epilogue: registers -> (+bias, statistics, optional residual / vector) -> swizzled staging tile -> TMA store
         const TileCoord tc = decode_tile(tile);
         const int oa = tc.phase >> 1, ob = tc.phase & 1;
         const int nt = tc.nt;
@@ -342,15 +362,22 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
         const bool valid = n < p.N;
         const long long pix = (static_cast<long long>(n) * (p.H * osf) + h * osf + oa) * (p.W * osf) + w * osf + ob;
         const long long ooff = pix * p.Cout + nt * BLOCK_N + col0;
+        const CUtensorMap* omap = &maps.o[tc.phase];
+        uint8_t* stg = staging + half * Cfg::kStagingHalf;
+        const uint32_t stg_u = smem_u32(stg);
+        const bool issuer = (q == 0) && (lane == 0);        // one thread per column half owns the bulk store groups
+
+        if (te < BLOCK_N) bias_s[te] = bias_reg;
+        named_bar_sync(1, 256);
 
 #pragma unroll
         for (int ch = 0; ch < CPW / 32; ++ch) {
           float* v = &acc[ch * 32];
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + col0 + ch * 32);
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + col0 + ch * 32);   // broadcast LDS
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              const float4 b = __ldg(b4 + jj);
+              const float4 b = b4[jj];
               v[4 * jj + 0] += b.x; v[4 * jj + 1] += b.y; v[4 * jj + 2] += b.z; v[4 * jj + 3] += b.w;
             }
           }
@@ -402,25 +429,42 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
               v[4 * jj + 0] += e.x; v[4 * jj + 1] += e.y; v[4 * jj + 2] += e.z; v[4 * jj + 3] += e.w;
             }
           }
-          if (valid) {
-            if (p.out_mode == kOutRaw) {
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff + ch * 32);
+          // the previous bulk store of this half must have finished reading the staging tile
+          if (issuer) tma_store_wait_read();
+          named_bar_sync(2 + half, 128);
+          if (p.out_mode == kOutRaw) {
+            // [128 rows][32 fp32] with the 128-byte swizzle of the store's tensor map: conflict-free 16-byte stores
+            const uint32_t srow = stg_u + row * 128;
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj)
-                o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-            } else {
-              __half* oh = reinterpret_cast<__half*>(p.out) + ooff + ch * 32;
+            for (int jj = 0; jj < 8; ++jj)
+              st_shared_v4(srow + ((jj ^ (row & 7)) << 4), __float_as_uint(v[4 * jj]), __float_as_uint(v[4 * jj + 1]),
+                           __float_as_uint(v[4 * jj + 2]), __float_as_uint(v[4 * jj + 3]));
+          } else {
+            // hi tile [128 rows][32 fp16] then lo tile, 64-byte swizzle
+            const uint32_t srow = stg_u + row * 64;
+            const int sw = (row >> 1) & 3;
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj)
-                st_split4(oh + 4 * jj, oh + p.out_plane + 4 * jj,
-                          make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]));
+            for (int jj = 0; jj < 4; ++jj) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) split16x2(v[8 * jj + 2 * k2], v[8 * jj + 2 * k2 + 1], hi[k2], lo[k2]);
+              st_shared_v4(srow + ((jj ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+              st_shared_v4(srow + Cfg::kStagingHalf / 2 + ((jj ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
             }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2 + half, 128);
+          if (issuer) {
+            const int c0 = nt * BLOCK_N + col0 + ch * 32;
+            tma_store_5d(omap, stg, c0, tc.w0, tc.h0, tc.n0, 0);
+            if (p.out_mode != kOutRaw) tma_store_5d(omap, stg + Cfg::kStagingHalf / 2, c0, tc.w0, tc.h0, tc.n0, 1);
+            tma_store_commit();
           }
         }
 
         if (p.stats != nullptr) {
           // combine the lane quarters (named barrier 1: only the 256 drain/epilogue threads participate)
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          named_bar_sync(1, 256);
           const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
           const int wps = 4 / spt;                         // lane quarters per sample
           constexpr int G8 = BLOCK_N / 8;
@@ -440,11 +484,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
               dst[1] = ss;
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // red[] is reused by the next tile
+          named_bar_sync(1, 256);   // red[] is reused by the next tile
         }
       }
       u += kb1 - kb0;
     }
+    if ((q == 0) && (lane == 0)) tma_store_wait_all();   // bulk stores issued by this thread have been written
   }
 
   // ---- teardown ---------------------------------------------------------------------------------
@@ -478,15 +523,16 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box, const cuuint32_t* estr) {
+                      const cuuint32_t* box, const cuuint32_t* estr,
+                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return 3;
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, dtype, rank, const_cast<void*>(base), dims, strides_b, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return 3;
@@ -577,6 +623,22 @@ static int encode_act_map(CUtensorMap* m, const __half* base, long long plane, i
   cuuint32_t box[5] = {(cuuint32_t)kTcBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return encode_map(m, base, 5, dims, strides, box, estr);
+}
+
+// Output view for the epilogue's TMA stores: NHWC [N, Ho, Wo, C] sub-sampled by `sub` starting at pixel (ph, pw)
+// (sub = 2: the output-parity grid one phase of the folded upsample writes).  32-channel boxes of 128 pixels.
+static int encode_out_map(CUtensorMap* m, void* base, int out_mode, long long plane, int N, int Ho, int Wo, int C, int bw,
+                          int bh, int bn, int sub = 1, int ph = 0, int pw = 0) {
+  const bool raw = out_mode == kOutRaw;
+  const size_t es = raw ? 4 : 2;
+  char* b = static_cast<char*>(base) + (static_cast<size_t>(ph) * Wo + pw) * C * es;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)(Wo / sub), (cuuint64_t)(Ho / sub), (cuuint64_t)N, raw ? 1u : 2u};
+  const cuuint64_t plane_b = raw ? (cuuint64_t)N * Ho * Wo * C * es : (cuuint64_t)plane * es;
+  cuuint64_t strides[4] = {(cuuint64_t)sub * C * es, (cuuint64_t)sub * Wo * C * es, (cuuint64_t)Ho * Wo * C * es, plane_b};
+  cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return encode_map(m, b, 5, dims, strides, box, estr, raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                    raw ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
@@ -686,6 +748,17 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
     plan->maps.a[2] = plan->maps.a[0];
     plan->maps.a[3] = plan->maps.a[0];
   }
+  MF_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "TMA store target must be 16-byte aligned");
+  if (d.up2) {
+    for (int ph = 0; ph < 2 && rc == 0; ++ph)
+      for (int pw = 0; pw < 2 && rc == 0; ++pw)
+        rc = encode_out_map(&plan->maps.o[2 * ph + pw], d.out, d.out_mode, d.out_plane, d.N, 2 * Ho, 2 * Wo, d.Cout, p.bw,
+                            p.bh, p.bn, 2, ph, pw);
+  } else {
+    rc = encode_out_map(&plan->maps.o[0], d.out, d.out_mode, d.out_plane, d.N, Ho, Wo, d.Cout, p.bw, p.bh, p.bn);
+    for (int i = 1; i < 4; ++i) plan->maps.o[i] = plan->maps.o[0];
+  }
+  if (rc) return rc;
   const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
   const long long wrows = static_cast<long long>(d.Cout) * (d.up2 ? 4 : 1);  // up2: four phase matrices stacked
   cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)wrows, 2};

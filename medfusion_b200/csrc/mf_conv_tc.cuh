@@ -64,6 +64,8 @@ struct ConvTcParams {
 struct TcMaps {
   CUtensorMap a[4];  // stride 1: a[0] = source 0, a[1] = source 1 (concat);  stride 2: a[2*ph + pw] = input parity grid
   CUtensorMap w;
+  CUtensorMap o[4];  // output (TMA store): o[0]; folded upsample: o[2*oa + ob] = the output-parity grid of phase (oa, ob).
+                     // 5-D {C, W, H, N, plane}: fp32 x 1 plane (raw, 128-byte swizzle) or fp16 x 2 planes (split, 64-byte)
 };
 
 struct ConvTcPlan {
