@@ -144,6 +144,14 @@ typedef struct {
 int mf_unet_forward_step(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
                          int H, int W, void* d_workspace, size_t workspace_bytes, const mf_step_args* step,
                          mf_stream_t stream);
+/* Classifier-free guidance (diffusion_pipeline.py:240-244: two estimator passes at batch B) as ONE pass at batch 2B
+ * (ABI v3): samples [0,B) run without / with the un_cond label, samples [B,2B) with the condition; the head combines
+ * pred_u + guidance_scale * (pred_c - pred_u) and applies the scheduler update.  d_cond2: int64[2B], the unconditional
+ * half first, where the value num_classes means "no label" (un_cond=None).  Needs step->uniform_t == 1 and
+ * step->d_pred_uncond == NULL; workspace from mf_unet_workspace_bytes(h, 2*B, H, W).  Outputs have batch B. */
+int mf_unet_forward_step_cfg(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond2, int B, int H,
+                             int W, void* d_workspace, size_t workspace_bytes, const mf_step_args* step,
+                             mf_stream_t stream);
 /* Same as mf_unet_forward but with a CUDA-event pair around every kernel launch of the plan (synchronises).
  * ms[i]: device time of launch i; kinds[i]: 0 conv_tc, 1 conv_simt, 2 GroupNorm family, 3 other;
  * flops[i]: algorithmic FLOPs of launch i (2*MACs of the reference formulation; 0 for non-GEMM work). */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mf_unet_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "mf_unet_forward_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, POINTER(StepArgs), _P]),
+    "mf_unet_forward_step_cfg": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, POINTER(StepArgs), _P]),
     "mf_unet_profile": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float),
                                 POINTER(c_int), POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "mf_unet_plan_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

@@ -28,6 +28,7 @@ struct mf_unet : public EngineBase {
   // fused local-embedder matrix [emb_total][emb_dim] + bias [emb_total]
   int emb_total = 0;
   DevBuf loc_w, loc_b;
+  DevBuf cond_ext;        // [num_classes + 1][E]: the label table plus an all-zero "no label" row (CFG as one batch)
   int loc_version = -1;
   std::vector<ResBlockLayer*> all_rb;
   // per-call IO (read by the launch closures)
@@ -125,6 +126,12 @@ int mf_unet::ensure_local_embedder(cudaStream_t s) {
     MF_CUDA_OK(cudaMemcpyAsync(loc_b.p + rb->emb_offset, rb->emb_b->data.p, static_cast<size_t>(rb->Cout) * 4,
                                cudaMemcpyDeviceToDevice, s));
   }
+  if (cond_table != nullptr) {
+    const size_t n = static_cast<size_t>(cfg.num_classes) * E;
+    if (cond_ext.alloc(n + E)) return 1;
+    MF_CUDA_OK(cudaMemcpyAsync(cond_ext.p, cond_table->data.p, n * 4, cudaMemcpyDeviceToDevice, s));
+    MF_CUDA_OK(cudaMemsetAsync(cond_ext.p + n, 0, static_cast<size_t>(E) * 4, s));
+  }
   loc_version = version;
   return 0;
 }
@@ -178,7 +185,7 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
       push_op([this, l2, table](cudaStream_t st) {
         LinearDesc d = l2;
         if (io_cond != nullptr && table != nullptr) {
-          d.add_table = table;
+          d.add_table = io_cfg_pair ? cond_ext.p : table;   // pair mode: index num_classes = the all-zero row
           d.add_idx = io_cond;
         }
         if (io_emb_dedup) {            // row r is class r (identity index); a single row when there is no condition
@@ -702,6 +709,39 @@ int mf_unet_forward_step(mf_unet* h, const float* d_x_t, const int64_t* d_t, con
   rc = h->run(s);
   h->io_step_on = false;
   h->io_emb_dedup = false;
+  return rc;
+}
+// Classifier-free guidance as one 2B batch.  d_cond2[2B]: labels of the unconditional half first (num_classes = "no
+// label"), then the conditional half.  The scheduler update consumes pred_u + g (pred_c - pred_u) inside the head.
+int mf_unet_forward_step_cfg(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond2, int B, int H,
+                             int W, void* d_workspace, size_t workspace_bytes, const mf_step_args* step,
+                             mf_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MF_REQUIRE(d_x_t && d_t && d_cond2 && step && step->tables && B > 0 && H > 0 && W > 0, "bad arguments");
+  MF_REQUIRE(step->uniform_t && step->d_pred_uncond == nullptr, "the one-batch CFG step needs uniform t and no separate uncond prediction");
+  MF_REQUIRE(h->cfg.num_classes > 0 && h->cfg.emb_dim > 0 && !h->has_attention, "the one-batch CFG step needs a label embedder (and no attention blocks)");
+  MF_REQUIRE(h->cfg.out_ch <= 8 && h->cfg.hid_chs[0] % 64 == 0 && h->cfg.kernel_sizes[0] % 2 == 1 && h->cfg.strides[0] == 1 &&
+                 h->cfg.in_ch < 64 && mf::g_stem_on_tc,
+             "the one-batch CFG step needs the narrow fused head and the tensor-core stem");
+  int rc = prepare_plan(h, 2 * B, H, W, d_workspace, workspace_bytes, s);
+  if (rc) return rc;
+  h->io_x = d_x_t;
+  h->io_t = reinterpret_cast<const long long*>(d_t);
+  h->io_cond = reinterpret_cast<const long long*>(d_cond2);
+  h->io_y = nullptr;
+  // embeddings: one row per class + the "no label" row, indexed by d_cond2
+  h->io_emb_dedup = true;
+  h->emb_rows = h->cfg.num_classes + 1;
+  h->io_emb_index = reinterpret_cast<const long long*>(d_cond2);
+  MF_REQUIRE(h->emb_rows <= 2 * B, "more classes than samples");
+  h->io_cfg_pair = true;
+  h->io_cfg_guidance = step->guidance_scale;
+  fill_step_desc(h->io_step, step, d_x_t, d_t, B, h->cfg.out_ch * H * W);
+  h->io_step_on = true;
+  rc = h->run(s);
+  h->io_step_on = false;
+  h->io_emb_dedup = false;
+  h->io_cfg_pair = false;
   return rc;
 }
 int mf_unet_profile(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B, int H,

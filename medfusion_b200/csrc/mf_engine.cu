@@ -345,8 +345,9 @@ int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, i
     if (!dry) {
       __half* xpp = xp.hptr();
       const long long xpl = xp.plane;
-      push_op([src, xpp, xpl, N, Cin, H, W](cudaStream_t s) { return pack_nchw_to_split(*src, xpp, xpl, N, Cin, H, W, s, 64); },
-              kOpOther);
+      push_op([this, src, xpp, xpl, N, Cin, H, W](cudaStream_t s) {
+        return pack_nchw_to_split(*src, xpp, xpl, N, Cin, H, W, s, 64, io_cfg_pair ? N / 2 : 0);
+      }, kOpOther);
       int rc = ensure_w_tc(L, 64);
       if (rc) return rc;
       ConvTcDesc d{};
@@ -408,6 +409,11 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
       HeadDesc h2 = hd;
       h2.out = *dst;
       h2.out_u8 = io_out_u8;
+      if (io_cfg_pair) {          // plan batch = 2N: uncond | cond halves, one guided output per sample pair
+        h2.N = hd.N / 2;
+        h2.cfg_pair = 1;
+        h2.cfg_guidance = io_cfg_guidance;
+      }
       return head1x1(h2, io_step_on ? &io_step : nullptr, s);
     }, kOpConvSimt, 2.0 * in0.N * in0.H * in0.W * L.Cout * static_cast<double>(L.Cin));
     return 0;

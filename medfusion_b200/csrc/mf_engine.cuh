@@ -154,6 +154,10 @@ class EngineBase {
   unsigned char* io_out_u8 = nullptr;   // optional uint8 HWC copy of the narrow head's output (VAE images)
   bool io_emb_dedup = false;
   const long long* io_emb_index = nullptr;
+  // classifier-free guidance as ONE 2B batch (diffusion_pipeline.py:240-244 runs two B passes): the stem packs every input
+  // sample twice, the label index of the first half points at the all-zero "no label" row, the head combines the halves
+  bool io_cfg_pair = false;
+  float io_cfg_guidance = 1.f;
 
   // ---- builder state (valid during build())
   bool dry = false;

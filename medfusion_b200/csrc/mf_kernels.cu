@@ -13,7 +13,7 @@ __device__ __forceinline__ float swish_stream(float x) { return __fdividef(x, 1.
 // Layout packing
 // =================================================================================================
 __global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, __half* __restrict__ out, long long plane, int N,
-                                          int C, int H, int W, int Cpad) {
+                                          int C, int H, int W, int Cpad, int n_mod) {
   const long long total = static_cast<long long>(N) * H * W * Cpad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -21,19 +21,20 @@ __global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, __half* _
     const long long pix = i / Cpad;
     const int w = static_cast<int>(pix % W);
     const int h = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    if (n_mod > 0) n %= n_mod;   // classifier-free guidance as one 2B batch: both halves read the same B samples
     const float v = c < C ? x[((static_cast<long long>(n) * C + c) * H + h) * W + w] : 0.f;  // zero-padded channels
     split16(v, out[i], out[plane + i]);
   }
 }
 
 int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s,
-                       int Cpad) {
+                       int Cpad, int n_mod) {
   if (Cpad < C) Cpad = C;
   const long long total = static_cast<long long>(N) * H * W * Cpad;
   if (total == 0) return 0;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W, Cpad);
+  pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W, Cpad, n_mod);
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -893,30 +894,38 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const HeadDesc h, const Sc
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long npix = static_cast<long long>(h.N) * h.HW;
+  const int passes = h.cfg_pair ? 2 : 1;
   for (long long pix = warp0; pix < npix; pix += nwarps) {
-    const __half* xh = h.in + pix * h.C;
-    const __half* xl = xh + h.in_plane;
-    float acc[8];
+    float ysel[2] = {0.f, 0.f};
+    for (int ps = 0; ps < passes; ++ps) {
+      // cfg_pair: the estimator ran on a 2N batch — samples [0, N) without the label, [N, 2N) with it
+      const __half* xh = h.in + (pix + static_cast<long long>(ps) * npix) * h.C;
+      const __half* xl = xh + h.in_plane;
+      float acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-    for (int c = lane * 2; c < h.C; c += 64) {  // two channels per lane per pass (4-byte loads on both planes)
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xh + c));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(xl + c));
-      const float x0 = a.x + b.x, x1 = a.y + b.y;
+      for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+      for (int c = lane * 2; c < h.C; c += 64) {  // two channels per lane per pass (4-byte loads on both planes)
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(xh + c));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(xl + c));
+        const float x0 = a.x + b.x, x1 = a.y + b.y;
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (o < h.Cout) acc[o] = fmaf(x1, wsm[o * h.C + c + 1], fmaf(x0, wsm[o * h.C + c], acc[o]));
+      }
 #pragma unroll
       for (int o = 0; o < 8; ++o)
-        if (o < h.Cout) acc[o] = fmaf(x1, wsm[o * h.C + c + 1], fmaf(x0, wsm[o * h.C + c], acc[o]));
+        if (o < h.Cout)   // warp-uniform
+          for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+      float yy = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o == lane) yy = acc[o];
+      ysel[ps] = yy + wsm[h.Cout * h.C + (lane < h.Cout ? lane : 0)];
     }
-#pragma unroll
-    for (int o = 0; o < 8; ++o)
-      if (o < h.Cout)   // warp-uniform
-        for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
     if (lane < h.Cout) {
-      float y = 0.f;
-#pragma unroll
-      for (int o = 0; o < 8; ++o)
-        if (o == lane) y = acc[o];
-      y += wsm[h.Cout * h.C + lane];
+      float y = ysel[0];
+      // classifier-free guidance combine (diffusion_pipeline.py:244): pred_uncond + g * (pred_cond - pred_uncond)
+      if (h.cfg_pair) y = ysel[0] + h.cfg_guidance * (ysel[1] - ysel[0]);
       const int n = static_cast<int>(pix / h.HW);
       const long long i = (static_cast<long long>(n) * h.Cout + lane) * h.HW + (pix - static_cast<long long>(n) * h.HW);
       if (h.out != nullptr) h.out[i] = y;
@@ -933,6 +942,8 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const HeadDesc h, const Sc
 
 int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s) {
   MF_REQUIRE(h.Cout >= 1 && h.Cout <= 8 && h.C % 64 == 0, "head1x1: Cout <= 8 and C % 64 == 0");
+  MF_REQUIRE(!h.cfg_pair || (step != nullptr && step->pred_uncond == nullptr && h.out_u8 == nullptr),
+             "head1x1 pair mode is the fused CFG step (no separate uncond prediction, no uint8 output)");
   const long long npix = static_cast<long long>(h.N) * h.HW;
   if (npix == 0) return 0;
   HeadDesc hh = h;

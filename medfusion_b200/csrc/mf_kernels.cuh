@@ -16,8 +16,9 @@ enum ActLayout : int {
 
 // ---- layout / weight preparation -----------------------------------------------------------------
 // Cpad > C: channels C..Cpad-1 of the NHWC output are zero (stem convolutions on the tensor-core path)
+// n_mod > 0: sample n of the output reads sample n % n_mod of x (a 2B batch fed from B inputs)
 int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s,
-                       int Cpad = 0);
+                       int Cpad = 0, int n_mod = 0);
 int unpack_to_nchw(const void* in, long long plane, int in_layout, float* out, int N, int C, int H, int W,
                    cudaStream_t s);
 // OIHW -> fp16 [2][Cout][K], K = ((c/64)*kh*kw + r*kw+s)*64 + c%64, pre-scaled by 2^S  (tensor-core path; Cin % 64 == 0)
@@ -130,6 +131,8 @@ struct HeadDesc {
   unsigned char* out_u8;                 // optional NHWC uint8 image [N][HW][Cout]: clip(-1,1) -> (x+1)/2*255 -> truncate
   int N, HW, C, Cout;
   int fuse_step;
+  int cfg_pair;                          // 1: `in` holds 2N samples (uncond | cond); outputs N samples of the CFG combine
+  float cfg_guidance;
 };
 // step != nullptr: every output element is fed to the scheduler update as `pred` (step->pred is ignored)
 int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s);

@@ -77,6 +77,7 @@ class UNet(EngineModule):
         self.in_ch, self.out_ch = in_ch, out_ch
         self.estimate_variance = estimate_variance
         self._hid0, self._k0, self._s0 = int(hid_chs[0]), int(kernel_sizes[0]), int(strides[0])
+        self._has_attention = any(a != "none" for a in attn)
 
         self.time_spec = time_embedder(**dict(time_embedder_kwargs or {})) if time_embedder is not None else None
         self.cond_spec = cond_embedder(**dict(cond_embedder_kwargs or {})) if cond_embedder is not None else None
@@ -203,6 +204,49 @@ class UNet(EngineModule):
                        "mf_unet_forward_step")
         if want_pred:
             outs["pred"] = pred
+        return outs
+
+    def supports_cfg_batch(self):
+        """mf_unet_forward_step_cfg: classifier-free guidance as one 2B batch (label embedder, no attention blocks)."""
+        return (self.supports_fused_step() and self.cond_spec is not None and self.in_ch < 64
+                and not getattr(self, "_has_attention", False))
+
+    def cfg_labels(self, condition, un_cond):
+        """int64 [2B] label vector of the one-batch CFG step: unconditional half first; `un_cond=None` (no label at all,
+        diffusion_pipeline.py:241 passes condition=None) is encoded as the extra all-zero row `num_classes`."""
+        cond = condition.to(device=self.device, dtype=torch.int64).reshape(-1)
+        if un_cond is None:
+            unc = torch.full_like(cond, self.cond_spec.num_classes)
+        else:
+            unc = un_cond.to(device=self.device, dtype=torch.int64).reshape(-1)
+        return torch.cat([unc, cond]).contiguous()
+
+    def forward_step_cfg(self, x_t, t, cond2, scheduler, *, guidance_scale, noise=None, t_next=None, noise_ddim=None,
+                         objective="x_T", clip_x0=True, want=("x_next",)):
+        """One reverse step with classifier-free guidance, both estimator passes of diffusion_pipeline.py:240-244 run as a
+        single 2B batch (mf_unet_forward_step_cfg).  `cond2` from cfg_labels(); all entries of t are equal."""
+        require_cuda(x_t, "UNet.forward_step_cfg(x_t)")
+        self.sync_params()
+        B, _, H, W = x_t.shape
+        x = x_t.contiguous().float()
+        tt = t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
+        outs = {k: torch.empty_like(x) for k in want}
+        if t_next is not None:
+            t_next = t_next.to(device=x.device, dtype=torch.int64).reshape(1).contiguous()
+        tab = scheduler._tables()
+        keep = [v.contiguous() if v is not None else None for v in (noise, noise_ddim)]
+
+        def ptr(v):
+            return None if v is None else v.data_ptr()
+
+        args = _lib.StepArgs(ctypes.pointer(tab), None, float(guidance_scale), ptr(keep[0]), ptr(t_next), ptr(keep[1]),
+                             1 if objective == "x_0" else 0, 1 if clip_x0 else 0, ptr(outs.get("x_prior")),
+                             ptr(outs.get("x_0")), ptr(outs.get("x_T")), ptr(outs.get("x_next")), 1)
+        with on_device(x):
+            ws, ws_bytes = self._workspace(2 * B, H, W)
+            _lib.check(_lib.load().mf_unet_forward_step_cfg(self._h, x.data_ptr(), tt.data_ptr(), cond2.data_ptr(), B, H, W,
+                                                            ws, ws_bytes, ctypes.byref(args), cuda_stream_ptr(x.device)),
+                       "mf_unet_forward_step_cfg")
         return outs
 
     def profile(self, x_t, t, condition=None):

@@ -38,8 +38,18 @@ class _StepGraph:
         self.un_cond = None if un_cond is None else un_cond.clone()
         cfg = (condition is not None) and (guidance_scale != 1.0)
         sched = pipe.noise_scheduler
+        one_batch = cfg and pipe.cfg_single_batch and est.supports_cfg_batch()
+        self.cond2 = est.cfg_labels(condition, un_cond) if one_batch else None
 
         def body():
+            if one_batch:     # both estimator passes of diffusion_pipeline.py:240-244 as ONE 2B batch
+                noise = noise_fn(self.x)
+                noise2 = noise_fn(self.x) if ddim else None
+                o = est.forward_step_cfg(self.x, self.t, self.cond2, sched, guidance_scale=guidance_scale, noise=noise,
+                                         t_next=self.t_next if ddim else None, noise_ddim=noise2,
+                                         objective=pipe.estimator_objective, clip_x0=pipe.clip_x0, want=("x_next",))
+                self.x.copy_(o["x_next"])
+                return
             pred_u = est(self.x, self.t, condition=self.un_cond, self_cond=None)[0] if cfg else None
             noise = noise_fn(self.x)
             noise2 = noise_fn(self.x) if ddim else None
@@ -64,7 +74,8 @@ class _StepGraph:
             body()
         # the captured launches point into the estimator's workspace for this shape and at its prepared weights:
         # keep the former alive with the graph, remember the version of the latter
-        self._workspace = est._workspace_tensor(B, x.shape[2], x.shape[3])
+        self._workspace = est._workspace_tensor(2 * B if one_batch else B, x.shape[2], x.shape[3])
+        self._workspace2 = est._workspace_tensor(B, x.shape[2], x.shape[3]) if (cfg and not one_batch) else None
         self.param_sig = est._synced_sig
         torch.cuda.set_rng_state(rng, x.device)   # capture does not draw, but keep the contract explicit
 
@@ -135,6 +146,10 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         # FloatingPointError if a value left the fp16 range of the split planes — the reference is fp32-range, so the
         # result would silently differ from it
         self.check_saturation = True
+        # classifier-free guidance: run the unconditional and the conditional estimator pass as ONE 2B batch (per-sample
+        # label index; un_cond=None -> an all-zero "no label" row) instead of the reference's two B passes — fills the GPU
+        # at the small batches of scripts/sample.py (B=16, guidance 8).  False: two passes, like the reference.
+        self.cfg_single_batch = True
         self._step_graphs = {}
         if use_ema:
             # weight selection only (diffusion_pipeline.py:234-237): a second estimator holding the averaged weights under
@@ -240,7 +255,7 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
                 # repeated sample(shard=True) calls reuse the captured graphs instead of re-capturing
                 nkey = getattr(custom_noise, "cache_key", id(custom_noise))
                 key = (id(est), tuple(x_t.shape), condition is not None, un_cond is not None, float(guidance_scale),
-                       ddim, self.estimator_objective, self.clip_x0, nkey)
+                       ddim, self.estimator_objective, self.clip_x0, nkey, self.cfg_single_batch)
                 g = self._step_graphs.get(key)
                 est.sync_params()
                 if g is not None and g.param_sig != est._synced_sig:   # weights changed since the capture
@@ -254,6 +269,8 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
                     g.cond.copy_(condition)
                 if un_cond is not None:
                     g.un_cond.copy_(un_cond)
+                if g.cond2 is not None:
+                    g.cond2.copy_(est.cfg_labels(condition, un_cond))
                 return g
 
             n_main = steps - 1 if use_ddim else steps        # the last DDIM step has no re-noise
@@ -284,7 +301,15 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
             tb = t.expand(B)
             ddim = use_ddim and (steps - i - 1 > 0)
             t_next = timesteps_array[steps - i - 2] if ddim else None
-            if fused:
+            if fused and cfg and self.cfg_single_batch and est.supports_cfg_batch():
+                if i == 0:
+                    cond2 = est.cfg_labels(condition, un_cond)
+                noise = noise_fn(x_t)
+                noise2 = noise_fn(x_t) if ddim else None
+                o = est.forward_step_cfg(x_t, tb, cond2, sched, guidance_scale=guidance_scale, noise=noise, t_next=t_next,
+                                         noise_ddim=noise2, objective=self.estimator_objective, clip_x0=self.clip_x0,
+                                         want=("x_next",))
+            elif fused:
                 # estimator pass(es) first (as in the reference), then the draws; the last estimator pass carries the
                 # CFG combine + scheduler update (+ DDIM re-noise) in the epilogue of its output head
                 pred_u = est(x_t, tb, condition=un_cond, self_cond=None)[0] if cfg else None

@@ -463,3 +463,32 @@ def test_vqvae_as_latent_embedder_of_the_pipeline():
     emb, pipe.latent_embedder = pipe.latent_embedder, None
     lat = pipe.sample(2, (4, 32, 32), steps=4, use_ddim=True)
     assert torch.equal(emb.decode(lat), img)
+
+
+@pytest.mark.parametrize("with_un_cond", [False, True])
+def test_cfg_as_one_batch_equals_two_passes(with_un_cond):
+    """Classifier-free guidance as ONE 2B batch (mf_unet_forward_step_cfg: per-sample label index, `no label` = an
+    all-zero row, guided combine + scheduler update in the head) against the reference's formulation with two estimator
+    passes (diffusion_pipeline.py:240-244) — same arithmetic per sample, only the batch the kernels see differs."""
+    from medfusion_b200.models import GaussianNoiseScheduler
+    g = load_golden("unet_small.pt")
+    gs = load_golden("sched.pt")
+    m = make_unet(g["cfg"], DEV)
+    s = GaussianNoiseScheduler(**gs["sched"]).to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 8, 32, 32, generator=gen).to(DEV)
+    n1, n2 = (torch.randn(4, 8, 32, 32, generator=gen).to(DEV) for _ in range(2))
+    t = torch.full((4,), 640, device=DEV)
+    c = torch.tensor([0, 1, 1, 0], device=DEV)
+    uc = torch.tensor([1, 0, 1, 0], device=DEV) if with_un_cond else None
+    assert m.supports_cfg_batch()
+    pu, _ = m(x, t, uc)
+    ref = m.forward_step(x, t, c, s, pred_uncond=pu, guidance_scale=4.0, noise=n1, t_next=torch.tensor(320),
+                         noise_ddim=n2, objective="x_T", clip_x0=True, want=("x_prior", "x_0", "x_T", "x_next"),
+                         uniform_t=True)
+    got = m.forward_step_cfg(x, t, m.cfg_labels(c, uc), s, guidance_scale=4.0, noise=n1, t_next=torch.tensor(320),
+                             noise_ddim=n2, objective="x_T", clip_x0=True, want=("x_prior", "x_0", "x_T", "x_next"))
+    B640 = float(s.sqrt_recipm1_alphas_cumprod[640])
+    for k in ("x_T", "x_0", "x_prior", "x_next"):
+        # x_T is the guided estimate itself (7 = |1-g| + |g| times the per-pass summation-order noise of ~1e-6)
+        assert_close(got[k].cpu(), ref[k].cpu(), rtol=1e-4, atol=1e-5 * max(1.0, B640), what=f"one-batch CFG {k}")
