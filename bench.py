@@ -297,8 +297,22 @@ def main():
                              estimator_objective="x_T", estimate_variance=False, use_self_conditioning=False,
                              use_ema=False, do_input_centering=False, clip_x0=c["clip_x0"])
     fill_(pipe.noise_estimator)                # random-init weights with the zero-init tensors re-randomised
+    if c["ddim"]:
+        # A RANDOM-init estimator has gain > 1 from x_t to its output (the residual path carries |x_t| through), so the
+        # DDIM-form update x_next = sqrt(ac_n) x_0 + c x_T + sigma n (x_T = the estimate) diverges once c ~ 1, i.e. for
+        # more than ~100 steps, clip_x0 or not: |x| reaches 1e5 — meaningless in the reference's fp32 too, and beyond the
+        # fp16 range of the split planes here (denoise() raises FloatingPointError).  A trained estimator does not do
+        # that; the synthetic one is tamed by a small output head (the reference zero-initialises it, unet2.py:213) and,
+        # under guidance, a small label embedding.  The work per step is identical.
+        with torch.no_grad():
+            pipe.noise_estimator.outc.conv.conv.weight.mul_(0.02)
+            pipe.noise_estimator.outc.conv.conv.bias.mul_(0.02)
+            if c["guidance"] != 1.0:
+                pipe.noise_estimator.cond_embedder.embedding.weight.mul_(1e-2)
     pipe.latent_embedder = fill_(VAE(**VAE_CFG))
     pipe = pipe.to(dev)
+    if os.environ.get("MF_CFG_TWO_PASS"):        # A/B switch for the one-batch CFG step (profiles/r02_cfg_one_batch.md)
+        pipe.cfg_single_batch = False
     unet, vae = pipe.noise_estimator, pipe.latent_embedder
 
     B, LAT, IMG = c["B"], c["latent"], c["img"]
