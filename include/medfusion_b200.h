@@ -69,6 +69,9 @@ int mf_set_fold_upsample(int enable);
 /* Cin < 64 stem convolutions (UNet in_conv, VAE inc_dec): 1 = tcgen05 path through a zero-padded 64-channel copy of the
  * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
 int mf_set_stem_on_tc(int enable);
+/* VAE / VQVAE image head (latent_embedders.py:743, 1x1 conv hid_chs[0] -> out_channels): 1 (default) = evaluated inside the
+ * last GroupNorm-apply kernel (the 1.07 GB activation at B=64, 256x256 is neither written nor re-read), 0 = own kernel. */
+int mf_set_fold_head(int enable);
 /* GroupNorm-apply kernel used by the engine plans (tuning knob): 3 (default) finalises the statistics inside the apply
  * kernel (one launch per GroupNorm, 8 channels per thread); 0 / 1 / 2 keep a separate finalize launch with a flat
  * grid-stride / fixed channel quad per thread / one channel quad per thread mapping.  Takes effect at the next plan build. */

@@ -4,6 +4,7 @@
 
 namespace mf {
 
+int g_fold_head = 1;        // VAE image head (64 -> 3) folded into the last GroupNorm-apply
 int g_fold_upsample = 1;
 int g_stem_on_tc = 1;      // Cin < 64 stem convolutions on the tensor core through a zero-padded 64-channel input  // BasicUp as four phase convolutions (0: explicit nearest-x2 kernel + conv3x3)
 
@@ -437,8 +438,16 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
 
 bool gn_needs_generic(int C, int groups) { return groups <= 0 || C % groups != 0 || (C / groups) % 8 != 0; }
 
+bool EngineBase::can_fold_head(const ConvLayer& head, int C, int groups) const {
+  const int c8 = C / 8;
+  return g_gn_variant == 3 && head.k == 1 && head.stride == 1 && head.Cout <= 8 && head.Cin == C && C % 8 == 0 &&
+         !gn_needs_generic(C, groups) && groups <= 128 && c8 <= 32 && (c8 & (c8 - 1)) == 0 && 256 % c8 == 0;
+}
+
 int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks,
-                             const Tens* res, const float* emb, int emb_stride, const Tens& out, int act) {
+                             const Tens* res, const float* emb, int emb_stride, const Tens& out, int act, ConvLayer* head,
+                             float* const* head_dst) {
+  MF_REQUIRE(head == nullptr || can_fold_head(*head, raw.C, groups), "this head cannot be folded into gn_apply");
   MF_REQUIRE(groups > 0 && raw.C % groups == 0, "GroupNorm: channels must be divisible by the group count (" + nl.g->name + ")");
   Tens mr = new_floats(static_cast<size_t>(raw.N) * groups * 2);
   if (gn_needs_generic(raw.C, groups)) {
@@ -492,14 +501,23 @@ int EngineBase::add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, c
     d.emb = emb; d.emb_stride = emb_stride;
     d.out = out.hptr(); d.out_plane = out.plane;
     d.N = raw.N; d.HW = raw.H * raw.W; d.C = raw.C; d.G = groups;
-    push_op([this, d](cudaStream_t s) {
+    if (head != nullptr) {
+      MF_REQUIRE(fused, "the folded head needs the fused gn_apply variant");
+      d.head_w = head->w->data.p; d.head_b = head->b->data.p; d.head_cout = head->Cout;
+      d.out = nullptr;
+    }
+    push_op([this, d, head_dst](cudaStream_t s) {
       GnApplyDesc dd = d;
       if (dd.emb != nullptr && io_emb_dedup) {   // deduplicated embedding rows: one per class (or a single row)
         dd.emb_index = io_emb_index;
         if (io_emb_index == nullptr) dd.emb_stride = 0;
       }
+      if (dd.head_cout > 0) {
+        dd.head_out = head_dst ? *head_dst : nullptr;
+        dd.head_out_u8 = io_out_u8;
+      }
       return gn_apply(dd, s);
-    }, kOpNorm);
+    }, kOpNorm, head ? 2.0 * raw.N * raw.H * raw.W * head->Cout * static_cast<double>(head->Cin) : 0.0);
   }
   free_tensor(mr);
   return 0;
@@ -653,7 +671,7 @@ int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, co
 
 // x1 = swish(gn(conv1(x))) + res(x) + emb ;  x2 = swish(gn(conv2(x1))) + x1      (conv_blocks.py:347-364)
 int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, const Tens* in1, const Tens* embT,
-                             int emb_stride, Tens* out) {
+                             int emb_stride, Tens* out, ConvLayer* head, float* const* head_dst) {
   const int N = in0.N, H = in0.H, W = in0.W;
   const int max_chunks = std::max(1, conv_tc_stats_chunks(H, W));
   Tens raw = new_tensor(N, H, W, rb.Cout, kNHWCRaw);
@@ -681,8 +699,14 @@ int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, con
   // second half reuses `raw` and `part`
   rc = add_conv(rb.conv2, x1, nullptr, raw, generic_gn ? nullptr : &part, &chunks);
   if (rc) return rc;
-  Tens x2 = new_tensor(N, H, W, rb.Cout, kNHWCSplit);
-  rc = add_gn_apply(rb.norm2, groups, raw, part, chunks, &x1, nullptr, 0, x2);
+  Tens x2;
+  if (head != nullptr) {
+    x2.N = N; x2.H = H; x2.W = W; x2.C = rb.Cout; x2.layout = kNHWCSplit;   // never materialised (bytes == 0)
+    rc = add_gn_apply(rb.norm2, groups, raw, part, chunks, &x1, nullptr, 0, x2, 1, head, head_dst);
+  } else {
+    x2 = new_tensor(N, H, W, rb.Cout, kNHWCSplit);
+    rc = add_gn_apply(rb.norm2, groups, raw, part, chunks, &x1, nullptr, 0, x2);
+  }
   if (rc) return rc;
   free_tensor(raw);
   free_tensor(part);

@@ -113,6 +113,7 @@ struct Tens {
   long long elems() const { return static_cast<long long>(N) * H * W * C; }
 };
 
+extern int g_fold_head;
 extern int g_fold_upsample;
 extern int g_stem_on_tc;
 using Launch = std::function<int(cudaStream_t)>;
@@ -186,11 +187,17 @@ class EngineBase {
   // BasicUp: out[2H,2W] = conv3x3(nearest_x2(in)) as four 2x2 phase convolutions on the tensor-core path, or
   // (shapes the tensor-core path cannot take) an explicit upsample followed by add_conv.
   int add_upconv2x(ConvLayer& L, const Tens& in, Tens* out);
+  // head != nullptr: the narrow 1x1 conv `head` (Cout <= 8) is evaluated inside the apply kernel and written to *head_dst
+  // (NCHW fp32, resolved at launch) and/or io_out_u8; `out` is then not written (pass a Tens with ptr == nullptr)
   int add_gn_apply(const NormLayer& nl, int groups, const Tens& raw, const Tens& stats, int chunks, const Tens* res,
-                   const float* emb, int emb_stride, const Tens& out, int act = 1);
-  // full res block: in0 (+in1 concat) -> returns output tensor (split)
+                   const float* emb, int emb_stride, const Tens& out, int act = 1, ConvLayer* head = nullptr,
+                   float* const* head_dst = nullptr);
+  // can the head be folded into the GroupNorm-apply of a C-channel tensor?
+  bool can_fold_head(const ConvLayer& head, int C, int groups) const;
+  // full res block: in0 (+in1 concat) -> returns output tensor (split).  head != nullptr (and foldable): the block's
+  // output only feeds that head, which is folded into the last GroupNorm-apply; *out is then an empty tensor.
   int add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, const Tens* in1, const Tens* embT, int emb_stride,
-                   Tens* out);
+                   Tens* out, ConvLayer* head = nullptr, float* const* head_dst = nullptr);
   int ensure_w_tc(ConvLayer& L, int cin_pad = 0);
   int ensure_w_simt(ConvLayer& L);
   int run(cudaStream_t s);

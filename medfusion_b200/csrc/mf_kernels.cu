@@ -558,6 +558,7 @@ __device__ __forceinline__ void ld_raw8(const GnApplyDesc& d, long long off, flo
   }
 }
 
+template <int HC>   // HC: compile-time bound on the folded head's outputs (0 = no head, 4, 8)
 __global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d) {
   __shared__ float s_mean[128], s_rstd[128];
   pdl_launch_dependents();
@@ -615,8 +616,19 @@ __global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d
     }
   }
   const long long base = static_cast<long long>(n) * d.HW * d.C + c;
-  for (int pix = blockIdx.x * ppb + psub; pix < d.HW; pix += gridDim.x * ppb) {
-    const long long off = base + static_cast<long long>(pix) * d.C;
+  // folded head: this thread's 8 weights of every head output stay in registers
+  float hw[HC > 0 ? HC : 1][8];
+  if (HC > 0) {
+#pragma unroll
+    for (int o = 0; o < HC; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hw[o][j] = (o < d.head_cout) ? __ldg(d.head_w + o * d.C + c + j) : 0.f;
+  }
+  // warp-uniform trip count (the head reduction shuffles across the C/8 lanes of a pixel)
+  for (int pix0 = blockIdx.x * ppb; pix0 < d.HW; pix0 += gridDim.x * ppb) {
+    const int pix = pix0 + psub;
+    const bool live = pix < d.HW;
+    const long long off = base + static_cast<long long>(live ? pix : 0) * d.C;
     float x[8];
     ld_raw8(d, off, x);
     float y[8];
@@ -643,13 +655,36 @@ __global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] += ce[j];
-    uint4 oh, ol;
-    uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
-    uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
+    if (HC > 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split16x2(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
-    *reinterpret_cast<uint4*>(d.out + off) = oh;
-    *reinterpret_cast<uint4*>(d.out + d.out_plane + off) = ol;
+      for (int o = 0; o < HC; ++o) {
+        if (o < d.head_cout) {                      // block-uniform
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(y[j], hw[o][j], acc);
+          for (int sh = c8n >> 1; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+          if (live && (threadIdx.x % c8n) == 0) {
+            const float v = acc + __ldg(d.head_b + o);
+            if (d.head_out != nullptr) d.head_out[(static_cast<long long>(n) * d.head_cout + o) * d.HW + pix] = v;
+            if (d.head_out_u8 != nullptr) {
+              // scripts/helpers/sample_dataset.py:47-50: clip(-1,1) -> (x+1)/2*255 -> HWC -> astype(uint8) (truncation)
+              const float c01 = fminf(fmaxf(v, -1.f), 1.f);
+              const float v255 = __fmul_rn(__fmul_rn(__fadd_rn(c01, 1.f), 0.5f), 255.f);
+              d.head_out_u8[(static_cast<long long>(n) * d.HW + pix) * d.head_cout + o] = static_cast<unsigned char>(v255);
+            }
+          }
+        }
+      }
+    }
+    if (d.out != nullptr && live) {
+      uint4 oh, ol;
+      uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
+      uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split16x2(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
+      *reinterpret_cast<uint4*>(d.out + off) = oh;
+      *reinterpret_cast<uint4*>(d.out + d.out_plane + off) = ol;
+    }
   }
 }
 
@@ -664,6 +699,9 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     MF_REQUIRE(d.C % 8 == 0 && (d.C / d.G) % 8 == 0 && d.G <= 128 && d.chunks >= 1 && 256 % (d.C / 8) == 0,
                "fused gn_apply: C/G % 8 == 0, G <= 128, C/8 divides 256");
     MF_REQUIRE(d.N <= 65535, "fused gn_apply: batch too large");
+    MF_REQUIRE(d.head_cout == 0 || (d.head_cout <= 8 && d.C / 8 <= 32 && ((d.C / 8) & (d.C / 8 - 1)) == 0 && d.head_w),
+               "folded head: <= 8 outputs, C/8 a power of two <= 32");
+    MF_REQUIRE(d.out != nullptr || d.head_cout > 0, "gn_apply without an output");
     const int ppb = 256 / (d.C / 8);
     // ~8 resident blocks per SM over the whole launch, at least 2 pixels per thread where the sample is big enough
     int bps = std::max(1, (148 * 8 + d.N - 1) / d.N);
@@ -677,9 +715,12 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 1 : 0;
-    MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel, d));
+    if (d.head_cout == 0) MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<0>, d));
+    else if (d.head_cout <= 4) MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<4>, d));
+    else MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<8>, d));
     return 0;
   }
+  MF_REQUIRE(d.head_cout == 0, "the folded head exists in the fused gn_apply variant only");
   const int c4n = d.C / 4;
   const int ppb = c4n < 256 ? 256 / c4n : 1;
   const long long total = npix * c4n;

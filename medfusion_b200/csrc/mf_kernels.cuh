@@ -62,8 +62,14 @@ struct GnApplyDesc {
   const void* res; long long res_plane; int res_kind;   // split: __half planes, raw: float
   const float* emb; int emb_stride;       // emb[row*emb_stride + c] or nullptr; row = emb_index ? emb_index[n] : n
   const long long* emb_index;             // optional row indirection (deduplicated embeddings: one row per class)
-  __half* out; long long out_plane;       // split planes
+  __half* out; long long out_plane;       // split planes (nullptr with a folded head: the activation is never written)
   int N, HW, C, G;
+  // optional folded narrow 1x1 head (fused variant only; latent_embedders.py:743 `outc`, 64 -> 3): the C/8 threads that hold
+  // one pixel's channels reduce head_cout dot products among themselves and write NCHW fp32 (and / or the uint8 HWC image
+  // of scripts/helpers/sample_dataset.py:47-50) — the last activation (1.07 GB at B=64, 256x256) is neither written nor re-read
+  const float* head_w; const float* head_b;   // [head_cout][C], [head_cout]
+  float* head_out; unsigned char* head_out_u8;
+  int head_cout;                          // 0: no head
 };
 int gn_apply(const GnApplyDesc& d, cudaStream_t s);
 // Any channel count / any channels-per-group (the fused path needs C/G % 8 == 0): statistics straight from the raw conv
