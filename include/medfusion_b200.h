@@ -69,6 +69,13 @@ int mf_set_fold_upsample(int enable);
 /* Cin < 64 stem convolutions (UNet in_conv, VAE inc_dec): 1 = tcgen05 path through a zero-padded 64-channel copy of the
  * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
 int mf_set_stem_on_tc(int enable);
+/* Res-block halves (conv -> GroupNorm -> Swish -> + residual -> + embedding, conv_blocks.py:184-192,236-240,362) whose
+ * output tile spans whole samples (H*W <= 128 per CTA, or H*W == 256 per CTA pair with the statistics exchanged through
+ * distributed shared memory): 1 = normalisation applied in the convolution's epilogue (no raw fp32 tensor, no GroupNorm
+ * launch: 65 instead of 89 launches per canonical UNet step), 0 (default) = separate GroupNorm-apply kernel everywhere.
+ * Measured slower end to end on B200 (the fused work runs exposed at the tail of a one-tile-per-CTA kernel;
+ * profiles/r02_gn_fusion.md), hence opt-in.  Takes effect at the next plan build. */
+int mf_set_fuse_gn(int enable);
 /* VAE / VQVAE image head (latent_embedders.py:743, 1x1 conv hid_chs[0] -> out_channels): 1 (default) = evaluated inside the
  * last GroupNorm-apply kernel (the 1.07 GB activation at B=64, 256x256 is neither written nor re-read), 0 = own kernel. */
 int mf_set_fold_head(int enable);

@@ -579,6 +579,10 @@ int mf_set_pdl(int enable) {
   mf::g_pdl = enable ? 1 : 0;
   return 0;
 }
+int mf_set_fuse_gn(int enable) {
+  mf::g_fuse_gn = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_fold_head(int enable) {
   mf::g_fold_head = enable ? 1 : 0;
   return 0;

@@ -10,6 +10,10 @@ namespace mf {
 int g_default_drain_interval = 3;
 int g_default_cta_group = 0;
 int g_default_block_n = 0;    // 0 = auto
+// Fused GroupNorm epilogue: correct and tested, but OFF by default — at the levels where it applies a CTA pair owns about
+// one tile, so the normalisation work runs exposed at the kernel's tail instead of in a bandwidth-bound kernel of its own:
+// canonical step 8.85 ms fused vs 8.72 ms separate, 66.7 vs 67.9 images/s (same box, profiles/r02_gn_fusion.md).
+int g_fuse_gn = 0;
 int g_stream_k = 1;           // persistent stream-K schedule (0: one tile per CTA group)
 float g_debias_eps_per_kblock = -1.0f;  // < 0: calibrated table (default); 0: off; > 0: explicit relative correction per K block  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
@@ -28,7 +32,9 @@ struct TcCfg {
   static constexpr int kStagingHalf = kTcBlockM * 128;
   static constexpr int kStagingBytes = 2 * kStagingHalf;
   static constexpr int kRedBytes = 4 * (BLOCK_N / 8) * 2 * 4;   // GroupNorm partial sums [4 quarters][BLOCK_N/8][2]
-  static constexpr int kAuxBytes = 512 + kRedBytes + BLOCK_N * 4;   // barriers + TMEM slot | red | bias
+  static constexpr int kXchBytes = 2 * (BLOCK_N / 8) * 8;           // fused GroupNorm: the pair's other CTA writes its per-slab
+                                                                    // (sum, sumsq) here (double-buffered by tile parity)
+  static constexpr int kAuxBytes = 512 + kRedBytes + BLOCK_N * 4 + kXchBytes;   // barriers + TMEM slot | red | bias | xch
   static constexpr int kSmemMax = 227 * 1024;
   static constexpr int kStagesFit = (kSmemMax - kAuxBytes - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
@@ -58,7 +64,9 @@ struct TcCfg {
 // to a scratch buffer and raises a flag; the group that owns the tile's first K block waits for the flag(s), adds
 // the partials and runs the epilogue.  Partial writers always process that segment FIRST, finalizers process theirs
 // LAST, so nobody waits on work that has not been scheduled.
-template <int BLOCK_N, int CG>
+// GN: compiled with the fused GroupNorm epilogue (p.gn_mode != 0).  A separate instantiation because that epilogue is large:
+// it runs as a rolled loop over 32-column chunks, while the plain epilogue stays fully unrolled (no register-window moves).
+template <int BLOCK_N, int CG, bool GN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, CG>;
@@ -85,6 +93,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + NB);
   float* red = reinterpret_cast<float*>(aux + 512);        // [4 quarters][BLOCK_N/8][2]
   float* bias_s = reinterpret_cast<float*>(aux + 512 + Cfg::kRedBytes);   // [BLOCK_N] bias of the current tile's columns
+  float2* xch = reinterpret_cast<float2*>(aux + 512 + Cfg::kRedBytes + BLOCK_N * 4);   // [2][BLOCK_N/8] written by the peer CTA
+  uint64_t* xch_bar = reinterpret_cast<uint64_t*>(aux + 256);              // [2] peer -> this CTA (fused GroupNorm exchange)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,6 +142,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       mbar_init(&acc_full_bar[b], 1);
       mbar_init(&acc_empty_bar[b], kTcDrainWarps * CG);
     }
+    mbar_init(&xch_bar[0], BLOCK_N / 8);
+    mbar_init(&xch_bar[1], BLOCK_N / 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -276,6 +288,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     const float pscale = p.partial_scale * __ldg(p.w_inv_scale);
     float* my_partial = p.sk_partials + static_cast<long long>(blockIdx.x) * (kTcBlockM * 256);
     int jc = 0;
+    int gn_tiles = 0;                       // fused-GroupNorm epilogues done (exchange buffer / barrier phase)
+    float2 own_slab = make_float2(0.f, 0.f);
 
     for (long long u = u_begin; u < u_end;) {
       const int tile = static_cast<int>(u / nkb);
@@ -369,7 +383,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
 
         if (te < BLOCK_N) bias_s[te] = bias_reg;
         named_bar_sync(1, 256);
+        const bool want_stats = (p.stats != nullptr) || GN;
+        constexpr int G8 = BLOCK_N / 8;
 
+        // ---- phase A: + bias, per-slab (sum, sumsq) over this warp's 32 rows
 #pragma unroll
         for (int ch = 0; ch < CPW / 32; ++ch) {
           float* v = &acc[ch * 32];
@@ -381,7 +398,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
               v[4 * jj + 0] += b.x; v[4 * jj + 1] += b.y; v[4 * jj + 2] += b.z; v[4 * jj + 3] += b.w;
             }
           }
-          if (p.stats != nullptr) {
+          if (want_stats) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float s = 0.f, ss = 0.f;
@@ -398,9 +415,171 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
                 ss += __shfl_xor_sync(0xffffffffu, ss, off);
               }
               if (lane == 0) {
-                float* r = red + ((q * (BLOCK_N / 8)) + (col0 + ch * 32) / 8 + g) * 2;
+                float* r = red + ((q * G8) + (col0 + ch * 32) / 8 + g) * 2;
                 r[0] = s;
                 r[1] = ss;
+              }
+            }
+          }
+        }
+
+        // ---- phase B: statistics out (separate GroupNorm kernel follows) or finalised here (fused GroupNorm)
+        const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
+        const int wps = 4 / spt;                         // lane quarters per sample
+        if (p.stats != nullptr) {
+          named_bar_sync(1, 256);
+          if (te < G8 * spt) {
+            const int j = te / G8, i = te - j * G8;
+            float s = 0.f, ss = 0.f;
+            for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
+              s += red[(wq * G8 + i) * 2 + 0];
+              ss += red[(wq * G8 + i) * 2 + 1];
+            }
+            const int ns = tc.n0 + (spt > 1 ? j : 0);
+            const int chunk = (p.chunks_per_sample > 1) ? (tc.th * p.tiles_w + tc.tw) : 0;
+            if (ns < p.N) {
+              float* dst = p.stats + ((static_cast<long long>(ns) * p.chunks_per_sample + chunk) * (p.Cout / 8) +
+                                      nt * G8 + i) * 2;
+              dst[0] = s;
+              dst[1] = ss;
+            }
+          }
+          named_bar_sync(1, 256);   // red[] is reused by the next tile
+        }
+        if (GN) {
+          // per (sample of the tile, group): mean / rstd.  Same partial sums as the separate kernel: fp32 per (sample,
+          // 8-channel slab, 128-pixel chunk), combined in fp64 across the group's slabs (and the pair's two chunks).
+          named_bar_sync(1, 256);
+          const int slabs = p.gn_cpg / 8;
+          const int ngrp = BLOCK_N / p.gn_cpg;
+          float g_mean = 0.f, g_rstd = 0.f;
+          if (p.gn_mode == 2) {
+            // this CTA's per-slab sums -> own copy (red quarter 0) and the other CTA's exchange buffer, then one remote
+            // arrival per slab; the tile parity double-buffers the exchange
+            const int par = gn_tiles & 1;
+            if (te < G8) {
+              float s = 0.f, ss = 0.f;
+              for (int wq = 0; wq < 4; ++wq) { s += red[(wq * G8 + te) * 2]; ss += red[(wq * G8 + te) * 2 + 1]; }
+              const uint32_t peer = cta_rank ^ 1u;
+              const uint32_t dst = mapa_u32(smem_u32(&xch[par * G8 + te]), peer);
+              asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(s), "f"(ss) : "memory");
+              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                               mapa_u32(smem_u32(&xch_bar[par]), peer)) : "memory");
+              own_slab = make_float2(s, ss);
+            }
+            if (te < G8) {
+              // wait for the peer's values (acquire at cluster scope), bounded
+              uint32_t ok = 0, spins = 0;
+              const uint32_t bar = smem_u32(&xch_bar[par]);
+              const uint32_t parity = (gn_tiles >> 1) & 1;
+              do {
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                if (++spins > (1u << 26)) { printf("mf: GroupNorm exchange timeout cta=%d\n", blockIdx.x); __trap(); }
+              } while (!ok);
+              const float2 other = xch[par * G8 + te];
+              // chunk order of the separate kernel: rank 0's rows first
+              const float2 c0v = cta_rank == 0 ? own_slab : other, c1v = cta_rank == 0 ? other : own_slab;
+              red[te * 2] = c0v.x; red[te * 2 + 1] = c0v.y;               // quarter 0 <- chunk 0
+              red[(G8 + te) * 2] = c1v.x; red[(G8 + te) * 2 + 1] = c1v.y;   // quarter 1 <- chunk 1
+            }
+            named_bar_sync(1, 256);
+            if (te < ngrp) {
+              double ds = 0.0, dss = 0.0;
+              for (int chk = 0; chk < 2; ++chk)
+                for (int sl = 0; sl < slabs; ++sl) {
+                  ds += static_cast<double>(red[(chk * G8 + te * slabs + sl) * 2]);
+                  dss += static_cast<double>(red[(chk * G8 + te * slabs + sl) * 2 + 1]);
+                }
+              const double cnt = static_cast<double>(p.gn_cpg) * (2 * kTcBlockM);
+              const double mean = ds / cnt;
+              double var = dss / cnt - mean * mean;
+              if (var < 0.0) var = 0.0;
+              g_mean = static_cast<float>(mean);
+              g_rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gn_eps)));
+            }
+          } else if (te < spt * ngrp) {
+            const int j = te / ngrp, gi = te - j * ngrp;
+            double ds = 0.0, dss = 0.0;
+            for (int sl = 0; sl < slabs; ++sl) {
+              float s = 0.f, ss = 0.f;
+              for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
+                s += red[(wq * G8 + gi * slabs + sl) * 2];
+                ss += red[(wq * G8 + gi * slabs + sl) * 2 + 1];
+              }
+              ds += static_cast<double>(s);
+              dss += static_cast<double>(ss);
+            }
+            const double cnt = static_cast<double>(p.gn_cpg) * p.rows_per_sample;
+            const double mean = ds / cnt;
+            double var = dss / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            g_mean = static_cast<float>(mean);
+            g_rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gn_eps)));
+          }
+          named_bar_sync(1, 256);                // everybody has read red[]: it now carries (mean, rstd) per (sample, group)
+          if (te < (p.gn_mode == 2 ? 1 : spt) * ngrp) { red[te * 2] = g_mean; red[te * 2 + 1] = g_rstd; }
+          named_bar_sync(1, 256);
+          ++gn_tiles;
+        }
+
+        // ---- phase C: (GroupNorm + Swish + residual + embedding | residual / vector of the attention convs) -> staging
+        //      tile -> TMA store
+        const int srow_sample = (p.gn_mode == 1) ? (row / p.rows_per_sample) : 0;
+        // GN: NOT unrolled — the body is ~1.5 k instructions and runs once per tile; unrolled 4x it was 108 KB of
+        // straight-line code whose instruction fetch (stall_no_inst) cost more than its arithmetic
+        // (profiles/r02_gn_fusion.md).  The chunk's 32 accumulators are selected into a fixed register window instead.
+#pragma unroll(GN ? 1 : 4)
+        for (int ch = 0; ch < CPW / 32; ++ch) {
+          float v[32];
+#pragma unroll
+          for (int c2 = 0; c2 < CPW / 32; ++c2)
+            if (c2 == ch) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = acc[c2 * 32 + i];
+            }
+          const int cbase = nt * BLOCK_N + col0 + ch * 32;       // first output channel of this 32-column chunk
+          if (GN) {
+            const int ngrp = BLOCK_N / p.gn_cpg;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int gi = (col0 + ch * 32 + g * 8) / p.gn_cpg;
+              const float mean = red[(srow_sample * ngrp + gi) * 2], rstd = red[(srow_sample * ngrp + gi) * 2 + 1];
+              const float4 ga0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + g * 8));
+              const float4 ga1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + cbase + g * 8 + 4));
+              const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + g * 8));
+              const float4 be1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + cbase + g * 8 + 4));
+              const float ga[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+              const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                // same operation order as gn_apply_fused_kernel: fma(x - mean, rstd * gamma, beta), Swish with MUFU division
+                const float y = fmaf(v[8 * g + jj] - mean, rstd * ga[jj], be[jj]);
+                v[8 * g + jj] = __fdividef(y, 1.0f + expf(-y));
+              }
+            }
+            if (valid && p.gn_res_kind != 0) {
+              const long long roff = ooff + ch * 32;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                float4 r;
+                if (p.gn_res_kind == 1) {
+                  const __half* rh = reinterpret_cast<const __half*>(p.gn_res) + roff + 4 * jj;
+                  r = ld_join4(rh, rh + p.gn_res_plane);
+                } else {
+                  r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.gn_res) + roff + 4 * jj);
+                }
+                v[4 * jj + 0] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
+              }
+            }
+            if (valid && p.gn_emb != nullptr) {
+              const long long er = (p.gn_emb_index ? p.gn_emb_index[n] : static_cast<long long>(n)) * p.gn_emb_stride;
+              const float4* e4 = reinterpret_cast<const float4*>(p.gn_emb + er + cbase);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float4 e = __ldg(e4 + jj);
+                v[4 * jj + 0] += e.x; v[4 * jj + 1] += e.y; v[4 * jj + 2] += e.z; v[4 * jj + 3] += e.w;
               }
             }
           }
@@ -421,8 +600,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           }
           if (valid && p.emb != nullptr) {
             // per-sample channel vector (one-token cross-attention collapses to this, attention_blocks.py:160-195)
-            const float4* e4 = reinterpret_cast<const float4*>(p.emb + static_cast<long long>(n) * p.emb_stride +
-                                                                nt * BLOCK_N + col0 + ch * 32);
+            const float4* e4 = reinterpret_cast<const float4*>(p.emb + static_cast<long long>(n) * p.emb_stride + cbase);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const float4 e = __ldg(e4 + jj);
@@ -455,37 +633,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
           fence_proxy_async_smem();
           named_bar_sync(2 + half, 128);
           if (issuer) {
-            const int c0 = nt * BLOCK_N + col0 + ch * 32;
-            tma_store_5d(omap, stg, c0, tc.w0, tc.h0, tc.n0, 0);
-            if (p.out_mode != kOutRaw) tma_store_5d(omap, stg + Cfg::kStagingHalf / 2, c0, tc.w0, tc.h0, tc.n0, 1);
+            tma_store_5d(omap, stg, cbase, tc.w0, tc.h0, tc.n0, 0);
+            if (p.out_mode != kOutRaw) tma_store_5d(omap, stg + Cfg::kStagingHalf / 2, cbase, tc.w0, tc.h0, tc.n0, 1);
             tma_store_commit();
           }
         }
-
-        if (p.stats != nullptr) {
-          // combine the lane quarters (named barrier 1: only the 256 drain/epilogue threads participate)
-          named_bar_sync(1, 256);
-          const int spt = kTcBlockM / p.rows_per_sample;   // samples per tile (1, 2 or 4)
-          const int wps = 4 / spt;                         // lane quarters per sample
-          constexpr int G8 = BLOCK_N / 8;
-          if (te < G8 * spt) {
-            const int j = te / G8, i = te - j * G8;
-            float s = 0.f, ss = 0.f;
-            for (int wq = j * wps; wq < (j + 1) * wps; ++wq) {
-              s += red[(wq * G8 + i) * 2 + 0];
-              ss += red[(wq * G8 + i) * 2 + 1];
-            }
-            const int ns = tc.n0 + (spt > 1 ? j : 0);
-            const int chunk = (p.chunks_per_sample > 1) ? (tc.th * p.tiles_w + tc.tw) : 0;
-            if (ns < p.N) {
-              float* dst = p.stats + ((static_cast<long long>(ns) * p.chunks_per_sample + chunk) * (p.Cout / 8) +
-                                      nt * G8 + i) * 2;
-              dst[0] = s;
-              dst[1] = ss;
-            }
-          }
-          named_bar_sync(1, 256);   // red[] is reused by the next tile
-        }
+        if (GN) named_bar_sync(1, 256);   // red[] (mean / rstd) is overwritten by the next tile's statistics
       }
       u += kb1 - kb0;
     }
@@ -612,6 +765,21 @@ int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, 
   return 1;
 }
 
+// Fused GroupNorm epilogue: the finalising CTA (H*W <= 128) or CTA pair (H*W == 256) must hold whole samples, the
+// widest tile the channel count allows must hold whole groups of a multiple of 8 channels.
+int conv_tc_gn_fusable(int H, int W, int Cout, int groups) {
+  if (!g_fuse_gn || groups <= 0 || Cout % groups) return 0;
+  const int cpg = Cout / groups;
+  if (cpg % 8) return 0;
+  int bn = 256;
+  while (bn > 64 && Cout % bn) bn /= 2;
+  if (Cout % bn || bn % cpg) return 0;
+  const int hw = H * W;
+  if (hw == 2 * kTcBlockM) return 2;
+  if (hw >= 32 && hw <= kTcBlockM && kTcBlockM % hw == 0) return 1;
+  return 0;
+}
+
 // View of an NHWC split tensor sub-sampled by `sub` in H and W starting at (ph, pw): sub = 1 is the tensor itself,
 // sub = 2 selects one of the four input-parity grids a stride-2 convolution reads.
 static int encode_act_map(CUtensorMap* m, const __half* base, long long plane, int N, int H, int W, int C, int bw,
@@ -696,14 +864,31 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   MF_REQUIRE(!(d.up2 && (d.res || d.emb)), "folded upsample conv has no fused residual");
   p.chunks_per_sample = conv_tc_stats_chunks(Ho, Wo);
   p.rows_per_sample = Ho * Wo >= kTcBlockM ? kTcBlockM : Ho * Wo;
+  p.gn_mode = 0;
+  if (d.gn_groups > 0) {
+    p.gn_mode = conv_tc_gn_fusable(Ho, Wo, d.Cout, d.gn_groups);
+    MF_REQUIRE(p.gn_mode != 0, "fused GroupNorm epilogue requested for a geometry that does not allow it");
+    MF_REQUIRE(!d.up2 && d.stats == nullptr && d.res == nullptr && d.emb == nullptr && d.out_mode == kOutSplit &&
+                   d.gn_gamma != nullptr && d.gn_beta != nullptr,
+               "fused GroupNorm epilogue: split output, no separate statistics / attention residual");
+    p.gn_cpg = d.Cout / d.gn_groups;
+    p.gn_eps = d.gn_eps;
+    p.gn_gamma = d.gn_gamma; p.gn_beta = d.gn_beta;
+    p.gn_res = d.gn_res; p.gn_res_plane = d.gn_res_plane; p.gn_res_kind = d.gn_res ? d.gn_res_kind : 0;
+    p.gn_emb = d.gn_emb; p.gn_emb_stride = d.gn_emb_stride; p.gn_emb_index = nullptr;
+  }
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   int cg = d.cta_group > 0 ? d.cta_group : g_default_cta_group;
   if (cg != 1 && cg != 2) cg = (m_tiles >= 2) ? 2 : 1;  // auto
+  if (p.gn_mode == 2) cg = 2;                           // a sample = the two tiles of one CTA pair
   plan->cta_group = cg;
   int bn = d.block_n > 0 ? d.block_n : g_default_block_n;
   if (bn != 64 && bn != 128 && bn != 256) bn = 256;     // auto: widest tile the channel count allows
+  if (p.gn_mode != 0) bn = 256;
   while (d.Cout % bn) bn /= 2;
+  MF_REQUIRE(p.gn_mode == 0 || bn % p.gn_cpg == 0, "fused GroupNorm: a tile must hold whole groups");
+  MF_REQUIRE(p.gn_mode != 2 || m_tiles % 2 == 0, "fused GroupNorm (pair mode): even tile count");
   plan->block_n = bn;
   // a CTA pair owns two consecutive M tiles; an odd tile count gets a padding tile (all loads out of range -> zeros,
   // all stores masked)
@@ -768,11 +953,11 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   return encode_map(&plan->maps.w, d.w_planes, 3, wd, ws, wb, we);
 }
 
-template <int BLOCK_N, int CG>
-static int launch_t(const ConvTcPlan& plan, cudaStream_t stream) {
+template <int BLOCK_N, int CG, bool GN>
+static int launch_t(const ConvTcPlan& plan, cudaStream_t stream, const ConvTcParams& params) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     TcCfg<BLOCK_N, CG>::kSmemBytes));
     attr_set = true;
   }
@@ -790,18 +975,33 @@ static int launch_t(const ConvTcPlan& plan, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  MF_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG>, plan.maps, plan.p));
+  MF_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG, GN>, plan.maps, params));
   return 0;
 }
 
-int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream, int emb_dedup, const long long* emb_index) {
+  ConvTcParams p = plan.p;
+  if (emb_dedup && p.gn_emb != nullptr) {   // deduplicated embedding rows: one per class (index) or a single shared row
+    p.gn_emb_index = emb_index;
+    if (emb_index == nullptr) p.gn_emb_stride = 0;
+  }
+  if (p.gn_mode != 0) {
+    switch (plan.block_n * 10 + plan.cta_group) {
+      case 2561: return launch_t<256, 1, true>(plan, stream, p);
+      case 2562: return launch_t<256, 2, true>(plan, stream, p);
+      case 1281: return launch_t<128, 1, true>(plan, stream, p);
+      case 1282: return launch_t<128, 2, true>(plan, stream, p);
+      case 641: return launch_t<64, 1, true>(plan, stream, p);
+      case 642: return launch_t<64, 2, true>(plan, stream, p);
+    }
+  }
   switch (plan.block_n * 10 + plan.cta_group) {
-    case 2561: return launch_t<256, 1>(plan, stream);
-    case 2562: return launch_t<256, 2>(plan, stream);
-    case 1281: return launch_t<128, 1>(plan, stream);
-    case 1282: return launch_t<128, 2>(plan, stream);
-    case 641: return launch_t<64, 1>(plan, stream);
-    case 642: return launch_t<64, 2>(plan, stream);
+    case 2561: return launch_t<256, 1, false>(plan, stream, p);
+    case 2562: return launch_t<256, 2, false>(plan, stream, p);
+    case 1281: return launch_t<128, 1, false>(plan, stream, p);
+    case 1282: return launch_t<128, 2, false>(plan, stream, p);
+    case 641: return launch_t<64, 1, false>(plan, stream, p);
+    case 642: return launch_t<64, 2, false>(plan, stream, p);
   }
   set_error("conv_tc_launch: bad block_n / cta_group");
   return 2;

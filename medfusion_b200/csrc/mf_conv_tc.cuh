@@ -59,6 +59,16 @@ struct ConvTcParams {
   int emb_stride;
   int chunks_per_sample;         // tiles per sample (1 if a tile spans >= 1 whole samples)
   int rows_per_sample;           // min(128, H*W)
+  // ---- GroupNorm + Swish + residual (+ embedding) applied in the epilogue (conv_blocks.py:184-192,236-240,362): possible
+  //      when the finalising CTA (gn_mode 1, H*W <= 128) or CTA pair (gn_mode 2, H*W == 256: the two CTAs swap their
+  //      per-slab sums through distributed shared memory) holds every pixel of a sample.  The raw fp32 conv output and
+  //      the separate gn_apply launch disappear; `out` receives the split planes of the block's result.
+  int gn_mode;                   // 0: off
+  int gn_cpg;                    // channels per group (multiple of 8, divides BLOCK_N)
+  float gn_eps;
+  const float* gn_gamma; const float* gn_beta;   // [Cout]
+  const void* gn_res; long long gn_res_plane; int gn_res_kind;   // residual added after the activation (1 split, 2 raw fp32)
+  const float* gn_emb; int gn_emb_stride; const long long* gn_emb_index;   // per-sample channel vector added last
 };
 
 struct TcMaps {
@@ -95,6 +105,11 @@ struct ConvTcDesc {
   int cta_group;            // 0 -> default (auto), 1 or 2
   int block_n;              // 0 -> default (auto), 64 / 128 / 256 output channels per tile
   int up2;                  // 1: input is HxW, output 2Hx2W = conv3x3(nearest_x2(input)); w_planes from prep_weight_up_tc
+  // fused GroupNorm epilogue (see ConvTcParams): gn_groups > 0 requests it; conv_tc_gn_fusable() says whether the
+  // geometry allows it.  The residual / embedding are those of the res block half (added AFTER norm + Swish).
+  int gn_groups; const float* gn_gamma; const float* gn_beta; float gn_eps;
+  const void* gn_res; long long gn_res_plane; int gn_res_kind;
+  const float* gn_emb; int gn_emb_stride;
   // stream-K scratch owned by the caller (an engine keeps its own, so two engines on different streams or devices never
   // share partial-sum tiles); nullptr: the per-device scratch of the library (stand-alone mf_op_* calls)
   const struct StreamKScratch* scratch;
@@ -118,8 +133,12 @@ extern int g_stream_k;
 extern int g_pdl;   // defined in mf_kernels.cu
 extern float g_debias_eps_per_kblock;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
+// can GroupNorm(groups) + Swish + residual be applied inside the epilogue of this convolution (OUTPUT geometry H, W)?
+int conv_tc_gn_fusable(int H, int W, int Cout, int groups);
+extern int g_fuse_gn;   // 1: engines use the fused GroupNorm epilogue wherever conv_tc_gn_fusable() allows (default 0)
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
-int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+// emb_dedup: the fused-GroupNorm embedding rows are deduplicated for this call (row = emb_index[n], or one shared row)
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream, int emb_dedup = 0, const long long* emb_index = nullptr);
 // number of chunks (tiles per sample) the stats buffer must provide for this geometry
 int conv_tc_stats_chunks(int H, int W);
 

@@ -219,8 +219,14 @@ int EngineBase::ensure_w_simt(ConvLayer& L) {
 }
 
 // ---- op builders ---------------------------------------------------------------------------------
+bool EngineBase::conv_gn_fusable(const ConvLayer& L, const Tens& in0, const Tens* in1, int Ho, int Wo, int groups) const {
+  const int C1 = in1 ? in1->C : 0;
+  return L.stride == 1 && in0.layout == kNHWCSplit && (!in1 || in1->layout == kNHWCSplit) && g_gn_variant == 3 &&
+         conv_tc_supported(in0.N, Ho, Wo, in0.C, C1, L.Cout, L.k, 1) && conv_tc_gn_fusable(Ho, Wo, L.Cout, groups) != 0;
+}
+
 int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const Tens& out, const Tens* stats,
-                         int* chunks, const Tens* res, const float* emb, int emb_stride) {
+                         int* chunks, const Tens* res, const float* emb, int emb_stride, const GnFuse* gn) {
   const int C1 = in1 ? in1->C : 0;
   MF_REQUIRE(in0.C + C1 == L.Cin, "conv input channels do not match the weight (" + L.w->name + ")");
   MF_REQUIRE(out.C == L.Cout, "conv output channels do not match the weight (" + L.w->name + ")");
@@ -246,16 +252,26 @@ int EngineBase::add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const T
       d.res = res->ptr; d.res_plane = res->plane; d.res_kind = res->layout == kNHWCSplit ? 1 : 2;
     }
     d.emb = emb; d.emb_stride = emb_stride;
+    if (gn != nullptr) {
+      MF_REQUIRE(stats == nullptr && res == nullptr && emb == nullptr && out.layout == kNHWCSplit,
+                 "fused GroupNorm conv: split output, no separate statistics");
+      d.gn_groups = gn->groups; d.gn_gamma = gn->nl->g->data.p; d.gn_beta = gn->nl->b->data.p; d.gn_eps = 1e-5f;
+      if (gn->res) {
+        d.gn_res = gn->res->ptr; d.gn_res_plane = gn->res->plane; d.gn_res_kind = gn->res->layout == kNHWCSplit ? 1 : 2;
+      }
+      d.gn_emb = gn->emb; d.gn_emb_stride = gn->emb_stride;
+    }
     d.scratch = scratch();
     MF_REQUIRE(d.scratch != nullptr, "stream-K scratch allocation failed");
     tc_plans.emplace_back(new ConvTcPlan());
     ConvTcPlan* plan = tc_plans.back().get();
     rc = conv_tc_build(d, plan);
     if (rc) return rc;
-    push_op([plan](cudaStream_t s) { return conv_tc_launch(*plan, s); }, kOpConvTc,
+    push_op([this, plan](cudaStream_t s) { return conv_tc_launch(*plan, s, io_emb_dedup ? 1 : 0, io_emb_index); }, kOpConvTc,
             2.0 * out.N * out.H * out.W * L.Cout * static_cast<double>(L.Cin) * L.k * L.k);
     return 0;
   }
+  MF_REQUIRE(gn == nullptr, "fused GroupNorm exists on the tensor-core path only (" + L.w->name + ")");
   // exact fp32 SIMT path (single source only)
   MF_REQUIRE(res == nullptr && emb == nullptr,
              "fused residual / embedding epilogues exist on the tensor-core path only (" + L.w->name + ")");
@@ -673,12 +689,44 @@ int EngineBase::add_attention(SpatialAttnLayer& A, int groups, const Tens& x, co
 int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, const Tens* in1, const Tens* embT,
                              int emb_stride, Tens* out, ConvLayer* head, float* const* head_dst) {
   const int N = in0.N, H = in0.H, W = in0.W;
+  const float* emb = (embT != nullptr && rb.emb_offset >= 0 && !dry) ? embT->ptr + rb.emb_offset : nullptr;
+  int rc = 0;
+  // ---- levels where a CTA (pair) holds whole samples: GroupNorm + Swish + residual + embedding ride in the conv epilogue,
+  //      no raw fp32 tensor, no GroupNorm launch
+  Tens x1_like = in0;            // geometry of the first half's output (what conv2 reads)
+  x1_like.C = rb.Cout; x1_like.layout = kNHWCSplit;
+  if (head == nullptr && conv_gn_fusable(rb.conv1, in0, in1, H, W, groups) &&
+      conv_gn_fusable(rb.conv2, x1_like, nullptr, H, W, groups)) {
+    Tens res_raw;
+    const Tens* res = nullptr;
+    if (rb.has_res_conv) {
+      res_raw = new_tensor(N, H, W, rb.Cout, kNHWCRaw);
+      rc = add_conv(rb.conv_res, in0, in1, res_raw, nullptr, nullptr);
+      if (rc) return rc;
+      res = &res_raw;
+    } else {
+      MF_REQUIRE(in1 == nullptr, "identity residual over a concatenated input is not representable");
+      res = &in0;
+    }
+    Tens x1 = new_tensor(N, H, W, rb.Cout, kNHWCSplit);
+    GnFuse g1{&rb.norm1, groups, res, emb, emb_stride};
+    rc = add_conv(rb.conv1, in0, in1, x1, nullptr, nullptr, nullptr, nullptr, 0, &g1);
+    if (rc) return rc;
+    if (rb.has_res_conv) free_tensor(res_raw);
+    Tens x2 = new_tensor(N, H, W, rb.Cout, kNHWCSplit);
+    GnFuse g2{&rb.norm2, groups, &x1, nullptr, 0};
+    rc = add_conv(rb.conv2, x1, nullptr, x2, nullptr, nullptr, nullptr, nullptr, 0, &g2);
+    if (rc) return rc;
+    free_tensor(x1);
+    *out = x2;
+    return 0;
+  }
   const int max_chunks = std::max(1, conv_tc_stats_chunks(H, W));
   Tens raw = new_tensor(N, H, W, rb.Cout, kNHWCRaw);
-  Tens part = new_floats(static_cast<size_t>(N) * max_chunks * (rb.Cout / 8) * 2);
+  Tens part = new_floats(static_cast<size_t>(N) * max_chunks * ((rb.Cout + 7) / 8) * 2);
   int chunks = 1;
   const bool generic_gn = gn_needs_generic(rb.Cout, groups);   // statistics then come from the raw tensor, not the conv
-  int rc = add_conv(rb.conv1, in0, in1, raw, generic_gn ? nullptr : &part, &chunks);
+  rc = add_conv(rb.conv1, in0, in1, raw, generic_gn ? nullptr : &part, &chunks);
   if (rc) return rc;
   Tens res_raw;
   const Tens* res = nullptr;
@@ -692,7 +740,6 @@ int EngineBase::add_resblock(ResBlockLayer& rb, int groups, const Tens& in0, con
     res = &in0;
   }
   Tens x1 = new_tensor(N, H, W, rb.Cout, kNHWCSplit);
-  const float* emb = (embT != nullptr && rb.emb_offset >= 0 && !dry) ? embT->ptr + rb.emb_offset : nullptr;
   rc = add_gn_apply(rb.norm1, groups, raw, part, chunks, res, emb, emb_stride, x1);
   if (rc) return rc;
   if (rb.has_res_conv) free_tensor(res_raw);

@@ -172,8 +172,12 @@ class EngineBase {
 
   // conv: in0 (+ optional in1 channel-concatenated) -> out.  If stats != nullptr the (sum, sumsq)
   // partials of the output are produced too and *chunks receives their chunk count.
+  // gn != nullptr: GroupNorm + Swish + gn->res + gn->emb applied in the conv's epilogue (tensor-core path, geometry
+  // permitting: conv_gn_fusable()); `out` is then the split result of the res-block half.
+  struct GnFuse { const NormLayer* nl; int groups; const Tens* res; const float* emb; int emb_stride; };
+  bool conv_gn_fusable(const ConvLayer& L, const Tens& in0, const Tens* in1, int Ho, int Wo, int groups) const;
   int add_conv(ConvLayer& L, const Tens& in0, const Tens* in1, const Tens& out, const Tens* stats, int* chunks,
-               const Tens* res = nullptr, const float* emb = nullptr, int emb_stride = 0);
+               const Tens* res = nullptr, const float* emb = nullptr, int emb_stride = 0, const GnFuse* gn = nullptr);
   // GroupNorm (no activation) of a split tensor -> split
   int add_group_norm_split(const NormLayer& nl, int groups, const Tens& x, const Tens& out);
   // attention block applied to x (split) -> *out (split).  emb: raw [B, emb_dim] embedding (may be null)

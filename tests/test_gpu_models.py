@@ -492,3 +492,33 @@ def test_cfg_as_one_batch_equals_two_passes(with_un_cond):
     for k in ("x_T", "x_0", "x_prior", "x_next"):
         # x_T is the guided estimate itself (7 = |1-g| + |g| times the per-pass summation-order noise of ~1e-6)
         assert_close(got[k].cpu(), ref[k].cpu(), rtol=1e-4, atol=1e-5 * max(1.0, B640), what=f"one-batch CFG {k}")
+
+
+def test_fused_groupnorm_epilogue_matches_reference_fixture():
+    """mf_set_fuse_gn(1): GroupNorm + Swish + residual + embedding applied inside the conv epilogue at the 16x16 level
+    (CTA pair = one sample, statistics swapped through distributed shared memory) and the 8x8 level (CTA = two samples):
+    65 instead of 89 launches, same numbers as the reference fixture and as the separate-kernel path."""
+    from medfusion_b200 import _lib
+    lib = _lib.load()
+    g = load_golden("unet_canonical.pt")
+    x, t, c = g["x"].to(DEV), g["t"].to(DEV), g["cond"].to(DEV)
+    try:
+        lib.mf_set_fuse_gn(1)
+        m = make_unet(g["cfg"], DEV)
+        y, _ = m(x, t, c)
+        assert m.plan_info()["launches"] == 65
+        assert_close(y.cpu(), g["y_cond"], what="fused GroupNorm, cond")
+        y_u, _ = m(x, t, None)
+        assert_close(y_u.cpu(), g["y_uncond"], what="fused GroupNorm, uncond")
+        # odd batch (ragged last tile: a CTA holding one real and one out-of-range sample) and per-class embedding rows
+        xb = x.repeat(3, 1, 1, 1)[:5].contiguous()
+        tb = torch.full((5,), int(t[0]), device=DEV)
+        yb, _ = m(xb, tb, c.repeat(3)[:5].contiguous())
+        y1, _ = m(x[:1].contiguous(), tb[:1], c[:1].contiguous())
+        assert_close(yb[2:3].cpu(), y1.cpu(), rtol=1e-4, atol=1e-5, what="fused GroupNorm, B=5 row vs B=1")
+    finally:
+        lib.mf_set_fuse_gn(0)
+    m0 = make_unet(g["cfg"], DEV)
+    y0, _ = m0(x, t, c)
+    assert m0.plan_info()["launches"] == 89
+    assert_close(y.cpu(), y0.cpu(), rtol=1e-4, atol=1e-5, what="fused vs separate GroupNorm")
