@@ -115,6 +115,9 @@ typedef struct {
   int num_classes;                 /* LabelEmbedder num_classes (cond_embedders.py:6); 0 = none */
   int norm_groups;                 /* GroupNorm groups (32) */
   int attention[MF_MAX_LEVELS];    /* per level: 0 = 'none', 1 = 'linear', 2 = 'spatial' (attention_blocks.py:291-335) */
+  int deep_supervision;            /* number of deep-supervision heads `outc_ver` (unet2.py:214-217; True = depth-2) (ABI v3) */
+  int ds_out_ch;                   /* their output channels (0 = out_ch; the reference uses the plain out_ch even when
+                                      estimate_variance doubles the main head) (ABI v3) */
 } mf_unet_config;
 
 typedef struct mf_unet mf_unet;
@@ -135,6 +138,12 @@ size_t mf_unet_workspace_bytes(mf_unet* h, int B, int H, int W);
 /* y[B,out_ch,H,W] = UNet(x_t[B,in_ch,H,W], t[B] (int64), cond[B] (int64) or NULL).  NCHW fp32. */
 int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
                     int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream);
+/* mf_unet_forward + (ABI v3) timesteps as fp32 (d_t_float != NULL takes precedence; the reference's sinusoid accepts any
+ * dtype, time_embedder.py:15-28) and the deep-supervision outputs: d_y_ver[k] (k < n_ver) = [B, out_ch, h_k, w_k] at the
+ * resolution of level k+1, or NULL to skip that head (unet2.py:258-269 returns them as the second output). */
+int mf_unet_forward_ex(mf_unet* h, const float* d_x_t, const int64_t* d_t, const float* d_t_float, const int64_t* d_cond,
+                       float* d_y, float* const* d_y_ver, int n_ver, int B, int H, int W, void* d_workspace,
+                       size_t workspace_bytes, mf_stream_t stream);
 /* UNet.forward with the scheduler update fused into the epilogue of the output head (unet2.py:267 +
  * gaussian_scheduler.py:80-124 + diffusion_pipeline.py:244,297-304): the estimator output never round-trips through a
  * separate elementwise kernel.  d_y may be NULL when only the step outputs are wanted.  Requires out_ch <= 8. */

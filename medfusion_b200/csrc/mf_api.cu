@@ -22,6 +22,9 @@ struct mf_unet : public EngineBase {
   struct DecEntry { ResBlockLayer rb; SpatialAttnLayer attn; bool has_up = false; ConvLayer up; int up_factor = 1; };
   std::vector<std::unique_ptr<DecEntry>> dec;          // out_blocks (module index order)
   ConvLayer outc;
+  std::vector<std::unique_ptr<ConvLayer>> outc_ver;    // deep-supervision heads (unet2.py:214-217), 1x1 on the concat input
+  float* io_y_ver[MF_MAX_LEVELS] = {nullptr};          // optional outputs of this call (NULL: head not evaluated)
+  const float* io_t_float = nullptr;                   // timesteps as fp32 (NULL: io_t int64)
   Param *t_w1 = nullptr, *t_b1 = nullptr, *t_w2 = nullptr, *t_b2 = nullptr, *cond_table = nullptr;
   DevBuf freqs;
   bool freqs_set = false;
@@ -55,7 +58,7 @@ int mf_unet::init(const mf_unet_config& c) {
   }
   const int E = c.emb_dim;
   if (E > 0) {
-    MF_REQUIRE(c.pos_emb_dim > 0 && c.pos_emb_dim % 64 == 0, "pos_emb_dim must be a multiple of 64");
+    MF_REQUIRE(c.pos_emb_dim > 0 && c.pos_emb_dim % 2 == 0, "pos_emb_dim must be even");
     t_w1 = add_param("time_embedder.time_emb.1.weight", {E, c.pos_emb_dim});
     t_b1 = add_param("time_embedder.time_emb.1.bias", {E});
     t_w2 = add_param("time_embedder.time_emb.3.weight", {E, E});
@@ -106,6 +109,14 @@ int mf_unet::init(const mf_unet_config& c) {
     }
   }
   init_conv(*this, outc, "outc.conv.conv", c.out_ch, hid[0], 1, 1);
+  // deep-supervision heads: UnetOutBlock(hid[i] + hid[i-1] -> out_ch) for i = 2 .. deep_supervision + 1 (unet2.py:214-217;
+  // always the plain out_ch, also with estimate_variance)
+  MF_REQUIRE(c.deep_supervision >= 0 && c.deep_supervision <= std::max(0, c.depth - 2), "deep_supervision must be in [0, depth-2]");
+  for (int i = 2; i < c.deep_supervision + 2; ++i) {
+    outc_ver.emplace_back(new ConvLayer());
+    init_conv(*this, *outc_ver.back(), "outc_ver." + std::to_string(i - 2) + ".conv.conv", c.ds_out_ch > 0 ? c.ds_out_ch : c.out_ch,
+              hid[i] + hid[i - 1], 1, 1);
+  }
   // embedding offsets
   emb_total = 0;
   if (E > 0)
@@ -174,6 +185,7 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
       push_op([this, l1](cudaStream_t st) {
         LinearDesc d = l1;
         d.t = io_t;
+        d.t_float = io_t_float;
         d.t_stride = 1;
         if (io_emb_dedup) { d.B = emb_rows; d.t_stride = 0; }
         return linear_small(d, st);
@@ -256,6 +268,16 @@ int mf_unet::build(int B, int H, int W, char* ws, bool dry_run, cudaStream_t s) 
     DecEntry& d = *dec[i - 1];
     Tens skip = skips.back();
     skips.pop_back();
+    // deep supervision (unet2.py:262): the head of level L = (i-1)/(num_res_blocks+1) + 1 reads the concat input of that
+    // level's first decoder block
+    {
+      const int per = cfg.num_res_blocks + 1;
+      const int level = (i - 1) / per + 1, kk = (i - 1) % per;
+      if (kk == 0 && level >= 2 && level - 2 < static_cast<int>(outc_ver.size())) {
+        rc = add_conv_nchw_out(*outc_ver[level - 2], hcur, &io_y_ver[level - 2], &skip);
+        if (rc) return rc;
+      }
+    }
     Tens o;
     rc = add_resblock(d.rb, G, hcur, &skip, embTp, emb_total, &o);
     if (rc) return rc;
@@ -661,18 +683,29 @@ size_t mf_unet_workspace_bytes(mf_unet* h, int B, int H, int W) {
   (void)saved;
   return need;
 }
-int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
-                    int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream) {
+int mf_unet_forward_ex(mf_unet* h, const float* d_x_t, const int64_t* d_t, const float* d_t_float, const int64_t* d_cond,
+                       float* d_y, float* const* d_y_ver, int n_ver, int B, int H, int W, void* d_workspace,
+                       size_t workspace_bytes, mf_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MF_REQUIRE(d_x_t && d_y && B > 0 && H > 0 && W > 0, "bad arguments");
-  MF_REQUIRE(h->cfg.emb_dim <= 0 || d_t != nullptr, "t is required when the UNet has a time embedder");
+  MF_REQUIRE(h->cfg.emb_dim <= 0 || d_t != nullptr || d_t_float != nullptr, "t is required when the UNet has a time embedder");
+  MF_REQUIRE(n_ver >= 0 && n_ver <= static_cast<int>(h->outc_ver.size()), "more deep-supervision outputs than heads");
   int rc = prepare_plan(h, B, H, W, d_workspace, workspace_bytes, s);
   if (rc) return rc;
   h->io_x = d_x_t;
   h->io_t = reinterpret_cast<const long long*>(d_t);
+  h->io_t_float = d_t_float;
   h->io_cond = reinterpret_cast<const long long*>(d_cond);
   h->io_y = d_y;
-  return h->run(s);
+  for (int k = 0; k < n_ver; ++k) h->io_y_ver[k] = d_y_ver ? d_y_ver[k] : nullptr;
+  rc = h->run(s);
+  h->io_t_float = nullptr;
+  for (int k = 0; k < MF_MAX_LEVELS; ++k) h->io_y_ver[k] = nullptr;
+  return rc;
+}
+int mf_unet_forward(mf_unet* h, const float* d_x_t, const int64_t* d_t, const int64_t* d_cond, float* d_y, int B,
+                    int H, int W, void* d_workspace, size_t workspace_bytes, mf_stream_t stream) {
+  return mf_unet_forward_ex(h, d_x_t, d_t, nullptr, d_cond, d_y, nullptr, 0, B, H, W, d_workspace, workspace_bytes, stream);
 }
 // All samples share the timestep (the sampling loop calls the estimator with t.expand(B)): the embedding MLP then
 // depends only on the class, so it is evaluated once per class (or once) instead of once per sample.

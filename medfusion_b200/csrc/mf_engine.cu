@@ -412,9 +412,11 @@ int EngineBase::add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, i
   return 0;
 }
 
-int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst) {
-  MF_REQUIRE(in0.C == L.Cin, "head conv channel mismatch (" + L.w->name + ")");
-  if (L.k == 1 && L.stride == 1 && L.Cout <= 8 && in0.layout == kNHWCSplit && in0.C % 64 == 0) {
+int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst, const Tens* in1) {
+  const int C1 = in1 ? in1->C : 0;
+  MF_REQUIRE(in0.C + C1 == L.Cin, "head conv channel mismatch (" + L.w->name + ")");
+  MF_REQUIRE(in1 == nullptr || (in1->layout == in0.layout && in0.layout != kNCHW), "two-source head: NHWC sources of one kind");
+  if (in1 == nullptr && L.k == 1 && L.stride == 1 && L.Cout <= 8 && in0.layout == kNHWCSplit && in0.C % 64 == 0) {
     // narrow 1x1 head straight from the reference-layout weights; the scheduler update can ride in its epilogue
     ++n_simt;
     if (dry) return 0;
@@ -441,10 +443,12 @@ int EngineBase::add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* d
   if (rc) return rc;
   ConvSimtDesc d{};
   d.in = in0.ptr; d.in_plane = in0.plane; d.in_layout = in0.layout;
-  d.N = in0.N; d.Cin = in0.C; d.Hin = in0.H; d.Win = in0.W;
+  d.in1 = in1 ? in1->ptr : nullptr; d.in1_plane = in1 ? in1->plane : 0; d.C1 = C1;
+  d.N = in0.N; d.Cin = in0.C + C1; d.Hin = in0.H; d.Win = in0.W;
   d.w_kc = L.w_simt.p; d.bias = L.b->data.p; d.Cout = L.Cout; d.ksize = L.k; d.stride = L.stride;
   d.out = nullptr; d.out_plane = 0; d.out_layout = kNCHW;
   push_op([d, dst](cudaStream_t s) {
+    if (*dst == nullptr) return 0;      // optional output not requested by this call
     ConvSimtDesc dd = d;
     dd.out = *dst;
     return conv_simt(dd, s);

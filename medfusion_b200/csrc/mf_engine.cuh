@@ -187,7 +187,8 @@ class EngineBase {
   int add_conv_nchw_in(ConvLayer& L, const float* const* src, int N, int Cin, int H, int W, const Tens& out,
                        const Tens* stats, int* chunks);
   // conv writing an external NCHW fp32 pointer only known at call time
-  int add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst);
+  // in1: optional second source (channel concat).  A NULL *dst at launch time skips the op (optional outputs).
+  int add_conv_nchw_out(ConvLayer& L, const Tens& in0, float* const* dst, const Tens* in1 = nullptr);
   // BasicUp: out[2H,2W] = conv3x3(nearest_x2(in)) as four 2x2 phase convolutions on the tensor-core path, or
   // (shapes the tensor-core path cannot take) an explicit upsample followed by add_conv.
   int add_upconv2x(ConvLayer& L, const Tens& in, Tens* out);

@@ -791,7 +791,8 @@ __global__ void linear_small_kernel(const LinearDesc d) {
       for (int i = 0; i < KPL; ++i) acc = fmaf(w[i], x[i * 32 + lane], acc);
     } else {
       // sinusoidal position embedding: cat(sin(t*f), cos(t*f)), f given by the host table
-      const float tf = static_cast<float>(d.t[static_cast<long long>(b) * d.t_stride]);
+      const float tf = d.t_float ? d.t_float[static_cast<long long>(b) * d.t_stride]
+                                 : static_cast<float>(d.t[static_cast<long long>(b) * d.t_stride]);
       const int half = d.K / 2;
 #pragma unroll
       for (int i = 0; i < KPL; ++i) {
@@ -811,9 +812,40 @@ __global__ void linear_small_kernel(const LinearDesc d) {
   }
 }
 
+// any K (e.g. the 16-wide sinusoid of a 64-wide time embedding, time_embedder.py:62): one thread per output, sequential k
+__global__ void linear_generic_kernel(const LinearDesc d) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(d.B) * d.J) return;
+  const int b = static_cast<int>(i / d.J), j = static_cast<int>(i % d.J);
+  float acc = 0.f;
+  if (d.in_mode == 0) {
+    for (int k = 0; k < d.K; ++k) acc = fmaf(d.W[static_cast<long long>(j) * d.K + k], d.in[static_cast<long long>(b) * d.K + k], acc);
+  } else {
+    const float tf = d.t_float ? d.t_float[static_cast<long long>(b) * d.t_stride]
+                               : static_cast<float>(d.t[static_cast<long long>(b) * d.t_stride]);
+    const int half = d.K / 2;
+    for (int k = 0; k < d.K; ++k) {
+      const float a = tf * d.freqs[k < half ? k : k - half];
+      acc = fmaf(d.W[static_cast<long long>(j) * d.K + k], k < half ? sinf(a) : cosf(a), acc);
+    }
+  }
+  float v = acc + (d.bias ? d.bias[j] : 0.f);
+  if (d.add_table != nullptr) v += d.add_table[(d.add_idx ? d.add_idx[b] : static_cast<long long>(b)) * d.J + j];
+  if (d.post == 1) v = swish(v);
+  d.out[i] = v;
+  if (d.out2 != nullptr) d.out2[i] = swish(v);
+}
+
 int linear_small(const LinearDesc& d, cudaStream_t s) {
-  MF_REQUIRE(d.K % 32 == 0 && d.K <= 2048, "linear_small: K must be a multiple of 32, <= 2048");
   if (d.B == 0 || d.J == 0) return 0;
+  const int kpl = d.K / 32;
+  const bool fast = d.K % 32 == 0 && d.K <= 2048 && (kpl & (kpl - 1)) == 0;
+  if (!fast) {
+    const long long total = static_cast<long long>(d.B) * d.J;
+    linear_generic_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(d);
+    MF_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const int blocks = ceil_div_ll(static_cast<long long>(d.J) * 32, 256);
   switch (d.K / 32) {
 #define MF_LIN_CASE(n) case n: linear_small_kernel<n><<<blocks, 256, 0, s>>>(d); break;

@@ -96,6 +96,7 @@ int upsample2x_split(const __half* in, long long in_plane, __half* out, long lon
 //   post 0: identity, 1: swish;  out2 (optional) receives swish(out)
 struct LinearDesc {
   const float* in; const long long* t; int t_stride; const float* freqs; int in_mode;  // t[b * t_stride]
+  const float* t_float;   // != nullptr: timesteps given as fp32 (the reference accepts any dtype, time_embedder.py:15-28)
   const float* W; const float* bias;
   const float* add_table; const long long* add_idx;  // optional embedding-table add: add_table[add_idx ? add_idx[b] : b][j]
   float* out; float* out2; int post;
