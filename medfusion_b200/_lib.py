@@ -24,7 +24,7 @@ class UNetConfig(ctypes.Structure):
         ("hid_chs", c_int * MF_MAX_LEVELS), ("kernel_sizes", c_int * MF_MAX_LEVELS),
         ("strides", c_int * MF_MAX_LEVELS), ("num_res_blocks", c_int), ("emb_dim", c_int),
         ("pos_emb_dim", c_int), ("num_classes", c_int), ("norm_groups", c_int),
-        ("attention", c_int * MF_MAX_LEVELS),
+        ("attention", c_int * MF_MAX_LEVELS), ("deep_supervision", c_int), ("ds_out_ch", c_int),
     ]
 
 
@@ -84,6 +84,7 @@ SIGNATURES = {
     "mf_unet_set_time_freqs": (c_int, [_P, _P, c_int, _P]),
     "mf_unet_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "mf_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "mf_unet_forward_ex": (c_int, [_P, _P, _P, _P, _P, _P, POINTER(_P), c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "mf_unet_forward_step": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, POINTER(StepArgs), _P]),
     "mf_unet_forward_step_cfg": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, POINTER(StepArgs), _P]),
     "mf_unet_profile": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P, POINTER(c_float),

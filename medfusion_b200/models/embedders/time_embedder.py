@@ -18,8 +18,8 @@ class SinusoidalPosEmb:
     def __init__(self, emb_dim=16, downscale_freq_shift=1, max_period=10000, flip_sin_to_cos=False):
         if flip_sin_to_cos:
             raise NotImplementedError("flip_sin_to_cos=True is not supported by the B200 embedding kernel")
-        if emb_dim % 64 != 0:
-            raise ValueError("SinusoidalPosEmb emb_dim must be a multiple of 64 for the B200 kernel")
+        if emb_dim % 2 != 0 or emb_dim < 4:
+            raise ValueError("SinusoidalPosEmb emb_dim must be even (cat(sin, cos) halves)")
         self.emb_dim = emb_dim
         self.downscale_freq_shift = downscale_freq_shift
         self.max_period = max_period

@@ -52,8 +52,6 @@ class UNet(EngineModule):
             raise NotImplementedError("medfusion_b200.UNet implements the 2-D model (spatial_dims=2)")
         if not use_res_block:
             raise NotImplementedError("use_res_block=False (UnetBasicBlock) is not on the accelerated hot path")
-        if deep_supervision not in (False, 0):
-            raise NotImplementedError("deep_supervision heads are training-only; construct with deep_supervision=False")
         if not learnable_interpolation:
             raise NotImplementedError("learnable_interpolation=False (pooling) is not implemented")
         if dropout not in (0, 0.0, None):
@@ -97,12 +95,18 @@ class UNet(EngineModule):
         cfg.pos_emb_dim = self.time_spec.pos_emb_dim if self.time_spec is not None else 0
         cfg.num_classes = self.cond_spec.num_classes if self.cond_spec is not None else 0
         cfg.norm_groups = dict(norm_name[1]).get("num_groups", 32) if isinstance(norm_name, (tuple, list)) else 32
+        # deep supervision (unet2.py:214-217): True = depth-2 heads on the concat inputs of levels 2.., plain out_ch each
+        self.deep_supervision = (depth - 2 if deep_supervision else 0) if isinstance(deep_supervision, bool) \
+            else int(deep_supervision)
+        cfg.deep_supervision = self.deep_supervision
+        cfg.ds_out_ch = out_ch
+        self._strides = [int(v) for v in strides]
         handle = ctypes.c_void_p()
         _lib.check(_lib.load().mf_unet_create(ctypes.byref(cfg), ctypes.byref(handle)), "mf_unet_create")
         # zero-initialised modules of the reference: 2nd conv of every res block (conv_blocks.py:336 -> :174)
         # and the output head (unet2.py:213)
         # ... plus every attention output projection (attention_blocks.py:149-152)
-        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc.", "*.to_out.0."))
+        self._engine_init(handle, zero_init=("*.block_seq.1.basic_block.conv.", "outc.", "outc_ver.", "*.to_out.0."))
 
     # ------------------------------------------------------------------------------------------
     def _after_param_sync(self, stream):
@@ -127,14 +131,37 @@ class UNet(EngineModule):
             # unet2.py:243-246, quirk kept: the second half is zeros on the first call and x_t ITSELF (not the
             # self_cond tensor) whenever a self_cond is passed
             x = torch.cat([x, torch.zeros_like(x) if self_cond is None else x], dim=1)
-        tt = None if t is None else t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
+        t_float = t is not None and torch.is_floating_point(t)      # the reference's sinusoid takes any dtype
+        if t is None:
+            tt = None
+        elif t_float:
+            tt = t.to(device=x.device, dtype=torch.float32).expand(B).contiguous()
+        else:
+            tt = t.to(device=x.device, dtype=torch.int64).expand(B).contiguous()
         cc = None
         if condition is not None and self.cond_spec is not None:
             cc = condition.to(device=x.device, dtype=torch.int64).contiguous()
         y = torch.empty((B, self.out_ch * (2 if self.estimate_variance else 1), H, W), device=x.device,
                         dtype=torch.float32)
-        self._forward_into(x, tt, cc, y)
-        return y, []
+        if not t_float and self.deep_supervision == 0:
+            self._forward_into(x, tt, cc, y)
+            return y, []
+        # deep-supervision outputs (unet2.py:258-269): head k sits at the resolution of level k+1
+        y_ver, h, w = [], H, W
+        k0, s0 = self._k0, self._s0
+        h, w = (h + 2 * (k0 // 2) - k0) // s0 + 1, (w + 2 * (k0 // 2) - k0) // s0 + 1
+        for lvl in range(1, self.deep_supervision + 1):
+            st = self._strides[lvl]
+            h, w = (h + 2 - 3) // st + 1, (w + 2 - 3) // st + 1
+            y_ver.append(torch.empty((B, self.out_ch, h, w), device=x.device, dtype=torch.float32))
+        ptrs = (ctypes.c_void_p * max(1, len(y_ver)))(*[v.data_ptr() for v in y_ver])
+        with on_device(x):
+            ws, ws_bytes = self._workspace(B, H, W)
+            _lib.check(_lib.load().mf_unet_forward_ex(
+                self._h, x.data_ptr(), None if (tt is None or t_float) else tt.data_ptr(),
+                tt.data_ptr() if t_float else None, None if cc is None else cc.data_ptr(), y.data_ptr(), ptrs, len(y_ver),
+                B, H, W, ws, ws_bytes, cuda_stream_ptr(x.device)), "mf_unet_forward_ex")
+        return y, y_ver
 
     def _check_inputs(self, x_t, t, condition):
         """The kernels index the embedding table with `condition` and the sinusoid / scheduler tables with `t`: out-of-range

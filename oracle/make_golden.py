@@ -328,6 +328,31 @@ def vqvae_fixture():
     torch.save(out, os.path.join(OUT, "vqvae.pt"))
 
 
+# /root/reference/tests/models/test_unet.py:13-28, verbatim: 3-channel images, widths 32..256 (1/2/4/8 channels per GroupNorm
+# group), a 1x1 stem, 'linear' attention at every level, the default 64-wide time embedding (16-wide sinusoid), the default
+# deep supervision (True -> depth-2 heads) and FLOATING-POINT timesteps (`time = torch.randn([1,])`, :34)
+UNET_REFTEST = dict(in_ch=3, out_ch=3, spatial_dims=2, hid_chs=[32, 64, 128, 256], kernel_sizes=[1, 3, 3, 3],
+                    strides=[1, 2, 2, 2], cond_embedder_kwargs={"emb_dim": 64, "num_classes": 2}, use_attention="linear")
+
+
+@torch.no_grad()
+def reftest_fixture():
+    """The model of the reference's own tests/models/test_unet.py (which asserts nothing): both outputs of forward — y and the
+    deep-supervision list — for a seeded 64x64 input, float timesteps and labels."""
+    m = UNet(cond_embedder=LabelEmbedder, time_embedder_kwargs={"pos_embedder_kwargs": {}},
+             **{k: (dict(v) if isinstance(v, dict) else v) for k, v in UNET_REFTEST.items()}).eval()
+    fill_(m)
+    g = gen(71)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.randn(2, generator=g)
+    c = torch.tensor([0, 1])
+    y, y_ver = m(x, t, c)
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    torch.save(dict(cfg=UNET_REFTEST, x=x, t=t, cond=c, y=y, y_ver=list(y_ver), keys=keys),
+               os.path.join(OUT, "unet_reftest.pt"))
+    print("reftest", float(y.abs().max()), [tuple(v.shape) for v in y_ver], len(keys))
+
+
 UNET_CONFIG4 = dict(in_ch=8, out_ch=8, spatial_dims=2, hid_chs=[256, 256, 512, 1024], kernel_sizes=[3, 3, 3, 3],
                     strides=[1, 2, 2, 2], time_embedder_kwargs={"emb_dim": 1024},
                     cond_embedder_kwargs={"emb_dim": 1024, "num_classes": 2}, deep_supervision=False,
@@ -461,7 +486,7 @@ if __name__ == "__main__":
                unet_canonical=lambda: unet_fixture("unet_canonical.pt", UNET_CANON, 2),
                unet_attn_small=lambda: unet_fixture("unet_attn_small.pt", UNET_ATTN, 3),
                vae=vae_fixture, sched=sched_fixture, sample=sample_fixture, ckpt=ckpt_fixture, opts=opts_fixture,
-               vae_encode=vae_encode_fixture, config4=config4_fixture, vqvae=vqvae_fixture, traj=traj_fixture, forward=forward_fixture)
+               vae_encode=vae_encode_fixture, config4=config4_fixture, vqvae=vqvae_fixture, reftest=reftest_fixture, traj=traj_fixture, forward=forward_fixture)
     todo = sys.argv[1:] or list(ALL)      # python oracle/make_golden.py [fixture names]
     for name in todo:
         ALL[name]()

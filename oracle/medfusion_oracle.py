@@ -159,9 +159,9 @@ def attention(sd, pre, x, emb, groups, heads=8):
 # ------------------------------------------------------------------------------------------------
 # UNet (models/estimators/unet2.py:222-269)
 # ------------------------------------------------------------------------------------------------
-def unet_forward(sd, cfg, x_t, t, cond=None, self_cond=None):
+def unet_forward(sd, cfg, x_t, t, cond=None, self_cond=None, with_ver=False):
     """cfg: dict(hid_chs, strides, num_res_blocks, groups, pos_emb_dim[, use_self_conditioning]).
-    Returns y (y_ver is empty)."""
+    Returns y, or (y, y_ver) with the deep-supervision outputs (unet2.py:262,269) when with_ver."""
     hid, strides, nrb, G = cfg["hid_chs"], cfg["strides"], cfg.get("num_res_blocks", 2), cfg.get("groups", 32)
     depth = len(hid)
     if cfg.get("use_self_conditioning", False):                                        # unet2.py:243-246 (x_t, not self_cond)
@@ -183,15 +183,20 @@ def unet_forward(sd, cfg, x_t, t, cond=None, self_cond=None):
     h = attention(sd, "middle_block.1", h, emb, G)
     h = unet_res_block(sd, "middle_block.2", h, emb, G)
     n_out = (depth - 1) * (nrb + 1)
+    y_ver = []
     for i in range(n_out, 0, -1):                                                      # unet2.py:258-264
         h = torch.cat([h, xs.pop()], dim=1)
+        dpt, j = i // (nrb + 1), i % (nrb + 1) - 1                                     # unet2.py:261-262
+        if dpt > 0 and j == 0 and f"outc_ver.{dpt - 1}.conv.conv.weight" in sd:
+            y_ver.append(conv2d(sd, f"outc_ver.{dpt - 1}.conv.conv", h))
         pre = f"out_blocks.{i - 1}"
         h = unet_res_block(sd, pre + ".0", h, emb, G)
         h = attention(sd, pre + ".1", h, emb, G)
         if pre + ".2.up_op.weight" in sd:
             level = (i - 1) // (nrb + 1) + 1
             h = basic_up(sd, pre + ".2.up_op", h, strides[level])
-    return conv2d(sd, "outc.conv.conv", h)                                             # unet2.py:267
+    y = conv2d(sd, "outc.conv.conv", h)                                                # unet2.py:267
+    return (y, y_ver[::-1]) if with_ver else y
 
 
 # ------------------------------------------------------------------------------------------------

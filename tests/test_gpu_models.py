@@ -522,3 +522,22 @@ def test_fused_groupnorm_epilogue_matches_reference_fixture():
     y0, _ = m0(x, t, c)
     assert m0.plan_info()["launches"] == 89
     assert_close(y.cpu(), y0.cpu(), rtol=1e-4, atol=1e-5, what="fused vs separate GroupNorm")
+
+
+def test_reference_test_model_builds_and_matches():
+    """/root/reference/tests/models/test_unet.py:13-35 — the reference's own test model (it asserts nothing; the fixture
+    pins it): in/out 3 channels, hid [32,64,128,256] (1/2/4/8 channels per GroupNorm group), kernel_sizes [1,3,3,3],
+    'linear' attention at every level, default 64-wide time embedding (16-wide sinusoid), deep_supervision=True (default),
+    floating-point timesteps.  Channel counts below 64 run on the exact-fp32 CUDA-core convolution."""
+    from medfusion_b200.models import UNet, LabelEmbedder
+    from medfusion_b200.synthetic import fill_
+    g = load_golden("unet_reftest.pt")
+    m = fill_(UNet(cond_embedder=LabelEmbedder, **{k: (dict(v) if isinstance(v, dict) else v) for k, v in g["cfg"].items()}))
+    m = m.to(DEV)
+    assert [k for k, _ in g["keys"]] == list(m.state_dict().keys())
+    y, y_ver = m(g["x"].to(DEV), g["t"].to(DEV), g["cond"].to(DEV))
+    assert_close(y.cpu(), g["y"], what="reference test model: y")
+    assert len(y_ver) == 2
+    for k, (a, b) in enumerate(zip(y_ver, g["y_ver"])):
+        assert_close(a.cpu(), b, what=f"reference test model: y_ver[{k}]")
+    assert m.plan_info()["simt_convs"] > 0 and m.plan_info()["tc_convs"] > 0
