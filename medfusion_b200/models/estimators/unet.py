@@ -175,8 +175,8 @@ class UNet(EngineModule):
             lo, hi = int(condition.min()), int(condition.max())
             if lo < 0 or hi >= self.cond_spec.num_classes:
                 raise IndexError(f"condition values must be in [0, {self.cond_spec.num_classes}), got [{lo}, {hi}]")
-        if t is not None and torch.is_tensor(t) and t.numel() > 0 and int(t.min()) < 0:
-            raise IndexError("timesteps must be >= 0")
+        if t is not None and torch.is_tensor(t) and not torch.is_floating_point(t) and t.numel() > 0 and int(t.min()) < 0:
+            raise IndexError("timesteps must be >= 0")     # (fp32 timesteps only feed the sinusoid: any value is fine)
 
     def supports_fused_step(self):
         """Mirror of the C-side requirements of mf_unet_forward_step (narrow 1x1 head with the scheduler update in its
