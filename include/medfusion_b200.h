@@ -69,6 +69,10 @@ int mf_set_fold_upsample(int enable);
 /* Cin < 64 stem convolutions (UNet in_conv, VAE inc_dec): 1 = tcgen05 path through a zero-padded 64-channel copy of the
  * NCHW input (default), 0 = exact-fp32 CUDA-core kernel. */
 int mf_set_stem_on_tc(int enable);
+/* Attention core (compute_attention, attention_blocks.py:35-43): 1 (default) = tcgen05 kernel (S = QK^T and PV as fp16x3
+ * tensor-core products, accumulators in TMEM, fp32 softmax in registers) for N in {64,128,192,256} tokens and head
+ * dim in {64,128}; 0 = the CUDA-core online-softmax kernel for every shape. */
+int mf_set_attn_tc(int enable);
 /* Res-block halves (conv -> GroupNorm -> Swish -> + residual -> + embedding, conv_blocks.py:184-192,236-240,362) whose
  * output tile spans whole samples (H*W <= 128 per CTA, or H*W == 256 per CTA pair with the statistics exchanged through
  * distributed shared memory): 1 = normalisation applied in the convolution's epilogue (no raw fp32 tensor, no GroupNorm

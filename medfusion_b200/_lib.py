@@ -74,6 +74,7 @@ SIGNATURES = {
     "mf_set_gn_variant": (c_int, [c_int]),
     "mf_set_fold_head": (c_int, [c_int]),
     "mf_set_fuse_gn": (c_int, [c_int]),
+    "mf_set_attn_tc": (c_int, [c_int]),
     "mf_set_debias_eps": (c_int, [c_float]),
     "mf_unet_create": (c_int, [POINTER(UNetConfig), POINTER(_P)]),
     "mf_unet_destroy": (None, [_P]),
@@ -162,6 +163,8 @@ def load():
         lib.mf_set_pdl(int(os.environ["MF_PDL"]))
     if os.environ.get("MF_STREAM_K"):
         lib.mf_set_stream_k(int(os.environ["MF_STREAM_K"]))
+    if os.environ.get("MF_ATTN_TC"):
+        lib.mf_set_attn_tc(int(os.environ["MF_ATTN_TC"]))
     if os.environ.get("MF_FUSE_GN"):
         lib.mf_set_fuse_gn(int(os.environ["MF_FUSE_GN"]))
     if os.environ.get("MF_FOLD_HEAD"):

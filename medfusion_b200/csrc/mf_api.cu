@@ -601,6 +601,10 @@ int mf_set_pdl(int enable) {
   mf::g_pdl = enable ? 1 : 0;
   return 0;
 }
+int mf_set_attn_tc(int enable) {
+  mf::g_attn_tc = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_fuse_gn(int enable) {
   mf::g_fuse_gn = enable ? 1 : 0;
   return 0;

@@ -17,6 +17,7 @@ int geglu_split(const float* in, __half* out, long long out_plane, long long tok
 // out: split [B*N][heads*d]
 int attention_core(const float* q, const float* k, const float* v, int row_stride, __half* out, long long out_plane,
                    int B, int N, int heads, int d, cudaStream_t s);
+extern int g_attn_tc;   // 1 (default): tcgen05 attention core for N in {64,128,192,256}, d in {64,128}; 0: CUDA-core kernel
 // out = in + bias[n][c] (one-token cross attention collapses to this): split -> split
 int add_channel_bias_split(const __half* in, long long in_plane, const float* bias, int bias_stride, __half* out,
                            long long out_plane, int N, int HW, int C, cudaStream_t s);

@@ -207,8 +207,10 @@ def test_scheduler_cfg_and_ddim_against_oracle():
 
 
 # the last three shapes have enough (batch, head, query-block) work to take the many-queries-per-warp variants
+# (N in {64,128,192,256}, d in {64,128}) take the tcgen05 kernel, everything else the CUDA-core one
 @pytest.mark.parametrize("B,N,heads,d", [(2, 64, 8, 32), (1, 256, 8, 128), (3, 100, 4, 64), (32, 256, 8, 128),
-                                         (16, 100, 8, 64), (24, 70, 8, 32)])
+                                         (16, 100, 8, 64), (24, 70, 8, 32), (3, 64, 8, 64), (2, 64, 8, 128),
+                                         (2, 128, 4, 64), (1, 192, 2, 128), (5, 256, 8, 64)])
 def test_attention_core_matches_oracle(B, N, heads, d):
     import ctypes
     import medfusion_oracle as O
