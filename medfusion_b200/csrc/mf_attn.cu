@@ -227,7 +227,7 @@ static int attention_launch(const float* q, const float* k, const float* v, int 
 //   stage 3  8 warps = 4 TMEM lane quarters x 2 key halves: tcgen05.ld, row max / row sum exchanged between the two
 //            halves through shared memory, p = exp(s - max) / sum -> hi/lo tiles (A operand of the second product)
 //   stage 4  v -> V^T hi/lo tiles (keys are the K dimension), in chunks of 128 keys; O MMAs (N = d) -> TMEM columns
-//            [256, 256 + d); each 128-key chunk is drained and added in fp32 registers (short TMEM accumulation chains)
+//            [N, N + d); each 128-key chunk is drained and added in fp32 registers (short TMEM accumulation chains)
 //   stage 5  O -> hi/lo split planes [token][heads*d]
 // Shared memory: stage 1 needs (d/64) * 2 * (16 KB + N * 128 B), stage 3/4 N/64 * 32 KB + 64 KB: 192 KB at N = 256, d = 128.
 // =================================================================================================
@@ -241,7 +241,7 @@ __device__ __forceinline__ uint32_t at_sw128(int row, int k) {   // byte offset 
 }
 
 template <int D>
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kAtThreads)
 attention_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int row_stride,
                     __half* __restrict__ out, long long out_plane, int N, int heads, float scale) {
   constexpr int KB = D / 64;                 // K blocks of the first product
@@ -274,38 +274,67 @@ attention_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, co
     mbar_init(mma_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  const uint32_t tmem_cols = (N + D <= 256) ? 256u : 512u;   // S: N columns, O: D columns behind it
+  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
 
   // ---- stage 1: q (this block's 128 rows, zero beyond N) and k (all N rows), scaled, split, swizzled
-  for (int e = threadIdx.x; e < kAtQ * (D / 4); e += kAtThreads) {
-    const int r = e / (D / 4), d4 = (e % (D / 4)) * 4;
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < N) val = *reinterpret_cast<const float4*>(q + (tok0 + q0 + r) * row_stride + h * D + d4);
-    uint32_t hi[2], lo[2];
-    split16x2(val.x * scale, val.y * scale, hi[0], lo[0]);
-    split16x2(val.z * scale, val.w * scale, hi[1], lo[1]);
-    const int kb = d4 / 64, kk = d4 % 64;
-    const uint32_t off = at_sw128(r, kk);
-    *reinterpret_cast<uint2*>(q_t + (0 * KB + kb) * 16384 + off) = make_uint2(hi[0], hi[1]);
-    *reinterpret_cast<uint2*>(q_t + (1 * KB + kb) * 16384 + off) = make_uint2(lo[0], lo[1]);
-  }
-  for (int e = threadIdx.x; e < N * (D / 4); e += kAtThreads) {
-    const int r = e / (D / 4), d4 = (e % (D / 4)) * 4;
-    const float4 val = *reinterpret_cast<const float4*>(k + (tok0 + r) * row_stride + h * D + d4);
-    uint32_t hi[2], lo[2];
-    split16x2(val.x * scale, val.y * scale, hi[0], lo[0]);
-    split16x2(val.z * scale, val.w * scale, hi[1], lo[1]);
-    const int kb = d4 / 64, kk = d4 % 64;
-    const uint32_t off = at_sw128(r, kk);
-    *reinterpret_cast<uint2*>(k_t + static_cast<size_t>(0 * KB + kb) * N * 128 + off) = make_uint2(hi[0], hi[1]);
-    *reinterpret_cast<uint2*>(k_t + static_cast<size_t>(1 * KB + kb) * N * 128 + off) = make_uint2(lo[0], lo[1]);
+  // 4 independent 16-byte loads in flight per thread (8 warps per SM cannot hide the latency of one load per iteration)
+  {
+    constexpr int ITEMS_Q = kAtQ * (D / 4);
+    for (int e0 = threadIdx.x; e0 < ITEMS_Q; e0 += 4 * kAtThreads) {
+      float4 val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kAtThreads;
+        const int r = e / (D / 4), d4 = (e % (D / 4)) * 4;
+        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < ITEMS_Q && q0 + r < N) val[u] = *reinterpret_cast<const float4*>(q + (tok0 + q0 + r) * row_stride + h * D + d4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kAtThreads;
+        if (e >= ITEMS_Q) break;
+        const int r = e / (D / 4), d4 = (e % (D / 4)) * 4;
+        uint32_t hi[2], lo[2];
+        split16x2(val[u].x * scale, val[u].y * scale, hi[0], lo[0]);
+        split16x2(val[u].z * scale, val[u].w * scale, hi[1], lo[1]);
+        const int kb = d4 / 64, kk = d4 % 64;
+        const uint32_t off = at_sw128(r, kk);
+        *reinterpret_cast<uint2*>(q_t + (0 * KB + kb) * 16384 + off) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(q_t + (1 * KB + kb) * 16384 + off) = make_uint2(lo[0], lo[1]);
+      }
+    }
+    const int items_k = N * (D / 4);
+    for (int e0 = threadIdx.x; e0 < items_k; e0 += 4 * kAtThreads) {
+      float4 val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kAtThreads;
+        const int r = e / (D / 4), d4 = (e % (D / 4)) * 4;
+        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < items_k) val[u] = *reinterpret_cast<const float4*>(k + (tok0 + r) * row_stride + h * D + d4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kAtThreads;
+        if (e >= items_k) break;
+        const int r = e / (D / 4), d4 = (e % (D / 4)) * 4;
+        uint32_t hi[2], lo[2];
+        split16x2(val[u].x * scale, val[u].y * scale, hi[0], lo[0]);
+        split16x2(val[u].z * scale, val[u].w * scale, hi[1], lo[1]);
+        const int kb = d4 / 64, kk = d4 % 64;
+        const uint32_t off = at_sw128(r, kk);
+        *reinterpret_cast<uint2*>(k_t + static_cast<size_t>(0 * KB + kb) * N * 128 + off) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(k_t + static_cast<size_t>(1 * KB + kb) * N * 128 + off) = make_uint2(lo[0], lo[1]);
+      }
+    }
   }
   fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = tmem_base + N;
 
   // ---- stage 2: S = Q K^T
   if (threadIdx.x == 0) {
@@ -403,20 +432,21 @@ attention_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   for (int key0 = 0; key0 < N; key0 += 128) {
     const int ckeys = min(128, N - key0);
     const int cb = ckeys / 64;                  // key blocks in this chunk
-    // V^T tiles: element (n = output column dd, k = key j) of block jb at v_t[plane][jb][dd*128 + swizzle(j)]
-    for (int e = threadIdx.x; e < ckeys * (D / 4); e += kAtThreads) {
-      const int j = e / (D / 4), d4 = (e % (D / 4)) * 4;
-      const float4 val = *reinterpret_cast<const float4*>(v + (tok0 + key0 + j) * row_stride + h * D + d4);
-      const float vals[4] = {val.x, val.y, val.z, val.w};
-      const int jb = j / 64, jk = j % 64;
+    // V^T tiles: element (n = output column dd, k = key j) of block jb at v_t[plane][jb][dd*128 + swizzle(j)].  An item
+    // = (group of 8 keys, one output column): 8 loads that are coalesced ACROSS the warp (lanes = consecutive columns of
+    // one key row) fill one 16-byte chunk per plane; rows 128 B apart + the chunk XOR make the stores conflict-free.
+    for (int e = threadIdx.x; e < (ckeys / 8) * D; e += kAtThreads) {
+      const int dd = e % D, g8 = e / D;
+      float vals[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        __half hh, ll;
-        split16(vals[u], hh, ll);
-        const uint32_t off = at_sw128(d4 + u, jk);
-        *reinterpret_cast<__half*>(v_t + static_cast<size_t>(0 * 2 + jb) * D * 128 + off) = hh;
-        *reinterpret_cast<__half*>(v_t + static_cast<size_t>(1 * 2 + jb) * D * 128 + off) = ll;
-      }
+      for (int u = 0; u < 8; ++u) vals[u] = v[(tok0 + key0 + g8 * 8 + u) * row_stride + h * D + dd];
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split16x2(vals[2 * u], vals[2 * u + 1], hi[u], lo[u]);
+      const int jb = (g8 * 8) / 64, jk = (g8 * 8) % 64;
+      const uint32_t off = at_sw128(dd, jk);
+      *reinterpret_cast<uint4*>(v_t + static_cast<size_t>(0 * 2 + jb) * D * 128 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(v_t + static_cast<size_t>(1 * 2 + jb) * D * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -471,7 +501,7 @@ attention_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 int g_attn_tc = 1;   // 1: tcgen05 attention core where the shape allows it (N in {64..256} step 64, d in {64, 128})
