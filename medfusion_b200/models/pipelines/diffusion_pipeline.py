@@ -217,8 +217,12 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         if check_sat:
             from ... import saturation_count
             saturation_count(reset=True, device=x_t.device)
-        out = self._denoise(x_t, steps, condition, use_ddim, custom_noise, graph_ok, as_uint8, cold, guidance_scale,
-                            un_cond, kwargs)
+        torch.cuda.nvtx.range_push("medfusion_b200.denoise")          # NVTX ranges for nsys / ncu timelines
+        try:
+            out = self._denoise(x_t, steps, condition, use_ddim, custom_noise, graph_ok, as_uint8, cold, guidance_scale,
+                                un_cond, kwargs)
+        finally:
+            torch.cuda.nvtx.range_pop()
         if check_sat:
             n_sat = saturation_count(reset=True, device=x_t.device)
             if n_sat:
@@ -284,6 +288,7 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
                 return self._denoise(x_t, steps, condition, use_ddim, custom_noise, False, as_uint8, cold,
                                      guidance_scale, un_cond, kwargs)
             g.x.copy_(x_t)
+            torch.cuda.nvtx.range_push(f"medfusion_b200.timesteps[{steps}] (CUDA graph replays)")
             for i in range(n_main):
                 g.t.copy_(ts[i].expand(B))
                 if use_ddim:
@@ -295,6 +300,7 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
                 g2.t.copy_(ts[steps - 1].expand(B))
                 g2.replay()
                 x_t = g2.x
+            torch.cuda.nvtx.range_pop()
             return self._decode(x_t.clone(), as_uint8)
         for i in range(steps):
             t = ts[i]
@@ -336,6 +342,13 @@ class DiffusionPipeline(CheckpointMixin, nn.Module):
         return self._decode(x_t, as_uint8)
 
     def _decode(self, x_t, as_uint8=False):
+        torch.cuda.nvtx.range_push("medfusion_b200.decode")
+        try:
+            return self._decode_impl(x_t, as_uint8)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _decode_impl(self, x_t, as_uint8=False):
         if as_uint8:
             if self.latent_embedder is None or not hasattr(self.latent_embedder, "decode_uint8"):
                 raise RuntimeError("sample_uint8 needs a latent embedder with decode_uint8 (medfusion_b200 VAE)")

@@ -250,3 +250,32 @@ def test_layernorm_and_geglu_match_oracle():
     dz = z.to(DEV)
     _lib.check(lib.mf_op_geglu(dz.data_ptr(), zo.data_ptr(), zo[0].numel(), T, C, st), "geglu")
     assert_close((zo[0].float() + zo[1].float()).cpu(), refg, what="geglu")
+
+
+@pytest.mark.parametrize("drain", [1, 3])
+@pytest.mark.parametrize("shape", [(2, 32, 32, 256, 256, 3), (2, 8, 8, 1024, 1024, 3), (1, 16, 16, 512, 512, 1)])
+def test_conv_tc_heavy_tailed_operands_keep_fp32_parity(shape, drain):
+    """the accumulator de-bias was calibrated on Gaussian / Swish-like operands.  Trained networks have
+    heavy-tailed weights and activation outliers: Student-t (3 degrees of freedom) weights, Swish-like activations with 1 %
+    outliers of 30x the scale, a non-zero mean — against the fp64 convolution at the plain tolerance, at the default drain
+    interval (3) and at the most exact one (1)."""
+    from medfusion_b200 import ops
+    N, H, W, Cin, Cout, k = shape
+    g = torch.Generator().manual_seed(Cin + 7 * k)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    x = x * torch.sigmoid(x) + 0.3
+    out_mask = torch.rand(N, Cin, H, W, generator=g) < 0.01
+    x = torch.where(out_mask, 30.0 * torch.randn(N, Cin, H, W, generator=g), x)
+    chi = torch.randn(3, Cout, Cin, k, k, generator=g).pow(2).sum(0) / 3
+    w = torch.randn(Cout, Cin, k, k, generator=g) / chi.sqrt() / (Cin * k * k) ** 0.5     # t_3 / sqrt(fan_in)
+    b = 0.1 * torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).float()
+    xs = ops.pack_split(x.to(DEV))
+    wp = ops.prep_weight_tc(w.to(DEV))
+    out, _ = ops.conv_tc(xs, wp, b.to(DEV), k, drain_interval=drain)
+    got = ops.unpack_nchw(out).cpu()
+    n, mx, rmax = violations(got, ref)
+    d = (got.double() - ref.double()).abs()
+    worst = float((d / (ATOL + RTOL * ref.double().abs())).max())
+    print(f"heavy-tailed conv {shape} drain {drain}: worst |err|/tol = {worst:.3f} (max abs err {mx:.2e}, |ref|max {rmax:.1f})")
+    assert n == 0, f"{n} elements outside tolerance (max err {mx:.3e}, |ref|max {rmax:.3e})"
