@@ -135,6 +135,12 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi takes ~0.5-1 s to attach and holds driver locks while it does: wait for its first line, so that
+            # its start-up does not fall into a short timed region (config 5: ten 25 ms decodes measured 4x slow once)
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.02)
+            self.n_before = len(self.rows)
         except Exception:
             self.proc = None
         return self
@@ -154,7 +160,8 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[getattr(self, "n_before", 0):] or self.rows     # samples taken during the timed region
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))

@@ -60,6 +60,11 @@ int mf_set_block_n(int block_n);
 /* 1 (default): persistent stream-K schedule — one CTA group per SM, (tile, K block) units split evenly, split tiles
  * reduced through a scratch buffer; 0: one output tile per CTA group. */
 int mf_set_stream_k(int enable);
+/* Small-batch fill (default 8): a convolution with fewer output tiles than half the SM pairs (batch 1..16 of
+ * scripts/sample.py) lets several CTA pairs share the K range of one tile, each keeping at least `min_k_blocks` 64-channel
+ * K blocks; their partial sums reach the tile's owner through the stream-K scratch.  0 = off (one pair per tile at most).
+ * Takes effect at the next plan build. */
+int mf_set_split_fill(int min_k_blocks);
 /* Relative correction applied to every drained TMEM partial sum, per K block of the drain interval, compensating the
  * round-toward-zero bias of the tcgen05 accumulator (0 disables, negative = built-in calibrated table, the default). */
 int mf_set_debias_eps(float eps_per_kblock);

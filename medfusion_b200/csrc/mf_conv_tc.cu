@@ -15,6 +15,7 @@ int g_default_block_n = 0;    // 0 = auto
 // canonical step 8.85 ms fused vs 8.72 ms separate, 66.7 vs 67.9 images/s (same box, profiles/r02_gn_fusion.md).
 int g_fuse_gn = 0;
 int g_stream_k = 1;           // persistent stream-K schedule (0: one tile per CTA group)
+int g_split_fill = 8;         // small-batch fill: layers with fewer tiles than half the SM pairs split K (>= this many K blocks per group); 0 = off
 float g_debias_eps_per_kblock = -1.0f;  // < 0: calibrated table (default); 0: off; > 0: explicit relative correction per K block  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
@@ -326,10 +327,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
 
       if (kb0 > 0) {
         // ---- this group's range started inside the tile: publish the partial sums, the tile's owner finishes it
-        float* prow = my_partial + static_cast<long long>(row) * BLOCK_N + col0;
+        // scratch layout [CPW/4][256 drain threads] float4: writer and reader are the SAME thread index (same row / column
+        // range in every CTA), so consecutive lanes touch consecutive 16 bytes (it was [row][column]: one line per lane)
+        float4* pv = reinterpret_cast<float4*>(my_partial) + te;
 #pragma unroll
         for (int i = 0; i < CPW; i += 4)
-          __stcg(reinterpret_cast<float4*>(prow + i), make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+          __stcg(pv + (i / 4) * 256, make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
         __threadfence();
         named_bar_sync(1, 256);
         if (te == 0) {
@@ -339,12 +342,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       } else {
         if (kb1 < nkb) {
           // ---- owner of a tile that other groups helped with: add their partial sums (they processed them first)
-          long long covered = static_cast<long long>(tile) * nkb + kb1;
+          // helpers are the groups right after this one; all their flags are polled in parallel (one thread each), then
+          // the partial tiles are added in group order (deterministic) with nothing but loads between them
           const long long tile_end = static_cast<long long>(tile + 1) * nkb;
-          for (int g2 = group + 1; covered < tile_end; ++g2) {
-            const long long g2_end = total_units * (g2 + 1) / ngroups;
-            const int other_cta = g2 * CG + static_cast<int>(cta_rank);
-            if (te == 0) {
+          int helpers = 0;
+          for (long long covered = static_cast<long long>(tile) * nkb + kb1; covered < tile_end; ++helpers)
+            covered = min(tile_end, total_units * (group + helpers + 2) / ngroups);
+          for (int h0 = 0; h0 < helpers; h0 += 256) {
+            const int hn = min(256, helpers - h0);
+            if (te < hn) {
+              const int other_cta = (group + 1 + h0 + te) * CG + static_cast<int>(cta_rank);
               const int* flag = p.sk_flags + other_cta;
               int v = 0, spins = 0;
               do {
@@ -353,16 +360,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
               } while (v == 0);
             }
             named_bar_sync(1, 256);
-            const float* orow = p.sk_partials + static_cast<long long>(other_cta) * (kTcBlockM * 256) +
-                                static_cast<long long>(row) * BLOCK_N + col0;
+            for (int h = 0; h < hn; ++h) {
+              const int other_cta = (group + 1 + h0 + h) * CG + static_cast<int>(cta_rank);
+              const float4* ov = reinterpret_cast<const float4*>(p.sk_partials + static_cast<long long>(other_cta) * (kTcBlockM * 256)) + te;
 #pragma unroll
-            for (int i = 0; i < CPW; i += 4) {
-              const float4 o = __ldcg(reinterpret_cast<const float4*>(orow + i));
-              acc[i] += o.x; acc[i + 1] += o.y; acc[i + 2] += o.z; acc[i + 3] += o.w;
+              for (int i = 0; i < CPW; i += 4) {
+                const float4 o = __ldcg(ov + (i / 4) * 256);
+                acc[i] += o.x; acc[i + 1] += o.y; acc[i + 2] += o.z; acc[i + 3] += o.w;
+              }
             }
             named_bar_sync(1, 256);
-            if (te == 0) p.sk_flags[other_cta] = 0;   // re-arm for the next launch (CUDA-graph replay safe)
-            covered = min(tile_end, g2_end);
+            if (te < hn) p.sk_flags[(group + 1 + h0 + te) * CG + static_cast<int>(cta_rank)] = 0;   // re-arm (CUDA-graph replay safe)
           }
         }
         // ---- epilogue: registers -> (+bias, statistics, optional residual / vector) -> swizzled staging tile -> TMA store
@@ -883,18 +891,6 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   if (cg != 1 && cg != 2) cg = (m_tiles >= 2) ? 2 : 1;  // auto
   if (p.gn_mode == 2) cg = 2;                           // a sample = the two tiles of one CTA pair
   plan->cta_group = cg;
-  int bn = d.block_n > 0 ? d.block_n : g_default_block_n;
-  if (bn != 64 && bn != 128 && bn != 256) bn = 256;     // auto: widest tile the channel count allows
-  if (p.gn_mode != 0) bn = 256;
-  while (d.Cout % bn) bn /= 2;
-  MF_REQUIRE(p.gn_mode == 0 || bn % p.gn_cpg == 0, "fused GroupNorm: a tile must hold whole groups");
-  MF_REQUIRE(p.gn_mode != 2 || m_tiles % 2 == 0, "fused GroupNorm (pair mode): even tile count");
-  plan->block_n = bn;
-  // a CTA pair owns two consecutive M tiles; an odd tile count gets a padding tile (all loads out of range -> zeros,
-  // all stores masked)
-  p.m_groups = (m_tiles + cg - 1) / cg;
-  p.n_tiles = d.Cout / bn;
-  p.num_tiles = p.m_groups * p.n_tiles * (d.up2 ? 4 : 1);
   const StreamKScratch* scp = d.scratch;
   if (scp == nullptr) {
     int rcs = get_streamk_scratch(&scp);
@@ -903,14 +899,63 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   const StreamKScratch& sc = *scp;
   p.sk_partials = sc.partials;
   p.sk_flags = sc.flags;
+  // a CTA pair owns two consecutive M tiles; an odd tile count gets a padding tile (all loads out of range -> zeros,
+  // all stores masked)
+  p.m_groups = (m_tiles + cg - 1) / cg;
+  const int phases = d.up2 ? 4 : 1;
+  const int max_groups = std::max(1, sc.max_ctas / cg);
+  const long long nkb = static_cast<long long>(p.ntaps) * ((d.C0 + d.C1) / kTcBlockK);
   // persistent grid: one CTA group per SM (pair); stream-K splits the (tile, K block) units evenly over the groups.
   // With stream-K off every tile gets its own group (classic one-tile-per-CTA launch).
-  int groups = p.num_tiles;
-  if (g_stream_k) groups = std::min(p.num_tiles, sc.max_ctas / cg);
-  MF_REQUIRE(groups * cg <= sc.max_ctas || !g_stream_k, "stream-K grid exceeds the scratch allocation");
-  if (!g_stream_k && groups * cg > sc.max_ctas) {
-    // scratch is indexed by blockIdx.x; without stream-K no partials are ever written, any grid size is fine
+  // Small-batch fill: a layer with fewer tiles than HALF the SM pairs (scripts/sample.py runs B = 4..16: the 8x8 level has
+  // 4-16 tiles of 256 x 256 for 74 pairs) would leave most of the GPU idle while a few SMs stream the whole weight tensor.
+  // Two levers, chosen by a small cost model (microseconds; constants from profiles/r02_small_batch.md): narrower tiles
+  // (more of them, cheaper partial tiles, but a lower MMA rate: shared-memory-bound below N = 256) and sharing the K
+  // range of a tile between several groups (each keeps >= min_kb K blocks; the owner adds the helpers' partial tiles,
+  // which costs time per helper).  NOT done when the tiles fill at least half the pairs (B = 64): under the 1000 W cap the
+  // idle SMs' power budget holds the busy ones' clock (profiles/r01_conv_tc_feed_probe.md).
+  auto groups_for = [&](int bn_c, int min_kb) {
+    const long long tiles = static_cast<long long>(p.m_groups) * (d.Cout / bn_c) * phases;
+    long long g = std::min<long long>(tiles, max_groups);
+    if (min_kb > 0 && 2 * tiles <= max_groups)
+      g = std::min<long long>(max_groups, std::max<long long>(tiles, tiles * nkb / min_kb));
+    return static_cast<int>(g);
+  };
+  auto cost_us = [&](int bn_c, int groups_c) {
+    const long long tiles = static_cast<long long>(p.m_groups) * (d.Cout / bn_c) * phases;
+    const double t_kb = bn_c == 256 ? 1.32 : (bn_c == 128 ? 0.94 : 0.72);       // one 64-channel K block of a 256 x bn tile
+    const double per_group = std::ceil(static_cast<double>(tiles * nkb) / groups_c);
+    const double helpers = std::ceil(static_cast<double>(groups_c) / static_cast<double>(tiles)) - 1.0;
+    return per_group * t_kb + helpers * (0.5 + 1.5 * bn_c / 256.0) + (helpers > 0 ? 2.0 : 0.0);
+  };
+  int bn = d.block_n > 0 ? d.block_n : g_default_block_n;
+  const bool bn_auto = (bn != 64 && bn != 128 && bn != 256);
+  if (bn_auto) bn = 256;                                // auto: widest tile the channel count allows ...
+  if (p.gn_mode != 0) bn = 256;
+  while (d.Cout % bn) bn /= 2;
+  int groups = static_cast<int>(static_cast<long long>(p.m_groups) * (d.Cout / bn) * phases);
+  if (g_stream_k) {
+    groups = groups_for(bn, 0);
+    if (g_split_fill > 0 && p.gn_mode == 0) {
+      double best = cost_us(bn, groups);
+      const int bn_top = bn;
+      for (int bn_c = bn_top; bn_c >= 64; bn_c /= 2) {  // ... unless the layer cannot fill the GPU with it
+        if (d.Cout % bn_c || (!bn_auto && bn_c != bn_top)) continue;
+        if (2LL * p.m_groups * (d.Cout / bn_top) * phases > max_groups) break;   // enough tiles: keep the default plan
+        for (int min_kb : {g_split_fill * 4, g_split_fill * 2, g_split_fill}) {
+          const int g_c = groups_for(bn_c, min_kb);
+          const double c = cost_us(bn_c, g_c);
+          if (c < best * 0.97) { best = c; bn = bn_c; groups = g_c; }
+        }
+      }
+    }
   }
+  MF_REQUIRE(p.gn_mode == 0 || bn % p.gn_cpg == 0, "fused GroupNorm: a tile must hold whole groups");
+  MF_REQUIRE(p.gn_mode != 2 || m_tiles % 2 == 0, "fused GroupNorm (pair mode): even tile count");
+  plan->block_n = bn;
+  p.n_tiles = d.Cout / bn;
+  p.num_tiles = p.m_groups * p.n_tiles * phases;
+  MF_REQUIRE(groups * cg <= sc.max_ctas || !g_stream_k, "stream-K grid exceeds the scratch allocation");
   plan->grid = dim3(groups * cg, 1, 1);
 
   int rc = 0;

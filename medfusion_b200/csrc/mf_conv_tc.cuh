@@ -130,6 +130,7 @@ extern int g_default_drain_interval;
 extern int g_default_cta_group;
 extern int g_default_block_n;
 extern int g_stream_k;
+extern int g_split_fill;
 extern int g_pdl;   // defined in mf_kernels.cu
 extern float g_debias_eps_per_kblock;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);

@@ -558,9 +558,36 @@ __device__ __forceinline__ void ld_raw8(const GnApplyDesc& d, long long off, flo
   }
 }
 
-template <int HC>   // HC: compile-time bound on the folded head's outputs (0 = no head, 4, 8)
-__global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d) {
+// 8 values of the residual at `off` (split planes or raw fp32)
+__device__ __forceinline__ void ld_res8(const GnApplyDesc& d, long long off, float (&r)[8]) {
+  if (d.res_kind == kResSplit) {
+    const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
+    const uint4 uh = *reinterpret_cast<const uint4*>(rh);
+    const uint4 ul = *reinterpret_cast<const uint4*>(rh + d.res_plane);
+    const __half2* h = reinterpret_cast<const __half2*>(&uh);
+    const __half2* l = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(h[j]), b = __half22float2(l[j]);
+      r[2 * j] = a.x + b.x; r[2 * j + 1] = a.y + b.y;
+    }
+  } else {
+    const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
+    const float4 a = rp[0], b = rp[1];
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  }
+}
+
+// HC: compile-time bound on the folded head's outputs (0 = no head, 4, 8); RES: a residual is added.
+// U pixels are in flight per thread and iteration (all their loads are issued before the first use): 4 without a residual,
+// 2 with one — 128 bytes of loads per thread either way.  Round 2 ncu (profiles/r02_ncu_unet_step.md): the one-pixel loop ran at
+// 64 registers = 4 blocks per SM with 32-64 bytes in flight per thread and a grid sized for 8 blocks per SM (2.05 waves):
+// 38-57 % of the HBM peak; the folded-head instantiation (110 registers, 2 blocks per SM) at 26 %.
+template <int HC, bool RES>
+__global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDesc d) {
+  constexpr int U = RES ? 2 : 4;
   __shared__ float s_mean[128], s_rstd[128];
+  __shared__ __align__(16) float s_hw[HC > 0 ? HC * 256 : 4];   // folded head weights [o][c] (C <= 256)
   pdl_launch_dependents();
   pdl_wait();
   const int n = blockIdx.y;
@@ -590,12 +617,15 @@ __global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d
         s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(d.eps)));
       }
     }
+    if (HC > 0) {
+      for (int i = threadIdx.x; i < d.head_cout * d.C; i += 256) s_hw[(i / d.C) * 256 + i % d.C] = __ldg(d.head_w + i);
+    }
   }
   __syncthreads();
   // A thread keeps ONE channel octet for its whole life (256 % (C/8) == 0 is checked by the host): the affine
   // coefficients a = rstd*gamma, b = beta (+ embedding) stay in registers and the loop body is pure streaming.
   const int c8n = d.C / 8;
-  const int ppb = 256 / c8n;                                // pixels per block iteration
+  const int ppb = 256 / c8n;                                // pixels per block and sub-iteration
   const int c = (threadIdx.x % c8n) * 8;
   const int psub = threadIdx.x / c8n;
   const int g = c / cpg;
@@ -616,76 +646,101 @@ __global__ void __launch_bounds__(256) gn_apply_fused_kernel(const GnApplyDesc d
     }
   }
   const long long base = static_cast<long long>(n) * d.HW * d.C + c;
-  // folded head: this thread's 8 weights of every head output stay in registers
-  float hw[HC > 0 ? HC : 1][8];
-  if (HC > 0) {
+  const int step = static_cast<int>(gridDim.x) * ppb;
+  // block-uniform trip count (the head reduction shuffles across the C/8 lanes of a pixel)
+  for (int pix0 = blockIdx.x * ppb; pix0 < d.HW; pix0 += U * step) {
+    float x[U][8], r[RES ? U : 1][8];
+    bool live[U];
+    long long off[U];
 #pragma unroll
-    for (int o = 0; o < HC; ++o)
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * step + psub;
+      live[u] = pix < d.HW;
+      off[u] = base + static_cast<long long>(live[u] ? pix : 0) * d.C;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) hw[o][j] = (o < d.head_cout) ? __ldg(d.head_w + o * d.C + c + j) : 0.f;
-  }
-  // warp-uniform trip count (the head reduction shuffles across the C/8 lanes of a pixel)
-  for (int pix0 = blockIdx.x * ppb; pix0 < d.HW; pix0 += gridDim.x * ppb) {
-    const int pix = pix0 + psub;
-    const bool live = pix < d.HW;
-    const long long off = base + static_cast<long long>(live ? pix : 0) * d.C;
-    float x[8];
-    ld_raw8(d, off, x);
-    float y[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      y[j] = fmaf(x[j] - mean, ca[j], cb[j]);
-      if (d.act != 0) y[j] = swish_stream(y[j]);
+      for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
+      if (live[u]) ld_raw8(d, off[u], x[u]);
     }
-    if (d.res_kind == kResSplit) {
-      const __half* rh = reinterpret_cast<const __half*>(d.res) + off;
-      const uint4 uh = *reinterpret_cast<const uint4*>(rh);
-      const uint4 ul = *reinterpret_cast<const uint4*>(rh + d.res_plane);
-      const __half2* h = reinterpret_cast<const __half2*>(&uh);
-      const __half2* l = reinterpret_cast<const __half2*>(&ul);
+    if (RES) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = __half22float2(h[j]), b = __half22float2(l[j]);
-        y[2 * j] += a.x + b.x; y[2 * j + 1] += a.y + b.y;
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[u][j] = 0.f;
+        if (live[u]) ld_res8(d, off[u], r[u]);
       }
-    } else if (d.res_kind == kResRaw) {
-      const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.res) + off);
-      const float4 a = rp[0], b = rp[1];
-      y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; y[4] += b.x; y[5] += b.y; y[6] += b.z; y[7] += b.w;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] += ce[j];
-    if (HC > 0) {
+    for (int u = 0; u < U; ++u) {
+      float y[8];
 #pragma unroll
-      for (int o = 0; o < HC; ++o) {
-        if (o < d.head_cout) {                      // block-uniform
-          float acc = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        y[j] = fmaf(x[u][j] - mean, ca[j], cb[j]);
+        if (d.act != 0) y[j] = swish_stream(y[j]);
+        if (RES) y[j] += r[u][j];
+        y[j] += ce[j];
+      }
+      if (HC > 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc = fmaf(y[j], hw[o][j], acc);
-          for (int sh = c8n >> 1; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-          if (live && (threadIdx.x % c8n) == 0) {
-            const float v = acc + __ldg(d.head_b + o);
-            if (d.head_out != nullptr) d.head_out[(static_cast<long long>(n) * d.head_cout + o) * d.HW + pix] = v;
-            if (d.head_out_u8 != nullptr) {
-              // scripts/helpers/sample_dataset.py:47-50: clip(-1,1) -> (x+1)/2*255 -> HWC -> astype(uint8) (truncation)
-              const float c01 = fminf(fmaxf(v, -1.f), 1.f);
-              const float v255 = __fmul_rn(__fmul_rn(__fadd_rn(c01, 1.f), 0.5f), 255.f);
-              d.head_out_u8[(static_cast<long long>(n) * d.HW + pix) * d.head_cout + o] = static_cast<unsigned char>(v255);
+        for (int o = 0; o < HC; ++o) {
+          if (o < d.head_cout) {                      // block-uniform
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_hw[o * 256 + c]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_hw[o * 256 + c + 4]);
+            float acc = 0.f;
+            acc = fmaf(y[0], w0.x, acc); acc = fmaf(y[1], w0.y, acc); acc = fmaf(y[2], w0.z, acc); acc = fmaf(y[3], w0.w, acc);
+            acc = fmaf(y[4], w1.x, acc); acc = fmaf(y[5], w1.y, acc); acc = fmaf(y[6], w1.z, acc); acc = fmaf(y[7], w1.w, acc);
+            for (int sh = c8n >> 1; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+            if (live[u] && (threadIdx.x % c8n) == 0) {
+              const int pix = pix0 + u * step + psub;
+              const float v = acc + __ldg(d.head_b + o);
+              if (d.head_out != nullptr) d.head_out[(static_cast<long long>(n) * d.head_cout + o) * d.HW + pix] = v;
+              if (d.head_out_u8 != nullptr) {
+                // scripts/helpers/sample_dataset.py:47-50: clip(-1,1) -> (x+1)/2*255 -> HWC -> astype(uint8) (truncation)
+                const float c01 = fminf(fmaxf(v, -1.f), 1.f);
+                const float v255 = __fmul_rn(__fmul_rn(__fadd_rn(c01, 1.f), 0.5f), 255.f);
+                d.head_out_u8[(static_cast<long long>(n) * d.HW + pix) * d.head_cout + o] = static_cast<unsigned char>(v255);
+              }
             }
           }
         }
       }
-    }
-    if (d.out != nullptr && live) {
-      uint4 oh, ol;
-      uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
-      uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
+      if (d.out != nullptr && live[u]) {
+        uint4 oh, ol;
+        uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
+        uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split16x2(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
-      *reinterpret_cast<uint4*>(d.out + off) = oh;
-      *reinterpret_cast<uint4*>(d.out + d.out_plane + off) = ol;
+        for (int j = 0; j < 4; ++j) split16x2(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
+        *reinterpret_cast<uint4*>(d.out + off[u]) = oh;
+        *reinterpret_cast<uint4*>(d.out + d.out_plane + off[u]) = ol;
+      }
     }
   }
+}
+
+// resident blocks per SM of an instantiation (asked once), and the grid: bps blocks per sample such that N * bps fills
+// whole waves of the 148 x resident block slots as evenly as possible
+template <int HC, bool RES>
+static int gn_fused_launch(const GnApplyDesc& d, cudaLaunchConfig_t& cfg, int max_bps) {
+  static int occ = 0, sms = 0;
+  if (occ == 0) {
+    MF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_fused_kernel<HC, RES>, 256, 0));
+    int dev = 0;
+    MF_CUDA_OK(cudaGetDevice(&dev));
+    MF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (occ < 1) occ = 1;
+  }
+  const long long slots = static_cast<long long>(sms) * occ;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int bps = 1; bps <= max_bps; ++bps) {
+    const long long blocks = static_cast<long long>(d.N) * bps;
+    const long long waves = (blocks + slots - 1) / slots;
+    if (waves > 4 && bps > 1) break;
+    const double eff = static_cast<double>(blocks) / static_cast<double>(waves * slots);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = bps; }   // prefer fewer, longer-lived blocks at equal efficiency
+  }
+  cfg.gridDim = dim3(best, d.N, 1);
+  MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<HC, RES>, d));
+  return 0;
 }
 
 int g_gn_variant = 3;
@@ -703,11 +758,10 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
                "folded head: <= 8 outputs, C/8 a power of two <= 32");
     MF_REQUIRE(d.out != nullptr || d.head_cout > 0, "gn_apply without an output");
     const int ppb = 256 / (d.C / 8);
-    // ~8 resident blocks per SM over the whole launch, at least 2 pixels per thread where the sample is big enough
-    int bps = std::max(1, (148 * 8 + d.N - 1) / d.N);
-    bps = std::min(bps, std::max(1, (d.HW + 2 * ppb - 1) / (2 * ppb)));
+    const bool res = d.res != nullptr && d.res_kind != kResNone;
+    const int upi = (res ? 2 : 4) * ppb;                     // pixels per block iteration
+    const int max_bps = std::max(1, (d.HW + upi - 1) / upi);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(bps, d.N, 1);
     cfg.blockDim = dim3(256, 1, 1);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -715,9 +769,10 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 1 : 0;
-    if (d.head_cout == 0) MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<0>, d));
-    else if (d.head_cout <= 4) MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<4>, d));
-    else MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<8>, d));
+    if (d.head_cout == 0) return res ? gn_fused_launch<0, true>(d, cfg, max_bps) : gn_fused_launch<0, false>(d, cfg, max_bps);
+    MF_REQUIRE(d.C <= 256, "folded head: at most 256 channels");
+    if (d.head_cout <= 4) return res ? gn_fused_launch<4, true>(d, cfg, max_bps) : gn_fused_launch<4, false>(d, cfg, max_bps);
+    return res ? gn_fused_launch<8, true>(d, cfg, max_bps) : gn_fused_launch<8, false>(d, cfg, max_bps);
     return 0;
   }
   MF_REQUIRE(d.head_cout == 0, "the folded head exists in the fused gn_apply variant only");

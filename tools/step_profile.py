@@ -13,6 +13,12 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 dev = "cuda:0"
+if os.environ.get("SPLIT_FILL") is not None:      # small-batch fill knob (mf_set_split_fill): A/B runs
+    from medfusion_b200 import _lib
+    _lib.load().mf_set_split_fill(int(os.environ["SPLIT_FILL"]))
+if os.environ.get("BLOCK_N") is not None:
+    from medfusion_b200 import _lib
+    _lib.load().mf_set_block_n(int(os.environ["BLOCK_N"]))
 B = int(os.environ.get("B", "64"))
 names = {0: "conv_tc", 1: "conv_simt", 2: "groupnorm family", 3: "other (embedding MLP, pack, attention)"}
 LAT = int(os.environ.get("LATENT", "32"))          # 64 + ATTN=1 = BASELINE.json configs[3] (config 4 of SURVEY.md §8d)
