@@ -47,7 +47,8 @@ const char* mf_last_error(void);
 int mf_abi_version(void);
 /* Sticky saturation counter (ABI v3).  Activations travel between kernels as fp16 hi/lo planes; the reference computes
  * in fp32 range.  Every value that had to be clamped to +-65504 (or was not finite) when a kernel wrote split planes is
- * counted on the device.  Synchronises `stream`, returns the count since the last reset on the CURRENT device; a
+ * counted on the device (the streaming GroupNorm-apply kernel counts once per thread that clamped: a lower bound).
+ * Synchronises `stream`, returns the count since the last reset on the CURRENT device; a
  * non-zero count means results from that point on are not the reference's (the Python layer raises). */
 int mf_saturation_count(unsigned long long* out_count, int reset, mf_stream_t stream);
 /* Default TMEM drain interval used by the engines' tensor-core convolutions (see mf_op_conv_tc). */
@@ -65,6 +66,11 @@ int mf_set_stream_k(int enable);
  * K blocks; their partial sums reach the tile's owner through the stream-K scratch.  0 = off (one pair per tile at most).
  * Takes effect at the next plan build. */
 int mf_set_split_fill(int min_k_blocks);
+/* Row-patch mode (default 1): 3x3 stride-1 convolutions whose tile is 128 pixels of one image row and at most 128 output
+ * channels wide (the 128x128 / 256x256 levels of the VAE) stage the 130-pixel patch of an input row once for its three taps
+ * (shifted shared-memory descriptors) instead of once per tap: a third of the L2 -> SM activation traffic.  0 = one
+ * activation tile per tap everywhere.  Takes effect at the next plan build. */
+int mf_set_row_patch(int enable);
 /* Relative correction applied to every drained TMEM partial sum, per K block of the drain interval, compensating the
  * round-toward-zero bias of the tcgen05 accumulator (0 disables, negative = built-in calibrated table, the default). */
 int mf_set_debias_eps(float eps_per_kblock);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mf_set_block_n": (c_int, [c_int]),
     "mf_set_stream_k": (c_int, [c_int]),
     "mf_set_split_fill": (c_int, [c_int]),
+    "mf_set_row_patch": (c_int, [c_int]),
     "mf_set_pdl": (c_int, [c_int]),
     "mf_set_fold_upsample": (c_int, [c_int]),
     "mf_set_stem_on_tc": (c_int, [c_int]),
@@ -166,6 +167,8 @@ def load():
         lib.mf_set_stream_k(int(os.environ["MF_STREAM_K"]))
     if os.environ.get("MF_SPLIT_FILL"):
         lib.mf_set_split_fill(int(os.environ["MF_SPLIT_FILL"]))
+    if os.environ.get("MF_ROW_PATCH"):
+        lib.mf_set_row_patch(int(os.environ["MF_ROW_PATCH"]))
     if os.environ.get("MF_ATTN_TC"):
         lib.mf_set_attn_tc(int(os.environ["MF_ATTN_TC"]))
     if os.environ.get("MF_FUSE_GN"):

@@ -634,6 +634,10 @@ int mf_set_split_fill(int min_k_blocks) {
   mf::g_split_fill = min_k_blocks;
   return 0;
 }
+int mf_set_row_patch(int enable) {
+  mf::g_row_patch = enable ? 1 : 0;
+  return 0;
+}
 int mf_set_block_n(int block_n) {
   MF_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 0, 64, 128 or 256");
   mf::g_default_block_n = block_n;

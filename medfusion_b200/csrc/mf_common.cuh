@@ -72,6 +72,22 @@ __device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi2, uint3
   hi2 = *reinterpret_cast<const uint32_t*>(&h);
   lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
+// Streaming variant for instruction-bound loops (GroupNorm-apply: 36 thread instructions per element, the per-value
+// compare + branch + warp-aggregated atomic of sat16 was a fifth of them): same clamp, the event is OR-ed into a
+// per-thread flag that the caller reports ONCE with sat16_report (the counter then counts threads that clamped, which is
+// all its users need: zero / non-zero, and a lower bound on the number of values).
+__device__ __forceinline__ void split16x2_flag(float a, float b, uint32_t& hi2, uint32_t& lo2, bool& clamped) {
+  const float ac = fminf(fmaxf(a, -65504.f), 65504.f), bc = fminf(fmaxf(b, -65504.f), 65504.f);
+  clamped = clamped || (ac != a) || (bc != b);      // true for NaN as well
+  const __half2 h = __floats2half2_rn(ac, bc);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(ac - hf.x, bc - hf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void sat16_report(bool clamped) {
+  if (clamped) atomicAdd(&g_mf_saturated, 1u);
+}
 // host side of the counter: defined once per translation unit that launches kernels using split16
 #define MF_DEFINE_SATURATION_READER(fn)                                                                     \
   int fn(unsigned long long* total, int reset, cudaStream_t s) {                                            \
@@ -337,8 +353,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 // "tcgen05 shared memory descriptor" / "instruction descriptor").
 // ------------------------------------------------------------------------------------------------
 // K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups are 1024 B apart.
-__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
+// base_offset: descriptor bits [49,52).  Left 0 everywhere: measured on B200 (tests/test_gpu_kernels.py row-patch shapes), a tile
+// addressed `r` rows into a TMA-written 128B-swizzled patch (start + r * 128 B) is read correctly with base offset 0 — the
+// swizzle XOR is taken from the absolute shared-memory address bits [7,10) — and wrongly with base offset r.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t base_offset = 0) {
+  uint64_t d = static_cast<uint64_t>(base_offset & 7u) << 49;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address  [0,14)
   d |= static_cast<uint64_t>(1) << 16;                      // leading byte offset (unused for SW128 K-major)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B

@@ -15,18 +15,27 @@ int g_default_block_n = 0;    // 0 = auto
 // canonical step 8.85 ms fused vs 8.72 ms separate, 66.7 vs 67.9 images/s (same box, profiles/r02_gn_fusion.md).
 int g_fuse_gn = 0;
 int g_stream_k = 1;           // persistent stream-K schedule (0: one tile per CTA group)
+int g_row_patch = 1;          // 1: row-patch mode (TcCfg ROW3) for the eligible 3x3 layers (tiles of one image row)
 int g_split_fill = 8;         // small-batch fill: layers with fewer tiles than half the SM pairs split K (>= this many K blocks per group); 0 = off
 float g_debias_eps_per_kblock = -1.0f;  // < 0: calibrated table (default); 0: off; > 0: explicit relative correction per K block  // 0 = auto (pairs whenever a conv has >= 2 M tiles)
 
 // =================================================================================================
 // Device side
 // =================================================================================================
-template <int BLOCK_N, int CG>
+// ROW3 ("row patch" mode, 3x3 stride-1 convolutions whose tile is 128 pixels of ONE image row): a pipeline stage holds the
+// (128 + 2)-pixel patch of one input row and one 64-channel slab (hi and lo planes) plus the weight tiles of the THREE taps
+// that read this row; the MMAs of tap dx address the same patch shifted by dx rows of 128 bytes (descriptor start +dx*128 B;
+// the swizzle follows the absolute address, no base offset).  The activation slab is fetched 3 times per tile instead of 9: profiles/r02_row_patch.md (the 128x128 /
+// 256x256 levels of the VAE were bound by the L2 -> SM fabric, ~8-9 TB/s, not by shared memory or the tensor pipe).
+constexpr int kTcPatchRows = kTcBlockM + 2;
+template <int BLOCK_N, int CG, bool ROW3 = false>
 struct TcCfg {
   static constexpr int kABytes = kTcBlockM * 128;        // one 128-row x 128-byte plane tile
+  static constexpr int kAPatchBytes = ((kTcPatchRows * 128 + 1023) / 1024) * 1024;   // 130 rows, padded to the swizzle atom
   static constexpr int kBRows = BLOCK_N / CG;            // weight rows this CTA stages (a CTA pair splits B)
   static constexpr int kBBytes = kBRows * 128;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStageBytes = ROW3 ? (2 * kAPatchBytes + 6 * kBBytes) : (2 * kABytes + 2 * kBBytes);
+  static constexpr int kStageTxBytes = ROW3 ? (2 * kTcPatchRows * 128 + 6 * kBBytes) : kStageBytes;   // bytes TMA delivers per stage
   // epilogue staging: per column half one [128 rows][128 B] tile (32 fp32 channels, or 32 fp16 channels hi | lo) that a
   // single thread hands to the TMA store engine — the global write is one bulk tensor store per 16 KB, not 32
   // row-strided STG.128 per thread (profiles/r02_conv_tc_ncu_32x32_before.md: the old epilogue cost 24 k cycles per tile)
@@ -67,10 +76,10 @@ struct TcCfg {
 // LAST, so nobody waits on work that has not been scheduled.
 // GN: compiled with the fused GroupNorm epilogue (p.gn_mode != 0).  A separate instantiation because that epilogue is large:
 // it runs as a rolled loop over 32-column chunks, while the plain epilogue stays fully unrolled (no register-window moves).
-template <int BLOCK_N, int CG, bool GN>
+template <int BLOCK_N, int CG, bool GN, bool ROW3 = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, CG>;
+  using Cfg = TcCfg<BLOCK_N, CG, ROW3>;
   constexpr int CPW = Cfg::kColsPerWarp;
   constexpr int NB = Cfg::kAccBufs;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -197,7 +206,32 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
             ma = &maps.a[1];
             cc = c - p.C0;
           }
-          if (CG == 2) {
+          if (ROW3) {
+            // tap = input row offset (dy = tap - 1): one 130-pixel patch of that row, the weight tiles of its 3 taps
+            const int yr = tc.h0 + tap - 1, xr = tc.w0 - 1;
+            const int kw0 = (cb * 9 + tap * 3) * kTcBlockK;
+            uint8_t* bt = st + 2 * Cfg::kAPatchBytes;
+            if (CG == 2) {
+              if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageTxBytes);
+              const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+              tma_load_5d_2sm(st, ma, fb, cc, xr, yr, tc.n0, 0);
+              tma_load_5d_2sm(st + Cfg::kAPatchBytes, ma, fb, cc, xr, yr, tc.n0, 1);
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                tma_load_3d_2sm(bt + (2 * dxi) * Cfg::kBBytes, &maps.w, fb, kw0 + dxi * kTcBlockK, brow, 0);
+                tma_load_3d_2sm(bt + (2 * dxi + 1) * Cfg::kBBytes, &maps.w, fb, kw0 + dxi * kTcBlockK, brow, 1);
+              }
+            } else {
+              mbar_expect_tx(&full_bar[s], Cfg::kStageTxBytes);
+              tma_load_5d(st, ma, &full_bar[s], cc, xr, yr, tc.n0, 0);
+              tma_load_5d(st + Cfg::kAPatchBytes, ma, &full_bar[s], cc, xr, yr, tc.n0, 1);
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                tma_load_3d(bt + (2 * dxi) * Cfg::kBBytes, &maps.w, &full_bar[s], kw0 + dxi * kTcBlockK, brow, 0);
+                tma_load_3d(bt + (2 * dxi + 1) * Cfg::kBBytes, &maps.w, &full_bar[s], kw0 + dxi * kTcBlockK, brow, 1);
+              }
+            }
+          } else if (CG == 2) {
             // all bytes of the pair are credited to the LEADER's full barrier
             if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
             const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
@@ -239,6 +273,37 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+            if (ROW3) {
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                // measured on B200: the 128-byte swizzle is a function of the ABSOLUTE shared-memory address bits, so a tile that
+                // starts dx rows into the TMA-written patch needs no descriptor base offset (with base offset = dx the results are wrong)
+                const uint64_t ra_hi = umma_smem_desc_sw128(st + dxi * 128);
+                const uint64_t ra_lo = umma_smem_desc_sw128(st + Cfg::kAPatchBytes + dxi * 128);
+                const uint64_t rb_hi = umma_smem_desc_sw128(st + 2 * Cfg::kAPatchBytes + (2 * dxi) * Cfg::kBBytes);
+                const uint64_t rb_lo = umma_smem_desc_sw128(st + 2 * Cfg::kAPatchBytes + (2 * dxi + 1) * Cfg::kBBytes);
+#pragma unroll
+                for (int k = 0; k < kTcBlockK / 16; ++k) {
+                  const uint64_t koff = static_cast<uint64_t>(k * 2);
+                  if (CG == 2) {
+                    umma_f16_2sm(d_tmem, ra_lo + koff, rb_hi + koff, idesc, first ? 0u : 1u);
+                    umma_f16_2sm(d_tmem, ra_hi + koff, rb_lo + koff, idesc, 1u);
+                  } else {
+                    umma_f16(d_tmem, ra_lo + koff, rb_hi + koff, idesc, first ? 0u : 1u);
+                    umma_f16(d_tmem, ra_hi + koff, rb_lo + koff, idesc, 1u);
+                  }
+                  first = false;
+                }
+#pragma unroll
+                for (int k = 0; k < kTcBlockK / 16; ++k) {
+                  const uint64_t koff = static_cast<uint64_t>(k * 2);
+                  if (CG == 2) umma_f16_2sm(d_tmem, ra_hi + koff, rb_hi + koff, idesc, 1u);
+                  else umma_f16(d_tmem, ra_hi + koff, rb_hi + koff, idesc, 1u);
+                }
+              }
+              if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+              continue;
+            }
             const uint64_t a_hi = umma_smem_desc_sw128(st);
             const uint64_t a_lo = umma_smem_desc_sw128(st + Cfg::kABytes);
             const uint64_t b_hi = umma_smem_desc_sw128(st + 2 * Cfg::kABytes);
@@ -856,12 +921,15 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   // round-to-nearest register sum removes the mean of that bias for free (the add becomes an FMA).
   // Calibrated on B200 against fp64 (profiles/r01_debias_calibration.jsonl): the relative bias of a drained partial is
   // -0.87e-7 / -2.7e-7 / -6.3e-7 for drain = 1 / 2 / 4, the same for Gaussian, all-positive and Swish-like operands.
-  if (g_debias_eps_per_kblock < 0.f) {
-    const long ulps = std::max(1L, std::lround(0.73 * std::pow(static_cast<double>(p.drain_interval), 1.43)));
-    p.partial_scale = 1.0f + static_cast<float>(ulps) * 1.1920929e-7f;
-  } else {
-    p.partial_scale = 1.0f + g_debias_eps_per_kblock * static_cast<float>(p.drain_interval);
-  }
+  auto set_partial_scale = [&](int kblocks_per_partial) {
+    if (g_debias_eps_per_kblock < 0.f) {
+      const long ulps = std::max(1L, std::lround(0.73 * std::pow(static_cast<double>(kblocks_per_partial), 1.43)));
+      p.partial_scale = 1.0f + static_cast<float>(ulps) * 1.1920929e-7f;
+    } else {
+      p.partial_scale = 1.0f + g_debias_eps_per_kblock * static_cast<float>(kblocks_per_partial);
+    }
+  };
+  set_partial_scale(p.drain_interval);
   p.bias = d.bias;
   p.out = d.out; p.out_plane = d.out_plane; p.out_mode = d.out_mode;
   p.stats = d.stats;
@@ -955,6 +1023,17 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   plan->block_n = bn;
   p.n_tiles = d.Cout / bn;
   p.num_tiles = p.m_groups * p.n_tiles * phases;
+  // Row-patch mode: 3x3 stride-1 layers whose tile is 128 pixels of one image row (W % 128 == 0: the VAE's 128x128 and
+  // 256x256 levels) and whose narrow tiles (N <= 128) make the activation re-reads the bottleneck.  A pipeline stage then
+  // covers the three taps of one input row: ntaps = 3 "row taps", one TMEM partial per stage (= 3 K blocks, the default).
+  plan->row3 = 0;
+  if (g_row_patch && d.ksize == 3 && stride == 1 && !d.up2 && p.bh == 1 && p.bw == kTcBlockM && p.bn == 1 && p.gn_mode == 0 &&
+      cg == 2 && (bn == 64 || bn == 128) && p.drain_interval >= 3 && 2LL * p.num_tiles > max_groups && g_stream_k) {
+    plan->row3 = 1;
+    p.ntaps = 3;
+    set_partial_scale(3 * (p.drain_interval / 3));
+    p.drain_interval /= 3;
+  }
   MF_REQUIRE(groups * cg <= sc.max_ctas || !g_stream_k, "stream-K grid exceeds the scratch allocation");
   plan->grid = dim3(groups * cg, 1, 1);
 
@@ -966,11 +1045,12 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
                             ph, pw);
     if (rc) return rc;
   } else {
-    rc = encode_act_map(&plan->maps.a[0], d.src0, d.src0_plane, d.N, d.H, d.W, d.C0, p.bw, p.bh, p.bn);
+    const int abw = plan->row3 ? p.bw + 2 : p.bw;   // row-patch mode: the tile's row plus one halo pixel on each side
+    rc = encode_act_map(&plan->maps.a[0], d.src0, d.src0_plane, d.N, d.H, d.W, d.C0, abw, p.bh, p.bn);
     if (rc) return rc;
     if (d.C1 > 0) {
       MF_REQUIRE((reinterpret_cast<uintptr_t>(d.src1) & 15) == 0, "TMA sources must be 16-byte aligned");
-      rc = encode_act_map(&plan->maps.a[1], d.src1, d.src1_plane, d.N, d.H, d.W, d.C1, p.bw, p.bh, p.bn);
+      rc = encode_act_map(&plan->maps.a[1], d.src1, d.src1_plane, d.N, d.H, d.W, d.C1, abw, p.bh, p.bn);
       if (rc) return rc;
     } else {
       plan->maps.a[1] = plan->maps.a[0];
@@ -989,7 +1069,7 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
     for (int i = 1; i < 4; ++i) plan->maps.o[i] = plan->maps.o[0];
   }
   if (rc) return rc;
-  const long long K = static_cast<long long>(p.ntaps) * (d.C0 + d.C1);
+  const long long K = static_cast<long long>(d.up2 ? 4 : d.ksize * d.ksize) * (d.C0 + d.C1);   // NOT p.ntaps: 3 row taps in row-patch mode
   const long long wrows = static_cast<long long>(d.Cout) * (d.up2 ? 4 : 1);  // up2: four phase matrices stacked
   cuuint64_t wd[3] = {(cuuint64_t)K, (cuuint64_t)wrows, 2};
   cuuint64_t ws[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * wrows * 2};
@@ -998,18 +1078,18 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   return encode_map(&plan->maps.w, d.w_planes, 3, wd, ws, wb, we);
 }
 
-template <int BLOCK_N, int CG, bool GN>
+template <int BLOCK_N, int CG, bool GN, bool ROW3 = false>
 static int launch_t(const ConvTcPlan& plan, cudaStream_t stream, const ConvTcParams& params) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    TcCfg<BLOCK_N, CG>::kSmemBytes));
+    MF_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CG, GN, ROW3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    TcCfg<BLOCK_N, CG, ROW3>::kSmemBytes));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = plan.grid;
   cfg.blockDim = dim3(kTcThreads, 1, 1);
-  cfg.dynamicSmemBytes = TcCfg<BLOCK_N, CG>::kSmemBytes;
+  cfg.dynamicSmemBytes = TcCfg<BLOCK_N, CG, ROW3>::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1020,7 +1100,7 @@ static int launch_t(const ConvTcPlan& plan, cudaStream_t stream, const ConvTcPar
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  MF_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG, GN>, plan.maps, params));
+  MF_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CG, GN, ROW3>, plan.maps, params));
   return 0;
 }
 
@@ -1039,6 +1119,12 @@ int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream, int emb_dedup, c
       case 641: return launch_t<64, 1, true>(plan, stream, p);
       case 642: return launch_t<64, 2, true>(plan, stream, p);
     }
+  }
+  if (plan.row3) {
+    if (plan.block_n == 64 && plan.cta_group == 2) return launch_t<64, 2, false, true>(plan, stream, p);
+    if (plan.block_n == 128 && plan.cta_group == 2) return launch_t<128, 2, false, true>(plan, stream, p);
+    set_error("conv_tc_launch: row-patch plan with an unsupported tile");
+    return 2;
   }
   switch (plan.block_n * 10 + plan.cta_group) {
     case 2561: return launch_t<256, 1, false>(plan, stream, p);

@@ -83,6 +83,7 @@ struct ConvTcPlan {
   ConvTcParams p;
   int block_n;
   int cta_group;  // 1: one CTA per tile; 2: CTA pairs (cluster of 2) sharing the weight tile
+  int row3;       // 1: row-patch mode (one stage = the 130-pixel patch of one input row + the weight tiles of its 3 taps)
   dim3 grid;
 };
 
@@ -131,6 +132,7 @@ extern int g_default_cta_group;
 extern int g_default_block_n;
 extern int g_stream_k;
 extern int g_split_fill;
+extern int g_row_patch;
 extern int g_pdl;   // defined in mf_kernels.cu
 extern float g_debias_eps_per_kblock;
 int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride);

@@ -647,6 +647,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
   }
   const long long base = static_cast<long long>(n) * d.HW * d.C + c;
   const int step = static_cast<int>(gridDim.x) * ppb;
+  bool clamped = false;
   // block-uniform trip count (the head reduction shuffles across the C/8 lanes of a pixel)
   for (int pix0 = blockIdx.x * ppb; pix0 < d.HW; pix0 += U * step) {
     float x[U][8], r[RES ? U : 1][8];
@@ -708,12 +709,13 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
         uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
         uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split16x2(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
+        for (int j = 0; j < 4; ++j) split16x2_flag(y[2 * j], y[2 * j + 1], ph[j], pl[j], clamped);
         *reinterpret_cast<uint4*>(d.out + off[u]) = oh;
         *reinterpret_cast<uint4*>(d.out + d.out_plane + off[u]) = ol;
       }
     }
   }
+  sat16_report(clamped);
 }
 
 // resident blocks per SM of an instantiation (asked once), and the grid: bps blocks per sample such that N * bps fills
