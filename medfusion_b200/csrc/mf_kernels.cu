@@ -28,13 +28,48 @@ __global__ void pack_nchw_to_split_kernel(const float* __restrict__ x, __half* _
   }
 }
 
+// Cpad % 8 == 0: one thread per (pixel, channel octet) — the eight lanes of a pixel write its 128-byte line with one
+// 16-byte store per plane each (the element-per-thread kernel above wrote 2 bytes per thread: 32 us for the 16.8 MB
+// stem input of the canonical UNet at B = 64, profiles/r02_ncu_unet_step.md); only octets below C read anything.
+__global__ void pack_nchw_to_split8_kernel(const float* __restrict__ x, __half* __restrict__ out, long long plane, int N,
+                                           int C, int H, int W, int Cpad, int n_mod) {
+  const int octs = Cpad / 8;
+  const long long HW = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(N) * HW * octs;
+  bool clamped = false;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % octs) * 8;
+    const long long pix = i / octs;
+    const long long hw = pix % HW;
+    int n = static_cast<int>(pix / HW);
+    if (n_mod > 0) n %= n_mod;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? __ldg(x + (static_cast<long long>(n) * C + c0 + j) * HW + hw) : 0.f;
+    uint4 oh, ol;
+    uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
+    uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split16x2_flag(v[2 * j], v[2 * j + 1], ph[j], pl[j], clamped);
+    *reinterpret_cast<uint4*>(out + pix * Cpad + c0) = oh;
+    *reinterpret_cast<uint4*>(out + plane + pix * Cpad + c0) = ol;
+  }
+  sat16_report(clamped);
+}
+
 int pack_nchw_to_split(const float* x, __half* out, long long plane, int N, int C, int H, int W, cudaStream_t s,
                        int Cpad, int n_mod) {
   if (Cpad < C) Cpad = C;
   const long long total = static_cast<long long>(N) * H * W * Cpad;
   if (total == 0) return 0;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W, Cpad, n_mod);
+  if (Cpad % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && plane % 8 == 0) {
+    const int blocks = static_cast<int>(std::min<long long>((total / 8 + 255) / 256, 148 * 16));
+    pack_nchw_to_split8_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W, Cpad, n_mod);
+  } else {
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    pack_nchw_to_split_kernel<<<blocks, 256, 0, s>>>(x, out, plane, N, C, H, W, Cpad, n_mod);
+  }
   MF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1070,6 +1105,97 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const HeadDesc h, const Sc
   }
 }
 
+// C == 256 (the canonical UNet head, unet2.py:213): a lane holds 8 consecutive channels of the pixel (one 16-byte load per
+// plane) and its 8 x 8 weights in registers; the 8 dot products are reduced over the warp by recursive halving (9 shuffles
+// instead of 40), after which lane 4*o (o = bit-reversed lane bits 4..2) holds output o.  The 4-byte-load kernel above
+// needed 81 us for the 67 MB activation of B = 64 (0.84 TB/s, profiles/r02_ncu_unet_step.md).
+__global__ void __launch_bounds__(256) head1x1_c256_kernel(const HeadDesc h, const SchedStepDesc sd) {
+  const int lane = threadIdx.x & 31;
+  float wr[8][8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[o][j] = (o < h.Cout) ? __ldg(h.w + o * 256 + lane * 8 + j) : 0.f;
+  }
+  const int my_o = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const bool writer = (lane & 3) == 0 && my_o < h.Cout;
+  const float my_bias = (writer && h.bias != nullptr) ? __ldg(h.bias + my_o) : 0.f;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long npix = static_cast<long long>(h.N) * h.HW;
+  // two slots per iteration, both requested before the first use: the two halves of a CFG pair (samples n and n + N), or
+  // two different pixels
+  const long long pstep = h.cfg_pair ? nwarps : 2 * nwarps;
+  for (long long pix = warp0; pix < npix; pix += pstep) {
+    float ysel[2] = {0.f, 0.f};
+    uint4 uh[2], ul[2];
+    long long spix[2];
+    bool live[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      spix[sl] = h.cfg_pair ? pix : pix + sl * nwarps;
+      live[sl] = spix[sl] < npix;                  // warp-uniform
+      const long long src = h.cfg_pair ? pix + static_cast<long long>(sl) * npix : (live[sl] ? spix[sl] : pix);
+      const __half* xh = h.in + src * 256 + lane * 8;
+      uh[sl] = *reinterpret_cast<const uint4*>(xh);
+      ul[sl] = *reinterpret_cast<const uint4*>(xh + h.in_plane);
+    }
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const __half2* hh = reinterpret_cast<const __half2*>(&uh[sl]);
+      const __half2* ll = reinterpret_cast<const __half2*>(&ul[sl]);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(hh[j]), b = __half22float2(ll[j]);
+        x[2 * j] = a.x + b.x; x[2 * j + 1] = a.y + b.y;
+      }
+      float acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        acc[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(x[j], wr[o][j], acc[o]);
+      }
+      float a4[4], a2[2];
+      const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float keep = b16 ? acc[4 + j] : acc[j], send = b16 ? acc[j] : acc[4 + j];
+        a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float keep = b8 ? a4[2 + j] : a4[j], send = b8 ? a4[j] : a4[2 + j];
+        a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      float a1 = (b4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b4 ? a2[0] : a2[1], 4);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      ysel[sl] = a1 + my_bias;
+    }
+    if (writer) {
+      // classifier-free guidance combine (diffusion_pipeline.py:244): pred_uncond + g * (pred_cond - pred_uncond)
+      if (h.cfg_pair) { ysel[0] = ysel[0] + h.cfg_guidance * (ysel[1] - ysel[0]); live[1] = false; }
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        if (!live[sl]) continue;
+        const float y = ysel[sl];
+        const long long px = spix[sl];
+        const int n = static_cast<int>(px / h.HW);
+        const long long i = (static_cast<long long>(n) * h.Cout + my_o) * h.HW + (px - static_cast<long long>(n) * h.HW);
+        if (h.out != nullptr) h.out[i] = y;
+        if (h.out_u8 != nullptr) {
+          const float c01 = fminf(fmaxf(y, -1.f), 1.f);
+          const float v255 = __fmul_rn(__fmul_rn(__fadd_rn(c01, 1.f), 0.5f), 255.f);
+          h.out_u8[px * h.Cout + my_o] = static_cast<unsigned char>(v255);
+        }
+        if (h.fuse_step) sched_element(sd, i, n, y);
+      }
+    }
+  }
+}
+
 int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s) {
   MF_REQUIRE(h.Cout >= 1 && h.Cout <= 8 && h.C % 64 == 0, "head1x1: Cout <= 8 and C % 64 == 0");
   MF_REQUIRE(!h.cfg_pair || (step != nullptr && step->pred_uncond == nullptr && h.out_u8 == nullptr),
@@ -1083,6 +1209,12 @@ int head1x1(const HeadDesc& h, const SchedStepDesc* step, cudaStream_t s) {
     sd = *step;
     hh.fuse_step = 1;
     MF_REQUIRE(sd.B == h.N && sd.CHW == h.Cout * h.HW, "fused scheduler step geometry must match the head output");
+  }
+  if (h.C == 256 && (reinterpret_cast<uintptr_t>(h.in) & 15) == 0 && h.in_plane % 8 == 0) {
+    const int blocks = static_cast<int>(std::min<long long>((npix + 7) / 8, 148 * 2));   // 2 x 8 warps per SM, persistent
+    head1x1_c256_kernel<<<blocks, 256, 0, s>>>(hh, sd);
+    MF_CUDA_OK(cudaGetLastError());
+    return 0;
   }
   const size_t smem = (static_cast<size_t>(h.Cout) * h.C + h.Cout) * sizeof(float);
   const int blocks = static_cast<int>(std::min<long long>((npix + 7) / 8, 148 * 8));

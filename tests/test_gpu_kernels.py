@@ -302,3 +302,71 @@ def test_conv_tc_heavy_tailed_operands_keep_fp32_parity(shape, profile, drain):
         assert worst <= 1.0, f"worst |err|/tol = {worst:.3f}"
     else:
         assert fwd <= 1.0, f"worst |err| / (tol + 2^-20 sum|x||w|) = {fwd:.3f}"
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 128, 128, 0, 128, 3), (1, 128, 128, 128, 128, 128, 3), (2, 256, 256, 64, 0, 64, 3),
+                                   (1, 256, 256, 128, 0, 64, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_row_patch_equals_per_tap_tiles(shape):
+    """Row-patch mode (mf_set_row_patch, the default for 3x3 layers tiled by image rows: the VAE's 128x128 / 256x256 levels):
+    the 130-pixel patch of an input row is staged once for its three taps and addressed by shifted descriptors.  Same
+    products as the per-tap tiles (equal up to the fp32 summation order of the stream-K split); and equal to the oracle.  Covers an
+    odd batch, the image borders (zero-filled halo) and a two-source (concat) K loop."""
+    from medfusion_b200 import _lib, ops
+    lib = _lib.load()
+    N, H, W, C0, C1, Cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    C = C0 + C1
+    x = _rnd(g, N, C, H, W)
+    w = _rnd(g, Cout, C, k, k, scale=1.0 / (C * k * k) ** 0.5)
+    b = _rnd(g, Cout, scale=0.1)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    s0 = ops.pack_split(xd[:, :C0].contiguous())
+    s1 = ops.pack_split(xd[:, C0:].contiguous()) if C1 else None
+    wp = ops.prep_weight_tc(wd)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.mf_set_row_patch(mode)
+            out, _ = ops.conv_tc(s0, wp, bd, k, src1=s1)
+            outs[mode] = ops.unpack_nchw(out).cpu()
+    finally:
+        lib.mf_set_row_patch(1)
+    assert_close(outs[1], ref, what=f"row-patch conv {shape}")
+    # same products; the stream-K unit boundaries (and with them the fp32 summation order) differ between the two plans
+    assert float((outs[0] - outs[1]).abs().max()) <= 4e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 8, 1024, 1024, 1024, 3), (4, 8, 8, 1024, 0, 1024, 3), (4, 32, 32, 256, 0, 256, 3),
+                                   (2, 16, 16, 512, 512, 512, 1), (1, 16, 16, 256, 0, 512, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_small_batch_fill_matches_unshared_tiles(shape):
+    """Small-batch fill (mf_set_split_fill): a layer with fewer tiles than half the SM pairs gets narrower tiles and / or
+    several CTA pairs per tile (partial tiles through the stream-K scratch, added by the owner in group order).  Against the
+    oracle, and against the one-pair-per-tile plan within fp32 re-association noise; run twice: the result is deterministic
+    and the flags are re-armed."""
+    from medfusion_b200 import _lib, ops
+    lib = _lib.load()
+    N, H, W, C0, C1, Cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    C = C0 + C1
+    x = _rnd(g, N, C, H, W)
+    w = _rnd(g, Cout, C, k, k, scale=1.0 / (C * k * k) ** 0.5)
+    b = _rnd(g, Cout, scale=0.1)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    s0 = ops.pack_split(xd[:, :C0].contiguous())
+    s1 = ops.pack_split(xd[:, C0:].contiguous()) if C1 else None
+    wp = ops.prep_weight_tc(wd)
+    outs = {}
+    try:
+        for mode in (0, 8, 4):
+            lib.mf_set_split_fill(mode)
+            a = ops.unpack_nchw(ops.conv_tc(s0, wp, bd, k, src1=s1, want_stats=True)[0]).cpu()
+            b2 = ops.unpack_nchw(ops.conv_tc(s0, wp, bd, k, src1=s1, want_stats=True)[0]).cpu()
+            assert torch.equal(a, b2), f"split_fill={mode}: not deterministic"
+            outs[mode] = a
+    finally:
+        lib.mf_set_split_fill(8)
+    for mode, o in outs.items():
+        assert_close(o, ref, what=f"conv {shape} split_fill={mode}")
+    assert float((outs[8] - outs[0]).abs().max()) <= 4e-6 * max(1.0, float(ref.abs().max()))
