@@ -207,26 +207,32 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
             cc = c - p.C0;
           }
           if (ROW3) {
-            // tap = input row offset (dy = tap - 1): one 130-pixel patch of that row, the weight tiles of its 3 taps
-            const int yr = tc.h0 + tap - 1, xr = tc.w0 - 1;
-            const int kw0 = (cb * 9 + tap * 3) * kTcBlockK;
+            // tap = input row (3x3: dy = tap - 1; folded upsample: row ty of the phase's 2x2 taps): one 130-pixel patch of that
+            // row, the weight tiles of the rt taps that read it (3, or 2 for a phase of the folded upsample)
+            const int rt = p.up2 ? 2 : 3;
+            const int yr = p.up2 ? (tc.h0 + oa - 1 + tap) : (tc.h0 + tap - 1);
+            const int xr = p.up2 ? (tc.w0 + ob - 1) : (tc.w0 - 1);
+            const int kw0 = (cb * (p.up2 ? 4 : 9) + tap * rt) * kTcBlockK;
+            const uint32_t tx_bytes = 2 * kTcPatchRows * 128 + 2 * rt * Cfg::kBBytes;
             uint8_t* bt = st + 2 * Cfg::kAPatchBytes;
             if (CG == 2) {
-              if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageTxBytes);
+              if (leader) mbar_expect_tx(&full_bar[s], 2 * tx_bytes);
               const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
               tma_load_5d_2sm(st, ma, fb, cc, xr, yr, tc.n0, 0);
               tma_load_5d_2sm(st + Cfg::kAPatchBytes, ma, fb, cc, xr, yr, tc.n0, 1);
 #pragma unroll
               for (int dxi = 0; dxi < 3; ++dxi) {
+                if (dxi >= rt) break;
                 tma_load_3d_2sm(bt + (2 * dxi) * Cfg::kBBytes, &maps.w, fb, kw0 + dxi * kTcBlockK, brow, 0);
                 tma_load_3d_2sm(bt + (2 * dxi + 1) * Cfg::kBBytes, &maps.w, fb, kw0 + dxi * kTcBlockK, brow, 1);
               }
             } else {
-              mbar_expect_tx(&full_bar[s], Cfg::kStageTxBytes);
+              mbar_expect_tx(&full_bar[s], tx_bytes);
               tma_load_5d(st, ma, &full_bar[s], cc, xr, yr, tc.n0, 0);
               tma_load_5d(st + Cfg::kAPatchBytes, ma, &full_bar[s], cc, xr, yr, tc.n0, 1);
 #pragma unroll
               for (int dxi = 0; dxi < 3; ++dxi) {
+                if (dxi >= rt) break;
                 tma_load_3d(bt + (2 * dxi) * Cfg::kBBytes, &maps.w, &full_bar[s], kw0 + dxi * kTcBlockK, brow, 0);
                 tma_load_3d(bt + (2 * dxi + 1) * Cfg::kBBytes, &maps.w, &full_bar[s], kw0 + dxi * kTcBlockK, brow, 1);
               }
@@ -276,6 +282,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
             if (ROW3) {
 #pragma unroll
               for (int dxi = 0; dxi < 3; ++dxi) {
+                if (dxi >= (p.up2 ? 2 : 3)) break;
                 // measured on B200: the 128-byte swizzle is a function of the ABSOLUTE shared-memory address bits, so a tile that
                 // starts dx rows into the TMA-written patch needs no descriptor base offset (with base offset = dx the results are wrong)
                 const uint64_t ra_hi = umma_smem_desc_sw128(st + dxi * 128);
@@ -1027,12 +1034,13 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   // 256x256 levels) and whose narrow tiles (N <= 128) make the activation re-reads the bottleneck.  A pipeline stage then
   // covers the three taps of one input row: ntaps = 3 "row taps", one TMEM partial per stage (= 3 K blocks, the default).
   plan->row3 = 0;
-  if (g_row_patch && d.ksize == 3 && stride == 1 && !d.up2 && p.bh == 1 && p.bw == kTcBlockM && p.bn == 1 && p.gn_mode == 0 &&
+  if (g_row_patch && d.ksize == 3 && stride == 1 && p.bh == 1 && p.bw == kTcBlockM && p.bn == 1 && p.gn_mode == 0 &&
       cg == 2 && (bn == 64 || bn == 128) && p.drain_interval >= 3 && 2LL * p.num_tiles > max_groups && g_stream_k) {
     plan->row3 = 1;
-    p.ntaps = 3;
-    set_partial_scale(3 * (p.drain_interval / 3));
-    p.drain_interval /= 3;
+    const int rt = d.up2 ? 2 : 3;             // taps per input row (a phase of the folded upsample has 2x2 taps)
+    p.ntaps = d.up2 ? 2 : 3;                  // K blocks are now (channel slab, input row)
+    set_partial_scale(rt * (p.drain_interval / rt));
+    p.drain_interval /= rt;
   }
   MF_REQUIRE(groups * cg <= sc.max_ctas || !g_stream_k, "stream-K grid exceeds the scratch allocation");
   plan->grid = dim3(groups * cg, 1, 1);

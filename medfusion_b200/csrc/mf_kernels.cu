@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(256) gn_apply_flat_kernel(const GnApplyDesc d)
 
 // fused variant (default): one block = a pixel range of ONE sample.
 //   prologue: the block reduces that sample's partial statistics to (mean, rstd) per group itself — same warp-per-group,
-//             lane-strided fp64 reduction as gn_finalize_kernel, so the numbers are bit-identical and the separate
+//             lane-strided fp64 reduction as gn_finalize_kernel (rstd by fp32 rsqrt + Newton: equal to ~1 ulp) and the separate
 //             finalize launch disappears;
 //   body:     a thread handles 8 consecutive channels of a pixel (two 16-byte loads, one 16-byte store per plane),
 //             two pixels in flight per iteration.
@@ -630,6 +630,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = cpg / 8, c8 = d.C / 8, items = d.chunks * sub;
+    const double inv_cnt = 1.0 / (static_cast<double>(cpg) * d.HW);
     for (int g = warp; g < d.G; g += 8) {
       double s = 0.0, ss = 0.0;
       for (int it = lane; it < items; it += 32) {
@@ -644,12 +645,17 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
         ss += __shfl_xor_sync(0xffffffffu, ss, off);
       }
       if (lane == 0) {
-        const double cnt = static_cast<double>(cpg) * d.HW;
-        const double mean = s / cnt;
-        double var = ss / cnt - mean * mean;
+        // fp64 only where the cancellation is (E[x^2] - mean^2); the reciprocal square root is fp32 rsqrt + one Newton
+        // step (<= 1 ulp): three fp64 divisions and an fp64 sqrt per group, in every block, were microseconds of
+        // dependent fp64 instructions in front of a 20-35 us kernel
+        const double mean = s * inv_cnt;
+        double var = fma(ss, inv_cnt, -mean * mean);
         if (var < 0.0) var = 0.0;
+        const float v32 = static_cast<float>(var + static_cast<double>(d.eps));
+        float r = rsqrtf(v32);
+        r = r * fmaf(-0.5f * v32, r * r, 1.5f);
         s_mean[g] = static_cast<float>(mean);
-        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(d.eps)));
+        s_rstd[g] = r;
       }
     }
     if (HC > 0) {
