@@ -478,28 +478,48 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
               v[4 * jj + 0] += b.x; v[4 * jj + 1] += b.y; v[4 * jj + 2] += b.z; v[4 * jj + 3] += b.w;
             }
           }
-          if (want_stats) {
+        }
+        if (want_stats) {
+          // V = 2 values (sum, sumsq) per 8-channel slab, SV slabs at a time; reduced over the warp's 32 rows by recursive
+          // halving (lane L ends up with value L >> (5 - log2 V) of the group): V + ... shuffles instead of 5 per value (the
+          // butterfly all-reduce cost 160 SHFL + 160 FADD per thread and tile at N = 256), same pairwise sums, same bits
+          constexpr int SV = CPW >= 64 ? 8 : 4;        // slabs per group
+          constexpr int V = 2 * SV;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+          for (int gp = 0; gp < CPW / (8 * SV); ++gp) {
+            float x[V];
+#pragma unroll
+            for (int g = 0; g < SV; ++g) {
               float s = 0.f, ss = 0.f;
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
-                const float x = v[8 * g + jj];
-                s += x;
-                ss = fmaf(x, x, ss);
+                const float xv = acc[(gp * SV + g) * 8 + jj];
+                s += xv;
+                ss = fmaf(xv, xv, ss);
               }
-              if (!valid) { s = 0.f; ss = 0.f; }
+              x[2 * g] = valid ? s : 0.f;
+              x[2 * g + 1] = valid ? ss : 0.f;
+            }
+            int nv = V;
 #pragma unroll
-              for (int off = 16; off > 0; off >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, off);
-                ss += __shfl_xor_sync(0xffffffffu, ss, off);
-              }
-              if (lane == 0) {
-                float* r = red + ((q * G8) + (col0 + ch * 32) / 8 + g) * 2;
-                r[0] = s;
-                r[1] = ss;
+            for (int off = 16; off > 0; off >>= 1) {
+              if (nv > 1) {
+                nv >>= 1;
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < V / 2; ++j) {
+                  if (j < nv) {
+                    const float keep = up ? x[nv + j] : x[j], send = up ? x[j] : x[nv + j];
+                    x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                  }
+                }
+              } else {
+                x[0] += __shfl_xor_sync(0xffffffffu, x[0], off);
               }
             }
+            constexpr int kShift = (V == 16) ? 1 : 2;       // lanes per value after the halving steps
+            if ((lane & ((1 << kShift) - 1)) == 0)
+              red[((q * G8) + (col0 + gp * SV * 8) / 8) * 2 + (lane >> kShift)] = x[0];
           }
         }
 

@@ -730,8 +730,10 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
             float acc = 0.f;
             acc = fmaf(y[0], w0.x, acc); acc = fmaf(y[1], w0.y, acc); acc = fmaf(y[2], w0.z, acc); acc = fmaf(y[3], w0.w, acc);
             acc = fmaf(y[4], w1.x, acc); acc = fmaf(y[5], w1.y, acc); acc = fmaf(y[6], w1.z, acc); acc = fmaf(y[7], w1.w, acc);
-            for (int sh = c8n >> 1; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-            if (live[u] && (threadIdx.x % c8n) == 0) {
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1)
+              if (sh < c8n) acc += __shfl_xor_sync(0xffffffffu, acc, sh);     // block-uniform predicate, no runtime loop
+            if (live[u] && c == 0) {                                          // c == 0: first of the pixel's C/8 lanes
               const int pix = pix0 + u * step + psub;
               const float v = acc + __ldg(d.head_b + o);
               if (d.head_out != nullptr) d.head_out[(static_cast<long long>(n) * d.head_cout + o) * d.HW + pix] = v;

@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]   # test_gpu_models imports the oracle
 
-CASES = ["vae_small_encode", "unet_attn_b3", "unet_canon_b5", "unet_small_b3", "unet_small_b1", "vae_small_b3", "vae_small_b3_u8", "pipe_b3_eager",
+CASES = ["vae_canon_b1", "vae_small_encode", "unet_attn_b3", "unet_canon_b5", "unet_small_b3", "unet_small_b1", "vae_small_b3", "vae_small_b3_u8", "pipe_b3_eager",
          "pipe_b3_graph", "pipe_b1_graph", "dataset"]
 
 
@@ -33,6 +33,13 @@ def run(name):
         m = make_unet(ga["cfg"], dev)
         x = torch.randn(3, 8, 32, 32, generator=gen).to(dev)
         y = m(x, torch.randint(0, 1000, (3,), generator=gen).to(dev), (torch.arange(3) % 2).to(dev))[0]
+        torch.cuda.synchronize()
+        print(name, float(y.abs().mean()))
+    elif name == "vae_canon_b1":
+        # canonical widths at 256x256: the row-patch mode of conv_tc (128x128 / 256x256 levels, folded up-conv phases)
+        import bench
+        m = make_vae(bench.VAE_CFG, dev)
+        y = m.decode(torch.randn(1, 8, 32, 32, generator=gen).to(dev))
         torch.cuda.synchronize()
         print(name, float(y.abs().mean()))
     elif name == "vae_small_encode":
