@@ -38,6 +38,8 @@ for k, n in names.items():
               "tflops": (sum(p[2] for p in sel) / max(1e-9, sum(p[0] for p in sel)) / 1e9) if k < 2 else None}
 slow = sorted(((p[0], i, p[1], p[2]) for i, p in enumerate(prof)), reverse=True)[:int(os.environ.get("TOP", "8"))]
 out["slowest"] = [dict(ms=round(a, 4), index=i, kind=names[k], gflop=round(f / 1e9, 1)) for a, i, k, f in slow]
+if os.environ.get("DUMP"):
+    out["launch_us"] = [[k, round(ms * 1e3, 1)] for ms, k, f in prof]
 print(json.dumps(out))
 v = make_vae(bench.VAE_CFG, dev)
 z = torch.randn(B, 8, LAT, LAT, device=dev)
