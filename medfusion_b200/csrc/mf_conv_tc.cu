@@ -361,6 +361,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
     const float pscale = p.partial_scale * __ldg(p.w_inv_scale);
     float* my_partial = p.sk_partials + static_cast<long long>(blockIdx.x) * (kTcBlockM * 256);
     int jc = 0;
+    bool clamped = false;                   // a split-plane output had to be clamped to +-65504 (reported once at the end)
     int gn_tiles = 0;                       // fused-GroupNorm epilogues done (exchange buffer / barrier phase)
     float2 own_slab = make_float2(0.f, 0.f);
 
@@ -725,7 +726,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
             for (int jj = 0; jj < 4; ++jj) {
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) split16x2(v[8 * jj + 2 * k2], v[8 * jj + 2 * k2 + 1], hi[k2], lo[k2]);
+              for (int k2 = 0; k2 < 4; ++k2) split16x2_flag(v[8 * jj + 2 * k2], v[8 * jj + 2 * k2 + 1], hi[k2], lo[k2], clamped);
               st_shared_v4(srow + ((jj ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
               st_shared_v4(srow + Cfg::kStagingHalf / 2 + ((jj ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
             }
@@ -742,6 +743,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvTcParams p) {
       }
       u += kb1 - kb0;
     }
+    sat16_report(clamped);                                // values beyond the fp16 range of the split planes (sticky counter)
     if ((q == 0) && (lane == 0)) tma_store_wait_all();   // bulk stores issued by this thread have been written
   }
 

@@ -631,20 +631,27 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = cpg / 8, c8 = d.C / 8, items = d.chunks * sub;
     const double inv_cnt = 1.0 / (static_cast<double>(cpg) * d.HW);
-    for (int g = warp; g < d.G; g += 8) {
+    // L lanes per group (the partial sums of a group are few: 8 at the UNet's 32x32 level), 32 / L groups per warp pass
+    int L = 1;
+    while (L < items && L < 32) L <<= 1;
+    const int gpp = 32 / L;
+    for (int g0 = warp * gpp; g0 < d.G; g0 += 8 * gpp) {
+      const int g = g0 + lane / L, it0 = lane % L;
       double s = 0.0, ss = 0.0;
-      for (int it = lane; it < items; it += 32) {
-        const int ch = it / sub, j = it % sub;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(
-            d.partial + ((static_cast<long long>(n) * d.chunks + ch) * c8 + g * sub + j) * 2));
-        s += static_cast<double>(v.x);
-        ss += static_cast<double>(v.y);
+      if (g < d.G) {
+        for (int it = it0; it < items; it += L) {
+          const int ch = it / sub, j = it % sub;
+          const float2 v = __ldg(reinterpret_cast<const float2*>(
+              d.partial + ((static_cast<long long>(n) * d.chunks + ch) * c8 + g * sub + j) * 2));
+          s += static_cast<double>(v.x);
+          ss += static_cast<double>(v.y);
+        }
       }
-      for (int off = 16; off > 0; off >>= 1) {
+      for (int off = L >> 1; off > 0; off >>= 1) {        // stays inside the group's L-lane segment
         s += __shfl_xor_sync(0xffffffffu, s, off);
         ss += __shfl_xor_sync(0xffffffffu, ss, off);
       }
-      if (lane == 0) {
+      if (it0 == 0 && g < d.G) {
         // fp64 only where the cancellation is (E[x^2] - mean^2); the reciprocal square root is fp32 rsqrt + one Newton
         // step (<= 1 ulp): three fp64 divisions and an fp64 sqrt per group, in every block, were microseconds of
         // dependent fp64 instructions in front of a 20-35 us kernel
