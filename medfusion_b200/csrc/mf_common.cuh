@@ -197,6 +197,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA prefetch of a 3-D box into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // TMA store (shared::cta -> global, tile mode), bulk-group completion.  The generic-proxy writes that filled the tile
 // must be made visible to the async proxy (fence_proxy_async by every writer, then a barrier) before the issue.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -569,11 +569,11 @@ __global__ void __launch_bounds__(256) gn_apply_flat_kernel(const GnApplyDesc d)
 }
 
 // fused variant (default): one block = a pixel range of ONE sample.
-//   prologue: the block reduces that sample's partial statistics to (mean, rstd) per group itself — same warp-per-group,
-//             lane-strided fp64 reduction as gn_finalize_kernel (rstd by fp32 rsqrt + Newton: equal to ~1 ulp) and the separate
-//             finalize launch disappears;
+//   prologue: the block reduces that sample's partial statistics to (mean, rstd) per group itself (fp64 sums, L lanes per
+//             group and 32 / L groups per warp pass; rstd by fp32 rsqrt + Newton: equal to gn_finalize_kernel's to ~1 ulp),
+//             so the separate finalize launch disappears;
 //   body:     a thread handles 8 consecutive channels of a pixel (two 16-byte loads, one 16-byte store per plane),
-//             two pixels in flight per iteration.
+//             2 (with a residual) or 4 pixels in flight per iteration.
 __device__ __forceinline__ void ld_raw8(const GnApplyDesc& d, long long off, float (&x)[8]) {
   if (d.raw_plane != 0) {
     const __half* xh = reinterpret_cast<const __half*>(d.raw) + off;
@@ -624,6 +624,15 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
   __shared__ float s_mean[128], s_rstd[128];
   __shared__ __align__(16) float s_hw[HC > 0 ? HC * 256 : 4];   // folded head weights [o][c] (C <= 256)
   pdl_launch_dependents();
+  // parameters (gamma, beta, head weights) do not depend on the previous kernel: requested before griddepcontrol.wait, so
+  // their latency overlaps the tail of the convolution that produces this kernel's input
+  const int c8n = d.C / 8;
+  const int c = (threadIdx.x % c8n) * 8;
+  const float4 ga0 = __ldg(reinterpret_cast<const float4*>(d.gamma + c)), ga1 = __ldg(reinterpret_cast<const float4*>(d.gamma + c + 4));
+  const float4 be0 = __ldg(reinterpret_cast<const float4*>(d.beta + c)), be1 = __ldg(reinterpret_cast<const float4*>(d.beta + c + 4));
+  if (HC > 0) {
+    for (int i = threadIdx.x; i < d.head_cout * d.C; i += 256) s_hw[(i / d.C) * 256 + i % d.C] = __ldg(d.head_w + i);
+  }
   pdl_wait();
   const int n = blockIdx.y;
   const int cpg = d.C / d.G;
@@ -665,23 +674,16 @@ __global__ void __launch_bounds__(256, 3) gn_apply_fused_kernel(const GnApplyDes
         s_rstd[g] = r;
       }
     }
-    if (HC > 0) {
-      for (int i = threadIdx.x; i < d.head_cout * d.C; i += 256) s_hw[(i / d.C) * 256 + i % d.C] = __ldg(d.head_w + i);
-    }
   }
   __syncthreads();
   // A thread keeps ONE channel octet for its whole life (256 % (C/8) == 0 is checked by the host): the affine
   // coefficients a = rstd*gamma, b = beta (+ embedding) stay in registers and the loop body is pure streaming.
-  const int c8n = d.C / 8;
   const int ppb = 256 / c8n;                                // pixels per block and sub-iteration
-  const int c = (threadIdx.x % c8n) * 8;
   const int psub = threadIdx.x / c8n;
   const int g = c / cpg;
   const float mean = s_mean[g], rstd = s_rstd[g];
   float ca[8], cb[8], ce[8];
   {
-    const float4 ga0 = __ldg(reinterpret_cast<const float4*>(d.gamma + c)), ga1 = __ldg(reinterpret_cast<const float4*>(d.gamma + c + 4));
-    const float4 be0 = __ldg(reinterpret_cast<const float4*>(d.beta + c)), be1 = __ldg(reinterpret_cast<const float4*>(d.beta + c + 4));
     const float ga[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
     const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
 #pragma unroll
@@ -781,14 +783,19 @@ static int gn_fused_launch(const GnApplyDesc& d, cudaLaunchConfig_t& cfg, int ma
     if (occ < 1) occ = 1;
   }
   const long long slots = static_cast<long long>(sms) * occ;
+  // cost of a grid in units of one loop iteration: waves x (prologue + iterations per block).  The prologue (statistics
+  // finalisation, coefficient loads) is worth ~3 iterations, so a small sample wants FEW, fat blocks in ONE wave (8x8 level of
+  // the UNet: 6 blocks per sample instead of 13: 18 -> 12 us per launch), a large one as many as fill whole waves.
+  const int upi = (RES ? 2 : 4) * (256 / (d.C / 8));
   int best = 1;
-  double best_eff = 0.0;
+  double best_cost = 1e30;
   for (int bps = 1; bps <= max_bps; ++bps) {
     const long long blocks = static_cast<long long>(d.N) * bps;
     const long long waves = (blocks + slots - 1) / slots;
     if (waves > 4 && bps > 1) break;
-    const double eff = static_cast<double>(blocks) / static_cast<double>(waves * slots);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = bps; }   // prefer fewer, longer-lived blocks at equal efficiency
+    const long long iters = (d.HW + static_cast<long long>(upi) * bps - 1) / (static_cast<long long>(upi) * bps);
+    const double cost = static_cast<double>(waves) * (3.0 + static_cast<double>(iters));
+    if (cost < best_cost * 0.98) { best_cost = cost; best = bps; }
   }
   cfg.gridDim = dim3(best, d.N, 1);
   MF_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply_fused_kernel<HC, RES>, d));
@@ -825,7 +832,6 @@ int gn_apply(const GnApplyDesc& d, cudaStream_t s) {
     MF_REQUIRE(d.C <= 256, "folded head: at most 256 channels");
     if (d.head_cout <= 4) return res ? gn_fused_launch<4, true>(d, cfg, max_bps) : gn_fused_launch<4, false>(d, cfg, max_bps);
     return res ? gn_fused_launch<8, true>(d, cfg, max_bps) : gn_fused_launch<8, false>(d, cfg, max_bps);
-    return 0;
   }
   MF_REQUIRE(d.head_cout == 0, "the folded head exists in the fused gn_apply variant only");
   const int c4n = d.C / 4;
