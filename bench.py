@@ -434,6 +434,14 @@ def main():
             tj = json.load(fh)
         traffic = tj.get("dram_bytes_per_launch_vae" if decode_only else "dram_bytes_per_launch")
         traffic_src = tj.get("source")
+        # the captures were taken at B = 64: the decoder's traffic is activations (linear in the batch), the estimator's
+        # is weights + activations (not linear), so other batch sizes report the scaled value / no value
+        if traffic is not None and B != 64:
+            if decode_only:
+                traffic = traffic * B / 64.0
+                traffic_src = f"{traffic_src}; captured at B=64, scaled linearly to B={B}"
+            else:
+                traffic, traffic_src = None, f"{traffic_src}; captured at B=64 only, not comparable at B={B}"
     except Exception:
         pass
     # kernels of this library per step: the estimator plan per timestep and pass (the scheduler update rides in the

@@ -25,6 +25,8 @@
  *
  * ABI version 2 (mf_abi_version): v1 + mf_vae_config.in_channels, mf_sched_step_opts, mf_vae_encode*, mf_set_pdl.
  * ABI version 3: v2 + mf_saturation_count, mf_vqvae_* (VQVAE.decode), mf_unet_forward_step2 (CFG as one 2B batch).
+ * Tuning knobs (mf_set_*) are not part of the versioned data-path ABI: later builds add knobs (mf_set_split_fill, mf_set_row_patch)
+ * without a version bump; a binding should resolve them optionally.
  */
 #ifndef MEDFUSION_B200_H_
 #define MEDFUSION_B200_H_
