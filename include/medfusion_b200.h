@@ -73,6 +73,12 @@ int mf_set_split_fill(int min_k_blocks);
  * (shifted shared-memory descriptors) instead of once per tap: a third of the L2 -> SM activation traffic.  0 = one
  * activation tile per tap everywhere.  Takes effect at the next plan build. */
 int mf_set_row_patch(int enable);
+/* Schedule the library would choose for a tensor-core convolution of this shape (INPUT geometry N x H x W, C0 (+ C1
+ * concatenated) -> Cout, ksize 1 | 3, stride 1 | 2, up2 = folded nearest-x2) on a device with `sm_count` SMs (<= 0: 148), under
+ * the current knobs.  Pure host arithmetic — no device is touched, so the planning heuristics are testable without a GPU.
+ * out8 = {supported, block_n, cta_group, CTA groups of the persistent grid, row-patch mode, output tiles, K blocks per tile,
+ * tile groups along M}. */
+int mf_op_conv_tc_plan(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride, int up2, int sm_count, int* out8);
 /* Relative correction applied to every drained TMEM partial sum, per K block of the drain interval, compensating the
  * round-toward-zero bias of the tcgen05 accumulator (0 disables, negative = built-in calibrated table, the default). */
 int mf_set_debias_eps(float eps_per_kblock);

@@ -70,6 +70,7 @@ SIGNATURES = {
     "mf_set_stream_k": (c_int, [c_int]),
     "mf_set_split_fill": (c_int, [c_int]),
     "mf_set_row_patch": (c_int, [c_int]),
+    "mf_op_conv_tc_plan": (c_int, [c_int] * 10 + [ctypes.POINTER(c_int)]),
     "mf_set_pdl": (c_int, [c_int]),
     "mf_set_fold_upsample": (c_int, [c_int]),
     "mf_set_stem_on_tc": (c_int, [c_int]),

@@ -634,6 +634,11 @@ int mf_set_split_fill(int min_k_blocks) {
   mf::g_split_fill = min_k_blocks;
   return 0;
 }
+int mf_op_conv_tc_plan(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride, int up2, int sm_count,
+                       int* out8) {
+  MF_REQUIRE(out8 != nullptr, "null argument");
+  return mf::conv_tc_plan_query(N, H, W, C0, C1, Cout, ksize, stride, up2, sm_count, out8);
+}
 int mf_set_row_patch(int enable) {
   mf::g_row_patch = enable ? 1 : 0;
   return 0;

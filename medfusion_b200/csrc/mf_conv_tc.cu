@@ -927,6 +927,99 @@ static int encode_out_map(CUtensorMap* m, void* base, int out_mode, long long pl
                     raw ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// Everything conv_tc_build decides about the SCHEDULE of a layer, as a pure function of the shape and the knobs (no device
+// access: exported as mf_op_conv_tc_plan so that the heuristics are testable without a GPU).
+//   m_tiles: 128-pixel tiles of the output; (bw, bh, bn_box): the pixel box of a tile; max_ctas: SMs of the device.
+int conv_tc_plan_shape(int m_tiles, int bw, int bh, int bn_box, int C0, int C1, int Cout, int ksize, int stride, int up2,
+                       int gn_mode, int forced_cg, int forced_bn, int drain_interval, int max_ctas, ConvTcShapePlan* out) {
+  int cg = forced_cg > 0 ? forced_cg : g_default_cta_group;
+  if (cg != 1 && cg != 2) cg = (m_tiles >= 2) ? 2 : 1;  // auto
+  if (gn_mode == 2) cg = 2;                             // a sample = the two tiles of one CTA pair
+  const int m_groups = (m_tiles + cg - 1) / cg;
+  const int phases = up2 ? 4 : 1;
+  const int ntaps = up2 ? 4 : ksize * ksize;
+  const int max_groups = std::max(1, max_ctas / cg);
+  const long long nkb = static_cast<long long>(ntaps) * ((C0 + C1) / kTcBlockK);
+  // persistent grid: one CTA group per SM (pair); stream-K splits the (tile, K block) units evenly over the groups.
+  // With stream-K off every tile gets its own group (classic one-tile-per-CTA launch).
+  // Small-batch fill: a layer with fewer tiles than HALF the SM pairs (scripts/sample.py runs B = 4..16: the 8x8 level has
+  // 4-16 tiles of 256 x 256 for 74 pairs) would leave most of the GPU idle while a few SMs stream the whole weight tensor.
+  // Two levers, chosen by a small cost model (microseconds; constants from profiles/r02_small_batch.md): narrower tiles
+  // (more of them, cheaper partial tiles, but a lower MMA rate: shared-memory-bound below N = 256) and sharing the K
+  // range of a tile between several groups (each keeps >= min_kb K blocks; the owner adds the helpers' partial tiles,
+  // which costs time per helper).  NOT done when the tiles fill at least half the pairs (B = 64): under the 1000 W cap the
+  // idle SMs' power budget holds the busy ones' clock (profiles/r01_conv_tc_feed_probe.md).
+  auto groups_for = [&](int bn_c, int min_kb) {
+    const long long tiles = static_cast<long long>(m_groups) * (Cout / bn_c) * phases;
+    long long g = std::min<long long>(tiles, max_groups);
+    if (min_kb > 0 && 2 * tiles <= max_groups)
+      g = std::min<long long>(max_groups, std::max<long long>(tiles, tiles * nkb / min_kb));
+    return static_cast<int>(g);
+  };
+  auto cost_us = [&](int bn_c, int groups_c) {
+    const long long tiles = static_cast<long long>(m_groups) * (Cout / bn_c) * phases;
+    const double t_kb = bn_c == 256 ? 1.32 : (bn_c == 128 ? 0.94 : 0.72);       // one 64-channel K block of a 256 x bn tile
+    const double per_group = std::ceil(static_cast<double>(tiles * nkb) / groups_c);
+    const double helpers = std::ceil(static_cast<double>(groups_c) / static_cast<double>(tiles)) - 1.0;
+    return per_group * t_kb + helpers * (0.5 + 1.5 * bn_c / 256.0) + (helpers > 0 ? 2.0 : 0.0);
+  };
+  int bn = forced_bn > 0 ? forced_bn : g_default_block_n;
+  const bool bn_auto = (bn != 64 && bn != 128 && bn != 256);
+  if (bn_auto) bn = 256;                                // auto: widest tile the channel count allows ...
+  if (gn_mode != 0) bn = 256;
+  while (Cout % bn) bn /= 2;
+  MF_REQUIRE(bn >= 8, "conv_tc: output channels must be a multiple of 64");
+  int groups = static_cast<int>(static_cast<long long>(m_groups) * (Cout / bn) * phases);
+  if (g_stream_k) {
+    groups = groups_for(bn, 0);
+    if (g_split_fill > 0 && gn_mode == 0) {
+      double best = cost_us(bn, groups);
+      const int bn_top = bn;
+      for (int bn_c = bn_top; bn_c >= 64; bn_c /= 2) {  // ... unless the layer cannot fill the GPU with it
+        if (Cout % bn_c || (!bn_auto && bn_c != bn_top)) continue;
+        if (2LL * m_groups * (Cout / bn_top) * phases > max_groups) break;   // enough tiles: keep the default plan
+        for (int min_kb : {g_split_fill * 4, g_split_fill * 2, g_split_fill}) {
+          const int g_c = groups_for(bn_c, min_kb);
+          const double c = cost_us(bn_c, g_c);
+          if (c < best * 0.97) { best = c; bn = bn_c; groups = g_c; }
+        }
+      }
+    }
+  }
+  out->cta_group = cg;
+  out->block_n = bn;
+  out->groups = groups;
+  out->m_groups = m_groups;
+  out->n_tiles = Cout / bn;
+  out->num_tiles = m_groups * out->n_tiles * phases;
+  out->nkb = static_cast<int>(nkb);
+  // Row-patch mode: 3x3 stride-1 layers whose tile is 128 pixels of one image row (W % 128 == 0: the VAE's 128x128 and
+  // 256x256 levels) and whose narrow tiles (N <= 128) make the activation re-reads the bottleneck.  A pipeline stage then
+  // covers the taps of one input row (3, or 2 for a phase of a folded up-conv), one TMEM partial per stage.
+  out->row3 = (g_row_patch && ksize == 3 && stride == 1 && bh == 1 && bw == kTcBlockM && bn_box == 1 && gn_mode == 0 && cg == 2 &&
+               (bn == 64 || bn == 128) && drain_interval >= 3 && 2LL * out->num_tiles > max_groups && g_stream_k) ? 1 : 0;
+  return 0;
+}
+
+// shape-only query behind mf_op_conv_tc_plan: out8 = {supported, block_n, cta_group, groups, row3, num_tiles, nkb, m_groups}
+int conv_tc_plan_query(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride, int up2, int sm_count, int* out8) {
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  stride = stride == 2 ? 2 : 1;
+  if (H % stride || W % stride) return 0;
+  const int Ho = H / stride, Wo = W / stride;
+  if (!conv_tc_supported(N, Ho, Wo, C0, C1, Cout, ksize, stride)) return 0;
+  int bw, bh, bnb;
+  if (!pick_box(Ho, Wo, &bw, &bh, &bnb)) return 0;
+  const int m_tiles = (Wo / bw) * (Ho / bh) * ((N + bnb - 1) / bnb);
+  ConvTcShapePlan sp;
+  const int rc = conv_tc_plan_shape(m_tiles, bw, bh, bnb, C0, C1, Cout, ksize, stride, up2, 0, 0, 0, g_default_drain_interval,
+                                    sm_count > 0 ? sm_count : 148, &sp);
+  if (rc) return rc;
+  out8[0] = 1; out8[1] = sp.block_n; out8[2] = sp.cta_group; out8[3] = sp.groups; out8[4] = sp.row3; out8[5] = sp.num_tiles;
+  out8[6] = sp.nkb; out8[7] = sp.m_groups;
+  return 0;
+}
+
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   const int stride = d.stride == 2 ? 2 : 1;
   MF_REQUIRE(!d.up2 || (stride == 1 && d.ksize == 3 && d.C1 == 0 && d.stats == nullptr),
@@ -1000,10 +1093,6 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   }
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  int cg = d.cta_group > 0 ? d.cta_group : g_default_cta_group;
-  if (cg != 1 && cg != 2) cg = (m_tiles >= 2) ? 2 : 1;  // auto
-  if (p.gn_mode == 2) cg = 2;                           // a sample = the two tiles of one CTA pair
-  plan->cta_group = cg;
   const StreamKScratch* scp = d.scratch;
   if (scp == nullptr) {
     int rcs = get_streamk_scratch(&scp);
@@ -1012,71 +1101,26 @@ int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan) {
   const StreamKScratch& sc = *scp;
   p.sk_partials = sc.partials;
   p.sk_flags = sc.flags;
-  // a CTA pair owns two consecutive M tiles; an odd tile count gets a padding tile (all loads out of range -> zeros,
-  // all stores masked)
-  p.m_groups = (m_tiles + cg - 1) / cg;
-  const int phases = d.up2 ? 4 : 1;
-  const int max_groups = std::max(1, sc.max_ctas / cg);
-  const long long nkb = static_cast<long long>(p.ntaps) * ((d.C0 + d.C1) / kTcBlockK);
-  // persistent grid: one CTA group per SM (pair); stream-K splits the (tile, K block) units evenly over the groups.
-  // With stream-K off every tile gets its own group (classic one-tile-per-CTA launch).
-  // Small-batch fill: a layer with fewer tiles than HALF the SM pairs (scripts/sample.py runs B = 4..16: the 8x8 level has
-  // 4-16 tiles of 256 x 256 for 74 pairs) would leave most of the GPU idle while a few SMs stream the whole weight tensor.
-  // Two levers, chosen by a small cost model (microseconds; constants from profiles/r02_small_batch.md): narrower tiles
-  // (more of them, cheaper partial tiles, but a lower MMA rate: shared-memory-bound below N = 256) and sharing the K
-  // range of a tile between several groups (each keeps >= min_kb K blocks; the owner adds the helpers' partial tiles,
-  // which costs time per helper).  NOT done when the tiles fill at least half the pairs (B = 64): under the 1000 W cap the
-  // idle SMs' power budget holds the busy ones' clock (profiles/r01_conv_tc_feed_probe.md).
-  auto groups_for = [&](int bn_c, int min_kb) {
-    const long long tiles = static_cast<long long>(p.m_groups) * (d.Cout / bn_c) * phases;
-    long long g = std::min<long long>(tiles, max_groups);
-    if (min_kb > 0 && 2 * tiles <= max_groups)
-      g = std::min<long long>(max_groups, std::max<long long>(tiles, tiles * nkb / min_kb));
-    return static_cast<int>(g);
-  };
-  auto cost_us = [&](int bn_c, int groups_c) {
-    const long long tiles = static_cast<long long>(p.m_groups) * (d.Cout / bn_c) * phases;
-    const double t_kb = bn_c == 256 ? 1.32 : (bn_c == 128 ? 0.94 : 0.72);       // one 64-channel K block of a 256 x bn tile
-    const double per_group = std::ceil(static_cast<double>(tiles * nkb) / groups_c);
-    const double helpers = std::ceil(static_cast<double>(groups_c) / static_cast<double>(tiles)) - 1.0;
-    return per_group * t_kb + helpers * (0.5 + 1.5 * bn_c / 256.0) + (helpers > 0 ? 2.0 : 0.0);
-  };
-  int bn = d.block_n > 0 ? d.block_n : g_default_block_n;
-  const bool bn_auto = (bn != 64 && bn != 128 && bn != 256);
-  if (bn_auto) bn = 256;                                // auto: widest tile the channel count allows ...
-  if (p.gn_mode != 0) bn = 256;
-  while (d.Cout % bn) bn /= 2;
-  int groups = static_cast<int>(static_cast<long long>(p.m_groups) * (d.Cout / bn) * phases);
-  if (g_stream_k) {
-    groups = groups_for(bn, 0);
-    if (g_split_fill > 0 && p.gn_mode == 0) {
-      double best = cost_us(bn, groups);
-      const int bn_top = bn;
-      for (int bn_c = bn_top; bn_c >= 64; bn_c /= 2) {  // ... unless the layer cannot fill the GPU with it
-        if (d.Cout % bn_c || (!bn_auto && bn_c != bn_top)) continue;
-        if (2LL * p.m_groups * (d.Cout / bn_top) * phases > max_groups) break;   // enough tiles: keep the default plan
-        for (int min_kb : {g_split_fill * 4, g_split_fill * 2, g_split_fill}) {
-          const int g_c = groups_for(bn_c, min_kb);
-          const double c = cost_us(bn_c, g_c);
-          if (c < best * 0.97) { best = c; bn = bn_c; groups = g_c; }
-        }
-      }
-    }
+  ConvTcShapePlan sp;
+  {
+    const int rcp = conv_tc_plan_shape(m_tiles, p.bw, p.bh, p.bn, d.C0, d.C1, d.Cout, d.ksize, stride, d.up2 ? 1 : 0, p.gn_mode,
+                                       d.cta_group, d.block_n, p.drain_interval, sc.max_ctas, &sp);
+    if (rcp) return rcp;
   }
+  const int cg = sp.cta_group, bn = sp.block_n, groups = sp.groups;
+  plan->cta_group = cg;
   MF_REQUIRE(p.gn_mode == 0 || bn % p.gn_cpg == 0, "fused GroupNorm: a tile must hold whole groups");
   MF_REQUIRE(p.gn_mode != 2 || m_tiles % 2 == 0, "fused GroupNorm (pair mode): even tile count");
   plan->block_n = bn;
-  p.n_tiles = d.Cout / bn;
-  p.num_tiles = p.m_groups * p.n_tiles * phases;
-  // Row-patch mode: 3x3 stride-1 layers whose tile is 128 pixels of one image row (W % 128 == 0: the VAE's 128x128 and
-  // 256x256 levels) and whose narrow tiles (N <= 128) make the activation re-reads the bottleneck.  A pipeline stage then
-  // covers the three taps of one input row: ntaps = 3 "row taps", one TMEM partial per stage (= 3 K blocks, the default).
-  plan->row3 = 0;
-  if (g_row_patch && d.ksize == 3 && stride == 1 && p.bh == 1 && p.bw == kTcBlockM && p.bn == 1 && p.gn_mode == 0 &&
-      cg == 2 && (bn == 64 || bn == 128) && p.drain_interval >= 3 && 2LL * p.num_tiles > max_groups && g_stream_k) {
-    plan->row3 = 1;
+  // a CTA pair owns two consecutive M tiles; an odd tile count gets a padding tile (all loads out of range -> zeros,
+  // all stores masked)
+  p.m_groups = sp.m_groups;
+  p.n_tiles = sp.n_tiles;
+  p.num_tiles = sp.num_tiles;
+  plan->row3 = sp.row3;
+  if (sp.row3) {
     const int rt = d.up2 ? 2 : 3;             // taps per input row (a phase of the folded upsample has 2x2 taps)
-    p.ntaps = d.up2 ? 2 : 3;                  // K blocks are now (channel slab, input row)
+    p.ntaps = rt;                             // K blocks are now (channel slab, input row)
     set_partial_scale(rt * (p.drain_interval / rt));
     p.drain_interval /= rt;
   }

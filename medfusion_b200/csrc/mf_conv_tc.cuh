@@ -139,6 +139,11 @@ int conv_tc_supported(int N, int H, int W, int C0, int C1, int Cout, int ksize, 
 // can GroupNorm(groups) + Swish + residual be applied inside the epilogue of this convolution (OUTPUT geometry H, W)?
 int conv_tc_gn_fusable(int H, int W, int Cout, int groups);
 extern int g_fuse_gn;   // 1: engines use the fused GroupNorm epilogue wherever conv_tc_gn_fusable() allows (default 0)
+struct ConvTcShapePlan { int cta_group, block_n, groups, row3, m_groups, n_tiles, num_tiles, nkb; };
+// the schedule of a layer as a pure function of its shape and the knobs (no device access)
+int conv_tc_plan_shape(int m_tiles, int bw, int bh, int bn_box, int C0, int C1, int Cout, int ksize, int stride, int up2,
+                       int gn_mode, int forced_cg, int forced_bn, int drain_interval, int max_ctas, ConvTcShapePlan* out);
+int conv_tc_plan_query(int N, int H, int W, int C0, int C1, int Cout, int ksize, int stride, int up2, int sm_count, int* out8);
 int conv_tc_build(const ConvTcDesc& d, ConvTcPlan* plan);
 // emb_dedup: the fused-GroupNorm embedding rows are deduplicated for this call (row = emb_index[n], or one shared row)
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream, int emb_dedup = 0, const long long* emb_index = nullptr);
