@@ -8,7 +8,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "medfusion_b200", "csrc", "libmedfusion_b200.so")
-PAT = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCATOMSWS", "USETMAXREG", "HMMA"]
+PAT = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTCBAR", "UTCATOMSWS", "USETMAXREG", "HMMA"]
 
 
 def main():
@@ -33,21 +33,23 @@ def main():
            "Counts of the SASS mnemonics that prove tcgen05 / TMEM / TMA (B200_PROFILING.md: `tcgen05.mma` -> `UTC*MMA`, `tcgen05.ld` ->",
            "`LDTM`, `cp.async.bulk.tensor` loads -> `UTMALDG`, stores -> `UTMASTG`, `tcgen05.commit` -> `UTCBAR`, `tcgen05.alloc` ->",
            "`UTCATOMSWS`, `setmaxnreg` -> `USETMAXREG`).  `HMMA` (legacy `mma.sync`) does not occur anywhere in the library.", "",
-           "| kernel | UTCHMMA (1-CTA) | UTCHMMA.2CTA | LDTM | UTMALDG | UTMASTG | UTCBAR | UTCATOMSWS | USETMAXREG | HMMA |",
-           "|---|---|---|---|---|---|---|---|---|---|"]
+           "| kernel | UTCHMMA (1-CTA) | UTCHMMA.2CTA | LDTM | UTMALDG | UTMASTG | UTMAPF | UTCBAR | UTCATOMSWS | USETMAXREG | HMMA |",
+           "|---|---|---|---|---|---|---|---|---|---|---|"]
     for (name, c), d in zip(rows, dem):
         if c["UTCHMMA"] + c["UTCHMMA.2CTA"] + c["UTMALDG"] + c["UTMASTG"] == 0:
             continue
         short = re.sub(r"\(.*", "", d).replace("void ", "")
-        out.append("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
-            short, c["UTCHMMA"], c["UTCHMMA.2CTA"], c["LDTM"], c["UTMALDG"], c["UTMASTG"], c["UTCBAR"], c["UTCATOMSWS"],
-            c["USETMAXREG"], c["HMMA"]))
-    out.append("| **whole library (%d kernels)** | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
-        len(rows), tot["UTCHMMA"], tot["UTCHMMA.2CTA"], tot["LDTM"], tot["UTMALDG"], tot["UTMASTG"], tot["UTCBAR"],
+        out.append("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
+            short, c["UTCHMMA"], c["UTCHMMA.2CTA"], c["LDTM"], c["UTMALDG"], c["UTMASTG"], c["UTMAPF"], c["UTCBAR"],
+            c["UTCATOMSWS"], c["USETMAXREG"], c["HMMA"]))
+    out.append("| **whole library (%d kernels)** | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
+        len(rows), tot["UTCHMMA"], tot["UTCHMMA.2CTA"], tot["LDTM"], tot["UTMALDG"], tot["UTMASTG"], tot["UTMAPF"], tot["UTCBAR"],
         tot["UTCATOMSWS"], tot["USETMAXREG"], tot["HMMA"]))
     out += ["", "New in round 2: `UTMASTG` — the convolution epilogue hands 16 KB staging tiles to the TMA store engine (one bulk tensor",
             "store per 32 channels x 128 pixels) instead of 32 row-strided `STG.128` per thread; the `<..., true>` instantiations carry",
-            "the fused GroupNorm epilogue (opt-in); attention kernels: see the rows of `mf::attn_*`.",
+            "the fused GroupNorm epilogue (opt-in), the `<64|128, 2, false, true>` ones the row-patch mode (one staged input-row patch for",
+            "three taps); `UTMAPF` = the weight tiles of a CTA's first pipeline stages prefetched into L2 before `griddepcontrol.wait`;",
+            "`attention_tc_kernel` issues its MMAs on operand tiles written by the threads (no TMA).",
             "Regenerate: `python tools/sass_summary.py`."]
     with open(os.path.join(ROOT, "profiles", "r02_sass_summary.md"), "w") as fh:
         fh.write("\n".join(out) + "\n")
